@@ -1,0 +1,69 @@
+"""Generate tests/golden/*.json from the compiled, unmodified reference (oracle/_ref).
+
+Run HERE (container with /root/reference):  make -C oracle && python tests/golden/make_golden.py
+The fixtures are what travels to the GPU box; nothing at test time reads /root/reference.
+All byte strings are the reference wire format (element_to_bytes), hex-encoded.
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref as R  # noqa: E402
+from pbc_b200.params import PARAMS  # noqa: E402
+
+SEED = 20260922
+N_SINGLE = {"a": 24, "f": 12, "d159": 16}
+PROD = {"a": (4, 3), "f": (3, 2), "d159": (4, 3)}  # (k, n_out)
+
+
+def chunks(b, n):
+    return [b[i:i + n].hex() for i in range(0, len(b), n)]
+
+
+def main():
+    for name, text in PARAMS.items():
+        rp = R.RefPairing(text)
+        R.RefPairing.seed(SEED)
+        n = N_SINGLE[name]
+        P = rp.random(R.G1, n)
+        Q = rp.random(R.G2, n)
+        E = rp.pairing(P, Q, n)
+        k, n_out = PROD[name]
+        PP = rp.random(R.G1, k * n_out)
+        QQ = rp.random(R.G2, k * n_out)
+        EP = rp.prod_pairing(PP, QQ, k, n_out)
+        # fixed-first-argument (pairing_pp_*) outputs: must equal plain pairings
+        EPP = rp.pp_pairing(P[:rp.g1_len], Q, 4)
+        # bilinearity material: P^a, Q^b, e^(ab)
+        a = rp.random(R.ZR, 4)
+        Pa = rp.pow_zn(R.G1, P[:4 * rp.g1_len], a, 4)
+        Ea = rp.pairing(Pa, Q[:4 * rp.g2_len], 4)
+        # off-curve inputs decode to O and pair to the GT identity
+        badP = bytes([P[0] ^ 1]) + P[1:rp.g1_len]
+        badQ = Q[:rp.g2_len - 1] + bytes([Q[rp.g2_len - 1] ^ 1])
+        e_badP = rp.pairing(badP, Q[:rp.g2_len], 1)
+        e_badQ = rp.pairing(P[:rp.g1_len], badQ, 1)
+        assert rp.is_identity(R.GT, e_badP) and rp.is_identity(R.GT, e_badQ)
+        doc = {
+            "source": "oracle/_ref/libpbcref.so (unmodified reference, commit cdf8e1b), "
+                      "pbc_random_set_deterministic(%d)" % SEED,
+            "param": name,
+            "lengths": {"g1": rp.g1_len, "g2": rp.g2_len, "gt": rp.gt_len, "zr": rp.zr_len},
+            "pairing": {"P": chunks(P, rp.g1_len), "Q": chunks(Q, rp.g2_len),
+                        "e": chunks(E, rp.gt_len)},
+            "prod": {"k": k, "P": chunks(PP, rp.g1_len), "Q": chunks(QQ, rp.g2_len),
+                     "e": chunks(EP, rp.gt_len)},
+            "pp": {"P": P[:rp.g1_len].hex(), "e": chunks(EPP, rp.gt_len)},
+            "pow": {"a": chunks(a, rp.zr_len), "Pa": chunks(Pa, rp.g1_len),
+                    "e_Pa_Q": chunks(Ea, rp.gt_len)},
+            "offcurve": {"badP": badP.hex(), "badQ": badQ.hex(), "identity": e_badP.hex()},
+        }
+        with open(os.path.join(ROOT, "tests", "golden", name + ".json"), "w") as f:
+            json.dump(doc, f, indent=0)
+        print(name, "ok")
+
+
+if __name__ == "__main__":
+    main()
