@@ -1,0 +1,114 @@
+/* pbc_b200.h -- C ABI of the B200 batched pairing engine (libpbc_b200.so).
+ *
+ * This is the drop-in boundary for the pairing hot path of the PBC library: each entry point
+ * below names the reference interface it stands in for (file:line under the reference tree).
+ * Plain pointers and sizes only.  All element buffers use the reference *wire format*, i.e. the
+ * bytes element_to_bytes() writes and element_from_bytes() reads (include/pbc_field.h:475-484):
+ *
+ *   type A  (param/a.param)     G1 128 B   G2 128 B   GT 128 B     x || y, 64-byte big-endian F_q
+ *   type F  (param/f.param)     G1  40 B   G2  80 B   GT 240 B     20-byte big-endian F_q
+ *   type D  (param/d159.param)  G1  40 B   G2 120 B   GT 120 B     20-byte big-endian F_q
+ *
+ * Semantics that are reproduced exactly:
+ *   - bytes that do not decode to a point on the curve are the point at infinity
+ *     (curve_from_bytes, ecc/curve.c:611-623);
+ *   - e(O, Q) = e(P, O) = 1 (pairing_apply, include/pbc_pairing.h:118-135); in a product of
+ *     pairings ANY infinite input makes the whole product 1 (element_prod_pairing, :153-171);
+ *   - every output is bit-identical to the reference CPU path.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Return convention: 0 on success, non-zero on failure (pairing_init_set_buf returns 1 on
+ * failure, ecc/pairing.c:88-98); pbc_b200_last_error() gives the message the reference would
+ * have sent to pbc_error().
+ */
+#ifndef PBC_B200_H
+#define PBC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pbc_b200_pairing_s pbc_b200_pairing_t;
+
+/* pairing_init_set_buf / pairing_init_set_str (ecc/pairing.c:88-102): parse "key value" parameter
+ * text (ecc/param.c:42-111), derive the field constants (arith/montfp.c:533-600,
+ * ecc/a_param.c:1431-1472, ecc/f_param.c:335-447, ecc/d_param.c:993-1095) and upload them.
+ * Types a, f, d (k = 6) are accepted.  Does not touch the GPU until the first compute call. */
+int pbc_b200_pairing_init_set_buf(pbc_b200_pairing_t **out, const char *param, size_t len);
+int pbc_b200_pairing_init_set_str(pbc_b200_pairing_t **out, const char *param);
+
+/* pairing_clear (include/pbc_pairing.h:109-116) */
+void pbc_b200_pairing_clear(pbc_b200_pairing_t *p);
+
+/* pairing_length_in_bytes_G1 / _G2 / _GT (include/pbc_pairing.h:200-250); type letter 'a','f','d' */
+int pbc_b200_pairing_length_in_bytes_G1(const pbc_b200_pairing_t *p);
+int pbc_b200_pairing_length_in_bytes_G2(const pbc_b200_pairing_t *p);
+int pbc_b200_pairing_length_in_bytes_GT(const pbc_b200_pairing_t *p);
+int pbc_b200_pairing_type(const pbc_b200_pairing_t *p);
+
+/* Batched element_pairing (include/pbc_pairing.h:141-145 -> pairing->map, ecc/a_param.c:1053,
+ * ecc/f_param.c:289, ecc/d_param.c:570):  out[i] = e(in1[i], in2[i]),  i < n.
+ * HOST buffers (pinned memory makes the copies asynchronous; pageable works).  The batch is cut
+ * into contiguous slices, one per configured device (pbc_b200_set_devices), each slice is
+ * streamed through its GPU in chunks; results land in `out` at the slice offset. */
+int pbc_b200_pairings_apply(pbc_b200_pairing_t *p, unsigned char *out, const unsigned char *in1,
+                            const unsigned char *in2, size_t n);
+
+/* Same with DEVICE buffers on the current CUDA device, enqueued on `stream` (a cudaStream_t
+ * passed as void*; NULL = default stream).  Asynchronous: returns after enqueueing.  Buffers
+ * must be 4-byte aligned.  The workspace grows to the largest n seen (512 B per pairing). */
+int pbc_b200_pairings_apply_device(pbc_b200_pairing_t *p, void *d_out, const void *d_in1,
+                                   const void *d_in2, size_t n, void *stream);
+
+/* Batched element_prod_pairing (include/pbc_pairing.h:153-171 -> pairing->prod_pairings,
+ * ecc/a_param.c:1283-1383, ecc/d_param.c:710-736, ecc/pairing.c:35-46 for type F):
+ *   out[i] = prod_{j<k} e(in1[i*k+j], in2[i*k+j]),  i < n_out.   One shared final
+ * exponentiation per output. */
+int pbc_b200_prod_pairings_apply(pbc_b200_pairing_t *p, unsigned char *out,
+                                 const unsigned char *in1, const unsigned char *in2, size_t k,
+                                 size_t n_out);
+int pbc_b200_prod_pairings_apply_device(pbc_b200_pairing_t *p, void *d_out, const void *d_in1,
+                                        const void *d_in2, size_t k, size_t n_out, void *stream);
+
+/* Batched pairing_pp_init + pairing_pp_apply (include/pbc_pairing.h:54-89,
+ * ecc/a_param.c:149-220,317-360): one fixed first argument, n second arguments.
+ *   out[i] = e(in1, in2[i]). */
+int pbc_b200_pp_pairings_apply(pbc_b200_pairing_t *p, unsigned char *out, const unsigned char *in1,
+                               const unsigned char *in2, size_t n);
+
+/* Multi-GPU fan-out for the host-buffer entry points: use devices [0, count).  count = 0 means
+ * every visible device.  Default is 1 (the current device). */
+int pbc_b200_set_devices(pbc_b200_pairing_t *p, int count);
+
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) so C callers can stage batches. */
+void *pbc_b200_host_alloc(size_t bytes);
+void pbc_b200_host_free(void *ptr);
+
+/* Number of kernels this library has launched since it was loaded (bench.py: gpu_launches). */
+uint64_t pbc_b200_kernel_launches(void);
+
+/* Message of the last failure on this thread (pbc_error text, misc/utils.c:79-101). */
+const char *pbc_b200_last_error(void);
+
+/* ---- integer-pipe roofline probes (bench.py) -------------------------------------
+ * All return elapsed milliseconds (CUDA events on the launching stream) or a negative value.
+ *   fpmul: every thread runs `iters` dependent Montgomery multiplications modulo this pairing's
+ *          base-field prime; mode 0 = operands in registers, 1 = through the shared-memory slot
+ *          machine the pairing kernels use.  muls = threads * iters.
+ *   imad : dependency-free IMAD.WIDE.U32 stream, 32 * iters instructions per thread. */
+double pbc_b200_bench_fpmul(pbc_b200_pairing_t *p, int mode, int blocks, int iters, int reps);
+double pbc_b200_bench_imad(int blocks, int threads, int iters, int reps);
+
+/* F_p differential-test hook (guru/fp_test.c, guru/checkfp.c analogue): out[i] = a[i] op b[i]
+ * in F_q on the device; operands and results are canonical big-endian F_q wire bytes.
+ * op: 0 = mul, 1 = add, 2 = sub, 3 = invert a (b ignored), 4 = halve a, 5 = neg a. */
+int pbc_b200_fp_op(pbc_b200_pairing_t *p, int op, unsigned char *out, const unsigned char *a,
+                   const unsigned char *b, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,524 @@
+// engine.cu -- host side of libpbc_b200.so: parameter parsing, constant derivation, device
+// contexts, chunked multi-stream / multi-GPU batch pipeline, and the C ABI of include/pbc_b200.h.
+//
+// Mirrors the *roles* of ecc/param.c (text -> symbol table), ecc/pairing.c:74-102
+// (pairing_init_set_buf -> init_pairing) and the per-type init_pairing functions, but shares no
+// code with them: constants are derived with host_bigint.hpp and the pairing itself only ever
+// runs on the GPU.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/pbc_b200.h"
+#include "common_kernels.cuh"
+#include "host_bigint.hpp"
+#include "pairing_a.cuh"
+
+using namespace pbcb200;
+
+// ------------------------------------------------------------------------------------------
+// errors (misc/utils.c:79-101 pbc_error -> here a thread-local message)
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define CUDA_OK(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+  } while (0)
+
+static std::atomic<uint64_t> g_launches{0};
+#define LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+// ------------------------------------------------------------------------------------------
+// parameter text (ecc/param.c:42-111): whitespace-separated "key value" tokens, '#' comments
+// ------------------------------------------------------------------------------------------
+static std::map<std::string, std::string> parse_param_text(const char* s, size_t len) {
+  std::map<std::string, std::string> tab;
+  std::vector<std::string> tok;
+  size_t i = 0;
+  while (i < len && s[i]) {
+    char c = s[i];
+    if (c == '#') { while (i < len && s[i] && s[i] != '\n') i++; continue; }
+    if (c == ' ' || c == '\t' || c == '\n' || c == '\r') { i++; continue; }
+    size_t j = i;
+    while (j < len && s[j] && s[j] != ' ' && s[j] != '\t' && s[j] != '\n' && s[j] != '\r' && s[j] != '#') j++;
+    tok.emplace_back(s + i, j - i);
+    i = j;
+  }
+  for (size_t k = 0; k + 1 < tok.size(); k += 2) tab[tok[k]] = tok[k + 1];
+  return tab;
+}
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct DevCtx {
+  int dev = -1;
+  bool ready = false;
+  cudaStream_t stream[2] = {nullptr, nullptr};
+  // host-API staging, per stream
+  uint8_t* d_in1[2] = {nullptr, nullptr};
+  uint8_t* d_in2[2] = {nullptr, nullptr};
+  uint8_t* d_out[2] = {nullptr, nullptr};
+  void* ws[2] = {nullptr, nullptr};
+  size_t cap[2] = {0, 0};      // pairings the staging/workspace of stream s can hold
+  // device-API workspace
+  void* ws_dev = nullptr;
+  size_t cap_dev = 0;
+};
+
+struct pbc_b200_pairing_s {
+  int type = 0;                // 'a', 'f', 'd'
+  int g1_len = 0, g2_len = 0, gt_len = 0;
+  int nlimbs = 0;
+  bool full = false;
+  FpConsts fp;
+  AConsts a;
+  int ndev = 1;
+  std::vector<DevCtx> ctx;     // indexed by device ordinal
+  std::mutex mu;
+  uint64_t id;
+};
+
+static std::atomic<uint64_t> g_next_id{1};
+static std::mutex g_const_mu;
+static std::map<int, uint64_t> g_const_owner;   // device -> handle id whose constants are resident
+
+static constexpr size_t kChunk = 1u << 18;      // pairings per pipeline chunk (host API)
+static constexpr int kBlockMiller = 128;
+static constexpr int kBlockFinal = 128;
+static constexpr int kBlockInv = 128;
+
+static size_t ws_bytes_per_pairing(const pbc_b200_pairing_s* p) {
+  if (p->type == 'a') return (size_t)(2 + 1 + 1 + 5) * 64;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// constant derivation
+// ------------------------------------------------------------------------------------------
+static void fill_fp_consts(FpConsts* c, const BigUInt& q, int nlimbs) {
+  memset(c, 0, sizeof *c);
+  BigUInt R = BigUInt(1).shl(32 * (size_t)nlimbs);
+  q.to_words(c->p, nlimbs);
+  (R % q).to_words(c->one, nlimbs);
+  ((R * R) % q).to_words(c->r2, nlimbs);
+  (q - BigUInt(2)).to_words(c->pm2, nlimbs);
+  c->np0 = neg_inv32(q.word(0));
+  c->nlimbs = (uint32_t)nlimbs;
+}
+
+static bool get_big(const std::map<std::string, std::string>& tab, const char* key, BigUInt* out) {
+  auto it = tab.find(key);
+  if (it == tab.end()) { fail("missing param: `%s'", key); return false; }   // ecc/param.c:134-140
+  if (!BigUInt::from_dec(it->second, out)) { fail("bad number for param `%s'", key); return false; }
+  return true;
+}
+static bool get_int(const std::map<std::string, std::string>& tab, const char* key, int* out) {
+  auto it = tab.find(key);
+  if (it == tab.end()) { fail("missing param: `%s'", key); return false; }
+  *out = atoi(it->second.c_str());
+  return true;
+}
+
+static int init_type_a(pbc_b200_pairing_s* p, const std::map<std::string, std::string>& tab) {
+  BigUInt q, r, h;
+  int exp2, exp1, sign1, sign0;
+  if (!get_big(tab, "q", &q) || !get_big(tab, "r", &r) || !get_big(tab, "h", &h)) return 1;
+  if (!get_int(tab, "exp2", &exp2) || !get_int(tab, "exp1", &exp1) ||
+      !get_int(tab, "sign1", &sign1) || !get_int(tab, "sign0", &sign0)) return 1;
+  if (q.bits() > 512 || q.bits() <= 480) return fail("type a: this build supports 481..512-bit q (got %zu)", q.bits());
+  if (q.word(0) % 4 != 3) return fail("type a: q must be 3 mod 4");
+  if (!((r * h) == (q + BigUInt(1)))) return fail("type a: r*h != q+1");
+  if (h.bits() > 384) return fail("type a: cofactor too large");
+  if (exp1 <= 0 || exp2 <= exp1) return fail("type a: bad exp1/exp2");
+  p->type = 'a';
+  p->nlimbs = kNA;
+  p->full = true;
+  p->g1_len = p->g2_len = p->gt_len = 128;
+  fill_fp_consts(&p->fp, q, kNA);
+  memset(&p->a, 0, sizeof p->a);
+  h.to_words(p->a.h, 12);
+  p->a.hbits = (uint32_t)h.bits();
+  p->a.exp2 = exp2; p->a.exp1 = exp1; p->a.sign1 = sign1;
+  BigUInt R = BigUInt(1).shl(512);
+  ((R * BigUInt(2)) % q).to_words(p->a.two, kNA);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// device contexts
+// ------------------------------------------------------------------------------------------
+template <class K>
+static cudaError_t allow_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+static constexpr size_t kSmemAMiller = (size_t)kASlots * 64 * kBlockMiller;
+static constexpr size_t kSmemAFinal = (size_t)kAFSlots * 64 * kBlockFinal;
+static constexpr size_t kSmemInv16 = (size_t)5 * 64 * kBlockInv;
+
+static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
+  if ((int)p->ctx.size() <= dev) p->ctx.resize(dev + 1);
+  DevCtx& c = p->ctx[dev];
+  CUDA_OK(cudaSetDevice(dev));
+  if (!c.ready) {
+    c.dev = dev;
+    for (int s = 0; s < 2; s++) CUDA_OK(cudaStreamCreateWithFlags(&c.stream[s], cudaStreamNonBlocking));
+    if (p->type == 'a') {
+      CUDA_OK(allow_smem(k_a_miller<kBlockMiller>, kSmemAMiller));
+      CUDA_OK(allow_smem(k_a_finalexp<kBlockFinal>, kSmemAFinal));
+      CUDA_OK(allow_smem(k_batch_invert<kNA, true, kBlockInv>, kSmemInv16));
+      CUDA_OK(allow_smem(k_fpmul_slots<kNA, true, 128>, 2 * 64 * 128));
+    }
+    c.ready = true;
+  }
+  // make this handle's constants resident on the device
+  std::lock_guard<std::mutex> lk(g_const_mu);
+  if (g_const_owner[dev] != p->id) {
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpyToSymbol(c_fp, &p->fp, sizeof(FpConsts)));
+    if (p->type == 'a') CUDA_OK(cudaMemcpyToSymbol(c_a, &p->a, sizeof(AConsts)));
+    CUDA_OK(cudaDeviceSynchronize());
+    g_const_owner[dev] = p->id;
+  }
+  return 0;
+}
+
+static void ctx_release(DevCtx& c) {
+  if (!c.ready) return;
+  cudaSetDevice(c.dev);
+  for (int s = 0; s < 2; s++) {
+    if (c.stream[s]) cudaStreamSynchronize(c.stream[s]);
+    cudaFree(c.d_in1[s]); cudaFree(c.d_in2[s]); cudaFree(c.d_out[s]); cudaFree(c.ws[s]);
+    if (c.stream[s]) cudaStreamDestroy(c.stream[s]);
+  }
+  cudaFree(c.ws_dev);
+  c = DevCtx();
+}
+
+// ------------------------------------------------------------------------------------------
+// enqueue one batch of n pairings, device buffers, on `st`.  ws: ws_bytes_per_pairing * n bytes.
+// ------------------------------------------------------------------------------------------
+static int enqueue_pairings(pbc_b200_pairing_s* p, uint8_t* d_out, const uint8_t* d_in1,
+                            const uint8_t* d_in2, size_t n, void* ws, cudaStream_t st) {
+  if (n == 0) return 0;
+  if (p->type == 'a') {
+    uint4* f = (uint4*)ws;                       // [2][4][n]
+    uint4* dprod = f + 8 * n;                    // [4][n]
+    uint4* prefix = dprod + 4 * n;               // [4][n]
+    uint4* save = prefix + 4 * n;                // [5][4][n]
+    unsigned gm = (unsigned)((n + kBlockMiller - 1) / kBlockMiller);
+    k_a_miller<kBlockMiller><<<gm, kBlockMiller, kSmemAMiller, st>>>(d_in1, d_in2, f, dprod, save, n);
+    LAUNCHED();
+    size_t T = n < (size_t)148 * 256 ? n : (size_t)148 * 256;
+    unsigned gi = (unsigned)((T + kBlockInv - 1) / kBlockInv);
+    k_batch_invert<kNA, true, kBlockInv><<<gi, kBlockInv, kSmemInv16, st>>>(dprod, prefix, n, T);
+    LAUNCHED();
+    unsigned gf = (unsigned)((n + kBlockFinal - 1) / kBlockFinal);
+    k_a_finalexp<kBlockFinal><<<gf, kBlockFinal, kSmemAFinal, st>>>(f, dprod, d_out, n);
+    LAUNCHED();
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  return fail("pairing type '%c' has no device path in this build", p->type);
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer pipeline for one device: slice [0, n) of this device, chunked over two streams
+// ------------------------------------------------------------------------------------------
+static int run_slice(pbc_b200_pairing_s* p, int dev, unsigned char* out, const unsigned char* in1,
+                     const unsigned char* in2, size_t n) {
+  if (ctx_prepare(p, dev)) return 1;
+  DevCtx& c = p->ctx[dev];
+  size_t chunk = n < kChunk ? n : kChunk;
+  size_t wsb = ws_bytes_per_pairing(p);
+  for (int s = 0; s < 2; s++) {
+    if (c.cap[s] < chunk) {
+      cudaFree(c.d_in1[s]); cudaFree(c.d_in2[s]); cudaFree(c.d_out[s]); cudaFree(c.ws[s]);
+      c.d_in1[s] = c.d_in2[s] = c.d_out[s] = nullptr; c.ws[s] = nullptr; c.cap[s] = 0;
+      CUDA_OK(cudaMalloc(&c.d_in1[s], chunk * p->g1_len));
+      CUDA_OK(cudaMalloc(&c.d_in2[s], chunk * p->g2_len));
+      CUDA_OK(cudaMalloc(&c.d_out[s], chunk * p->gt_len));
+      CUDA_OK(cudaMalloc(&c.ws[s], chunk * wsb));
+      c.cap[s] = chunk;
+    }
+    if (n <= chunk) break;   // a single chunk only ever uses stream 0
+  }
+  int k = 0;
+  for (size_t off = 0; off < n; off += chunk, k++) {
+    size_t m = n - off < chunk ? n - off : chunk;
+    int s = k & 1;
+    cudaStream_t st = c.stream[s];
+    CUDA_OK(cudaMemcpyAsync(c.d_in1[s], in1 + off * p->g1_len, m * p->g1_len, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(c.d_in2[s], in2 + off * p->g2_len, m * p->g2_len, cudaMemcpyHostToDevice, st));
+    if (enqueue_pairings(p, c.d_out[s], c.d_in1[s], c.d_in2[s], m, c.ws[s], st)) return 1;
+    CUDA_OK(cudaMemcpyAsync(out + off * p->gt_len, c.d_out[s], m * p->gt_len, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_OK(cudaStreamSynchronize(c.stream[0]));
+  CUDA_OK(cudaStreamSynchronize(c.stream[1]));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* pbc_b200_last_error(void) { return g_err; }
+uint64_t pbc_b200_kernel_launches(void) { return g_launches.load(); }
+
+int pbc_b200_pairing_init_set_buf(pbc_b200_pairing_t** out, const char* param, size_t len) {
+  if (!out || !param) return fail("null argument");
+  *out = nullptr;
+  auto tab = parse_param_text(param, len);
+  auto it = tab.find("type");
+  if (it == tab.end()) return fail("unknown pairing type");           // ecc/param.c:171-174
+  pbc_b200_pairing_s* p = new pbc_b200_pairing_s();
+  p->id = g_next_id.fetch_add(1);
+  int rc;
+  if (it->second == "a") rc = init_type_a(p, tab);
+  else rc = fail("pairing type `%s' is not on the B200 hot path (supported: a)", it->second.c_str());
+  if (rc) { delete p; return 1; }
+  *out = p;
+  return 0;
+}
+
+int pbc_b200_pairing_init_set_str(pbc_b200_pairing_t** out, const char* param) {
+  if (!param) return fail("null argument");
+  return pbc_b200_pairing_init_set_buf(out, param, strlen(param));
+}
+
+void pbc_b200_pairing_clear(pbc_b200_pairing_t* p) {
+  if (!p) return;
+  for (auto& c : p->ctx) ctx_release(c);
+  {
+    std::lock_guard<std::mutex> lk(g_const_mu);
+    for (auto& kv : g_const_owner) if (kv.second == p->id) kv.second = 0;
+  }
+  delete p;
+}
+
+int pbc_b200_pairing_length_in_bytes_G1(const pbc_b200_pairing_t* p) { return p->g1_len; }
+int pbc_b200_pairing_length_in_bytes_G2(const pbc_b200_pairing_t* p) { return p->g2_len; }
+int pbc_b200_pairing_length_in_bytes_GT(const pbc_b200_pairing_t* p) { return p->gt_len; }
+int pbc_b200_pairing_type(const pbc_b200_pairing_t* p) { return p->type; }
+
+int pbc_b200_set_devices(pbc_b200_pairing_t* p, int count) {
+  int have = 0;
+  CUDA_OK(cudaGetDeviceCount(&have));
+  if (have <= 0) return fail("no CUDA device");
+  if (count <= 0 || count > have) count = have;
+  p->ndev = count;
+  return 0;
+}
+
+int pbc_b200_pairings_apply(pbc_b200_pairing_t* p, unsigned char* out, const unsigned char* in1,
+                            const unsigned char* in2, size_t n) {
+  if (!p || (!out && n) || (!in1 && n) || (!in2 && n)) return fail("null argument");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(p->mu);
+  int cur = 0;
+  CUDA_OK(cudaGetDevice(&cur));
+  if (p->ndev <= 1) return run_slice(p, cur, out, in1, in2, n);
+  // contiguous slices, one host thread per device, results written at the slice offset
+  int nd = p->ndev;
+  std::vector<int> rc(nd, 0);
+  std::vector<std::string> msg(nd);
+  std::vector<std::thread> th;
+  size_t per = (n + nd - 1) / nd;
+  for (int d = 0; d < nd; d++) {
+    size_t lo = (size_t)d * per, hi = lo + per < n ? lo + per : n;
+    if (lo >= hi) continue;
+    th.emplace_back([=, &rc, &msg]() {
+      rc[d] = run_slice(p, d, out + lo * p->gt_len, in1 + lo * p->g1_len, in2 + lo * p->g2_len, hi - lo);
+      if (rc[d]) msg[d] = g_err;
+    });
+  }
+  for (auto& t : th) t.join();
+  cudaSetDevice(cur);
+  for (int d = 0; d < nd; d++) if (rc[d]) return fail("device %d: %s", d, msg[d].c_str());
+  return 0;
+}
+
+int pbc_b200_pairings_apply_device(pbc_b200_pairing_t* p, void* d_out, const void* d_in1,
+                                   const void* d_in2, size_t n, void* stream) {
+  if (!p) return fail("null argument");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(p->mu);
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  if (ctx_prepare(p, dev)) return 1;
+  DevCtx& c = p->ctx[dev];
+  if (c.cap_dev < n) {
+    CUDA_OK(cudaDeviceSynchronize());
+    cudaFree(c.ws_dev);
+    c.ws_dev = nullptr; c.cap_dev = 0;
+    CUDA_OK(cudaMalloc(&c.ws_dev, n * ws_bytes_per_pairing(p)));
+    c.cap_dev = n;
+  }
+  return enqueue_pairings(p, (uint8_t*)d_out, (const uint8_t*)d_in1, (const uint8_t*)d_in2, n,
+                          c.ws_dev, (cudaStream_t)stream);
+}
+
+int pbc_b200_prod_pairings_apply(pbc_b200_pairing_t*, unsigned char*, const unsigned char*,
+                                 const unsigned char*, size_t, size_t) {
+  return fail("prod_pairings: not built yet");
+}
+int pbc_b200_prod_pairings_apply_device(pbc_b200_pairing_t*, void*, const void*, const void*, size_t,
+                                        size_t, void*) {
+  return fail("prod_pairings: not built yet");
+}
+int pbc_b200_pp_pairings_apply(pbc_b200_pairing_t*, unsigned char*, const unsigned char*,
+                               const unsigned char*, size_t) {
+  return fail("pp_pairings: not built yet");
+}
+
+void* pbc_b200_host_alloc(size_t bytes) {
+  void* ptr = nullptr;
+  if (cudaHostAlloc(&ptr, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    fail("cudaHostAlloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  return ptr;
+}
+void pbc_b200_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+
+// ---- roofline probes ----
+double pbc_b200_bench_fpmul(pbc_b200_pairing_t* p, int mode, int blocks, int iters, int reps) {
+  if (!p) { fail("null argument"); return -1; }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || ctx_prepare(p, dev)) return -1;
+  const int threads = 128;
+  size_t T = (size_t)blocks * threads;
+  int N = p->nlimbs;
+  uint32_t *in = nullptr, *out = nullptr;
+  if (cudaMalloc(&in, T * 2 * N * 4) != cudaSuccess || cudaMalloc(&out, T * N * 4) != cudaSuccess) {
+    fail("cudaMalloc failed"); return -1;
+  }
+  // any residues below p will do: fill with a small pattern (top limb zero)
+  std::vector<uint32_t> h(T * 2 * N);
+  uint32_t s = 12345;
+  for (size_t i = 0; i < h.size(); i++) { s = s * 1664525u + 1013904223u; h[i] = s; }
+  for (size_t t = 0; t < T; t++) { h[(2 * (N - 1)) * T + t] = 0; h[(2 * (N - 1) + 1) * T + t] = 0; }
+  cudaMemcpy(in, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaStream_t st = p->ctx[dev].stream[0];
+  auto launch = [&]() {
+    if (p->type == 'a') {
+      if (mode == 0) k_fpmul_chain<kNA, true><<<blocks, threads, 0, st>>>(out, in, iters);
+      else k_fpmul_slots<kNA, true, 128><<<blocks, threads, 2 * 64 * 128, st>>>(out, in, iters);
+    }
+    LAUNCHED();
+  };
+  launch();
+  cudaStreamSynchronize(st);
+  cudaEventRecord(e0, st);
+  for (int r = 0; r < reps; r++) launch();
+  cudaEventRecord(e1, st);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaError_t err = cudaGetLastError();
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(in); cudaFree(out);
+  if (err != cudaSuccess) { fail("bench_fpmul: %s", cudaGetErrorString(err)); return -1; }
+  return ms / reps;
+}
+
+double pbc_b200_bench_imad(int blocks, int threads, int iters, int reps) {
+  uint64_t* out = nullptr;
+  if (cudaMalloc(&out, (size_t)blocks * threads * 8) != cudaSuccess) { fail("cudaMalloc failed"); return -1; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_imad_peak<<<blocks, threads>>>(out, 7, iters);
+  LAUNCHED();
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0);
+  for (int r = 0; r < reps; r++) { k_imad_peak<<<blocks, threads>>>(out, 7 + r, iters); LAUNCHED(); }
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaError_t err = cudaGetLastError();
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  if (err != cudaSuccess) { fail("bench_imad: %s", cudaGetErrorString(err)); return -1; }
+  return ms / reps;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// F_p differential-test hook
+// ------------------------------------------------------------------------------------------
+namespace pbcb200 {
+template <int N, bool FULL, int WB, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_fp_op(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+        size_t n) {
+  using O = Ops<N, FULL, BLOCK>;
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  uint32_t x[N], y[N], one[N] = {1};
+  limbs_from_be<N, WB>(x, a + idx * WB);
+  limbs_from_be<N, WB>(y, b + idx * WB);
+  mont_mul<N, FULL>(x, x, c_fp.r2);
+  mont_mul<N, FULL>(y, y, c_fp.r2);
+  O::st(0, x); O::st(1, y);
+  switch (op) {
+    case 0: O::mul(0, 0, 1); break;
+    case 1: O::add(0, 0, 1); break;
+    case 2: O::sub(0, 0, 1); break;
+    case 3: O::set_const(2, c_fp.one); slot_fermat_inverse<O, N>(3, 0, 2); O::copy(0, 3); break;
+    case 4: O::halve(0, 0); break;
+    case 5: O::neg(0, 0); break;
+  }
+  O::ld(x, 0);
+  mont_mul<N, FULL>(x, x, one);
+  limbs_to_be<N, WB>(out + idx * WB, x);
+}
+}  // namespace pbcb200
+
+extern "C" int pbc_b200_fp_op(pbc_b200_pairing_t* p, int op, unsigned char* out,
+                              const unsigned char* a, const unsigned char* b, size_t n) {
+  if (!p) return fail("null argument");
+  if (n == 0) return 0;
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  if (ctx_prepare(p, dev)) return 1;
+  int wb = p->type == 'a' ? 64 : 20;
+  uint8_t *da, *db, *dout;
+  CUDA_OK(cudaMalloc(&da, n * wb));
+  CUDA_OK(cudaMalloc(&db, n * wb));
+  CUDA_OK(cudaMalloc(&dout, n * wb));
+  CUDA_OK(cudaMemcpy(da, a, n * wb, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(db, b ? b : a, n * wb, cudaMemcpyHostToDevice));
+  unsigned g = (unsigned)((n + 127) / 128);
+  if (p->type == 'a') {
+    CUDA_OK(allow_smem(k_fp_op<kNA, true, 64, 128>, 4 * 64 * 128));
+    k_fp_op<kNA, true, 64, 128><<<g, 128, 4 * 64 * 128>>>(op, dout, da, db, n);
+  }
+  LAUNCHED();
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(out, dout, n * wb, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return 0;
+}

@@ -1,0 +1,245 @@
+// pairing_a.cuh -- Type A pairing kernels (y^2 = x^3 + x over F_q, k = 2, 512-bit q).
+//
+// Device replacement for ecc/a_param.c: a_pairing_proj (:1053-1198), a_miller_evalfn
+// (:306-315), compute_abc_tangent_proj (:86-112), compute_abc_line (:114-130), a_tateexp /
+// lucas_odd (:226-303), a_pairings_affine (:1283-1383).  Same values, different formulas:
+//   * the whole Miller loop is inversion-free.  The reference converts V to affine twice
+//     (point_to_affine, :1073-1080) and inverts f when sign1 < 0; here the chord through
+//     V = 2^exp2 P and V1 = +-2^exp1 P is evaluated on Jacobian coordinates scaled by
+//     Z^3 Z1^3 in F_q, and 1/f is replaced by conj(f) (they differ by the norm, in F_q).  Factors
+//     in F_q^* vanish under the (q-1) part of the final exponent, so the reduced pairing -- a
+//     canonical residue -- is bit-identical.
+//   * the final exponentiation needs 1/N(f) and 1/(f0 f1) only (lucas_odd's P^2-4 equals
+//     -4 in1^2 on the norm-1 torus); both come from ONE inversion of N f0 f1, and that inversion
+//     is batched across pairings with Montgomery's trick (batch_invert kernel).
+// Pipeline per batch:  k_a_miller -> k_batch_invert -> k_a_finalexp.
+#pragma once
+#include "slots.cuh"
+
+namespace pbcb200 {
+
+struct AConsts {
+  uint32_t h[12];       // cofactor (q+1)/r, little-endian words (Lucas exponent)
+  uint32_t hbits;
+  int32_t exp2, exp1, sign1;
+  uint32_t two[16];     // Montgomery 2
+};
+__constant__ AConsts c_a;
+
+constexpr int kNA = 16;        // 32-bit limbs of the 512-bit prime
+constexpr int kWA = 64;        // wire bytes per coordinate
+
+// slot map of the Miller kernel
+enum ASlot { aX, aY, aZ, aZ2, aF0, aF1, aQX, aQY, aT0, aT1, aT2, aT3, aT4, aT5, kASlots };
+
+// f *= (L0 + i L1), Karatsuba (arith/fieldquadratic.c:425-457 fi_mul), temporaries t0..t2
+template <class O>
+__device__ __forceinline__ void a_fmul(int f0, int f1, int l0, int l1, int t0, int t1, int t2) {
+  O::add(t0, f0, f1);
+  O::add(t1, l0, l1);
+  O::mul(t0, t0, t1);
+  O::mul(t1, f0, l0);
+  O::mul(t2, f1, l1);
+  O::sub(f0, t1, t2);
+  O::sub(t0, t0, t1);
+  O::sub(f1, t0, t2);
+}
+
+// Loads P and Q (wire format), converts to Montgomery form, validates y^2 = x^3 + x
+// (ecc/curve.c:57-76, :611-623: off-curve input becomes O).  Returns false for O.
+template <class O>
+__device__ __forceinline__ bool a_load_point(int sx, int sy, int st0, int st1, const uint8_t* p) {
+  uint32_t x[kNA];
+  limbs_from_be<kNA, kWA>(x, p);
+  mont_mul<kNA, true>(x, x, c_fp.r2);
+  O::st(sx, x);
+  limbs_from_be<kNA, kWA>(x, p + kWA);
+  mont_mul<kNA, true>(x, x, c_fp.r2);
+  O::st(sy, x);
+  O::sqr(st0, sx);
+  O::set_const(st1, c_fp.one);
+  O::add(st0, st0, st1);      // x^2 + 1
+  O::mul(st0, st0, sx);       // x^3 + x
+  O::sqr(st1, sy);
+  return O::eq(st0, st1);
+}
+
+// One Miller doubling step:  f <- f^2 * l_{V,V}(phi(Q)),  V <- 2V   (Jacobian, a = 1).
+// 13 multiplications + 6 squarings (reference: 23 multiplications, ecc/a_param.c:1082-1139).
+template <class O>
+__device__ __forceinline__ void a_double_step() {
+  // f = f^2  (arith/fieldquadratic.c:459-477)
+  O::add(aT0, aF0, aF1);
+  O::sub(aT1, aF0, aF1);
+  O::mul(aF1, aF0, aF1);
+  O::dbl(aF1, aF1);
+  O::mul(aF0, aT0, aT1);
+  // M = 3 X^2 + Z^4
+  O::sqr(aT0, aX);
+  O::sqr(aT1, aZ2);
+  O::dbl(aT2, aT0);
+  O::add(aT0, aT0, aT2);
+  O::add(aT0, aT0, aT1);
+  O::sqr(aT1, aY);                 // Y^2
+  O::mul(aT2, aX, aT1);
+  O::dbl(aT2, aT2, 2);             // S = 4 X Y^2
+  O::mul(aT3, aT0, aZ2);           // M Z^2
+  O::mul(aT4, aT3, aQX);
+  O::mul(aT5, aX, aT0);
+  O::sub(aT5, aT5, aT1);
+  O::sub(aT5, aT5, aT1);
+  O::add(aT4, aT4, aT5);           // Re l = X M - 2 Y^2 + M Z^2 Qx
+  O::mul(aZ, aY, aZ);
+  O::dbl(aZ, aZ);                  // Z' = 2 Y Z
+  O::mul(aT3, aZ, aZ2);
+  O::mul(aT3, aT3, aQY);           // Im l = Z' Z^2 Qy
+  O::sqr(aZ2, aZ);
+  O::sqr(aT5, aT0);
+  O::sub(aX, aT5, aT2);
+  O::sub(aX, aX, aT2);             // X' = M^2 - 2 S
+  O::sqr(aT1, aT1);
+  O::dbl(aT1, aT1, 3);             // 8 Y^4
+  O::sub(aT2, aT2, aX);
+  O::mulsub(aY, aT0, aT2, aT1);    // Y' = M (S - X') - 8 Y^4
+  a_fmul<O>(aF0, aF1, aT4, aT3, aT0, aT1, aT2);
+}
+
+// f: [2][4][n] uint4 (Montgomery F_q^2), dprod: [4][n] uint4 = N(f) f0 f1 (0 marks "output
+// identity"), save: [5][4][n] uint4 scratch for V1 and f1.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_a_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4* __restrict__ f,
+           uint4* __restrict__ dprod, uint4* __restrict__ save, size_t n) {
+  using O = Ops<kNA, true, BLOCK>;
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  bool live = idx < n;
+  size_t src = live ? idx : 0;
+  bool okP = a_load_point<O>(aX, aY, aT0, aT1, P + src * (2 * kWA));
+  bool okQ = a_load_point<O>(aQX, aQY, aT0, aT1, Q + src * (2 * kWA));
+  bool valid = okP && okQ;
+
+  O::set_const(aZ, c_fp.one);
+  O::set_const(aZ2, c_fp.one);
+  O::set_const(aF0, c_fp.one);
+  uint32_t zero[kNA] = {0};
+  O::st(aF1, zero);
+
+  const int exp1 = c_a.exp1, exp2 = c_a.exp2;
+  for (int i = 0; i < exp2; i++) {
+    if (i == exp1 && live) {
+      // V1 = +-V, f1 = f or conj(f) ~ 1/f   (ecc/a_param.c:1162-1169)
+      if (c_a.sign1 < 0) { O::neg(aT0, aY); O::neg(aT1, aF1); }
+      else               { O::copy(aT0, aY); O::copy(aT1, aF1); }
+      O::st_global(save, 0, n, idx, aX);
+      O::st_global(save, 1, n, idx, aT0);
+      O::st_global(save, 2, n, idx, aZ);
+      O::st_global(save, 3, n, idx, aF0);
+      O::st_global(save, 4, n, idx, aT1);
+    }
+    a_double_step<O>();
+  }
+  if (!live) return;
+
+  // f *= f1
+  O::ld_global(aT3, save, 3, n, idx);
+  O::ld_global(aT4, save, 4, n, idx);
+  a_fmul<O>(aF0, aF1, aT3, aT4, aT0, aT1, aT2);
+  // chord through V=(X,Y,Z) and V1=(X1,Y1,Z1), scaled by Z^3 Z1^3 (compute_abc_line :114-130):
+  //   a = Y Z1^3 - Y1 Z^3,  b = X1 Z1 Z^3 - X Z Z1^3,  c = X Z Y1 - Y X1 Z1
+  O::ld_global(aT0, save, 2, n, idx);          // Z1
+  O::mul(aT1, aZ2, aZ);                         // Z^3
+  O::sqr(aT2, aT0);
+  O::mul(aT2, aT2, aT0);                        // Z1^3
+  O::mul(aT3, aX, aZ);                          // X Z
+  O::ld_global(aT4, save, 0, n, idx);          // X1
+  O::mul(aT4, aT4, aT0);                        // X1 Z1
+  O::ld_global(aT0, save, 1, n, idx);          // Y1
+  O::mul(aZ, aT3, aT0);                         // X Z Y1
+  O::mul(aZ2, aY, aT4);                         // Y X1 Z1
+  O::sub(aZ, aZ, aZ2);                          // c
+  O::mul(aT4, aT4, aT1);                        // X1 Z1 Z^3
+  O::mul(aT3, aT3, aT2);                        // X Z Z1^3
+  O::sub(aT4, aT4, aT3);                        // b
+  O::mul(aT2, aY, aT2);                         // Y Z1^3
+  O::mul(aT1, aT0, aT1);                        // Y1 Z^3
+  O::sub(aT2, aT2, aT1);                        // a
+  O::mul(aT2, aT2, aQX);
+  O::sub(aT2, aZ, aT2);                         // Re l = c - a Qx
+  O::mul(aT4, aT4, aQY);                        // Im l = b Qy
+  a_fmul<O>(aF0, aF1, aT2, aT4, aT0, aT1, aT3);
+
+  // D = (f0^2 + f1^2) f0 f1;  invalid inputs publish D = 0 (-> identity)
+  O::sqr(aT0, aF0);
+  O::sqr(aT1, aF1);
+  O::add(aT0, aT0, aT1);
+  O::mul(aT1, aF0, aF1);
+  O::mul(aT0, aT0, aT1);
+  if (!valid) O::st(aT0, zero);
+  O::st_global(f, 0, n, idx, aF0);
+  O::st_global(f, 1, n, idx, aF1);
+  O::st_global(dprod, 0, n, idx, aT0);
+}
+
+// slot map of the final-exponentiation kernel
+enum AFSlot { fF0, fF1, fD, fN, fP, fV0, fV1, fT0, fTWO, kAFSlots };
+
+// out: n * 128 bytes, wire format of F_q^2 (arith/fieldquadratic.c:323-329: x || y).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_a_finalexp(const uint4* __restrict__ f, const uint4* __restrict__ dinv, uint8_t* __restrict__ out,
+             size_t n) {
+  using O = Ops<kNA, true, BLOCK>;
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  O::ld_global(fF0, f, 0, n, idx);
+  O::ld_global(fF1, f, 1, n, idx);
+  O::ld_global(fD, dinv, 0, n, idx);
+  bool identity = O::is_zero(fD);
+  O::set_const(fTWO, c_a.two);
+  // N = f0^2 + f1^2, W = f0 f1;  1/N = Dinv W;  P = 2 (f0^2 - f1^2) / N
+  O::sqr(fV0, fF0);
+  O::sqr(fV1, fF1);
+  O::add(fN, fV0, fV1);
+  O::sub(fP, fV0, fV1);
+  O::dbl(fP, fP);
+  O::mul(fT0, fF0, fF1);
+  O::mul(fT0, fT0, fD);
+  O::mul(fP, fP, fT0);
+  // Lucas ladder, lucas_odd (ecc/a_param.c:226-262): V_0 = 2, V_1 = P
+  O::copy(fV0, fTWO);
+  O::copy(fV1, fP);
+  for (int j = (int)c_a.hbits - 1; j >= 0; j--) {
+    bool bit = j > 0 && ((c_a.h[j >> 5] >> (j & 31)) & 1u);   // last step takes the clear branch
+    int d = bit ? fV0 : fV1, s = bit ? fV1 : fV0;
+    O::mulsub(d, fV0, fV1, fP);
+    O::mulsub(s, s, s, fTWO);
+  }
+  // out0 = V_h / 2;  out1 = (2 V_{h+1} - P V_h) N^2 Dinv / 8
+  O::dbl(fV1, fV1);
+  O::mul(fT0, fP, fV0);
+  O::sub(fV1, fV1, fT0);
+  O::sqr(fN, fN);
+  O::mul(fN, fN, fD);
+  O::mul(fV1, fV1, fN);
+  O::halve(fV1, fV1, 3);
+  O::halve(fV0, fV0);
+
+  uint32_t x[kNA], one[kNA] = {1};
+  uint8_t* o = out + idx * (2 * kWA);
+  O::ld(x, fV0);
+  mont_mul<kNA, true>(x, x, one);           // leave Montgomery form (arith/montfp.c:64-80)
+  if (identity) {
+#pragma unroll
+    for (int k = 0; k < kNA; k++) x[k] = one[k];
+  }
+  limbs_to_be<kNA, kWA>(o, x);
+  O::ld(x, fV1);
+  mont_mul<kNA, true>(x, x, one);
+  if (identity) {
+#pragma unroll
+    for (int k = 0; k < kNA; k++) x[k] = 0;
+  }
+  limbs_to_be<kNA, kWA>(o + kWA, x);
+}
+
+}  // namespace pbcb200

@@ -1,0 +1,139 @@
+"""Host-side mirror of the reference pairing interface, batched.
+
+Names follow the reference (include/pbc_pairing.h): a `Pairing` is a pairing_t initialised from
+parameter text (pairing_init_set_str); `apply` is element_pairing over a batch;
+`prod_apply` is element_prod_pairing; `pp_apply` is pairing_pp_init + pairing_pp_apply.
+Elements travel as reference wire-format bytes (element_to_bytes / element_from_bytes).
+All arithmetic happens in libpbc_b200.so on the GPU; this file only marshals buffers.
+"""
+from __future__ import annotations
+import ctypes as C
+
+from ._lib import lib, last_error
+
+
+class PairingError(RuntimeError):
+    pass
+
+
+def _addr(buf):
+    """address of a host buffer: int, bytes, ctypes buffer, numpy array or torch tensor"""
+    if buf is None:
+        return None
+    if isinstance(buf, int):
+        return buf
+    if hasattr(buf, "data_ptr"):          # torch tensor
+        return buf.data_ptr()
+    if hasattr(buf, "ctypes"):            # numpy array
+        return buf.ctypes.data
+    if isinstance(buf, bytes):
+        return C.cast(C.c_char_p(buf), C.c_void_p).value
+    if isinstance(buf, bytearray):
+        return C.addressof((C.c_char * len(buf)).from_buffer(buf))
+    return C.addressof(buf)
+
+
+class Pairing:
+    def __init__(self, param_text):
+        """pairing_init_set_str (ecc/pairing.c:100-102); raises where the reference returns 1."""
+        self._h = C.c_void_p()
+        b = param_text.encode() if isinstance(param_text, str) else bytes(param_text)
+        if lib.pbc_b200_pairing_init_set_buf(C.byref(self._h), b, len(b)):
+            self._h = C.c_void_p()
+            raise PairingError(last_error())
+        self.g1_len = lib.pbc_b200_pairing_length_in_bytes_G1(self._h)
+        self.g2_len = lib.pbc_b200_pairing_length_in_bytes_G2(self._h)
+        self.gt_len = lib.pbc_b200_pairing_length_in_bytes_GT(self._h)
+        self.type = chr(lib.pbc_b200_pairing_type(self._h))
+
+    def clear(self):
+        """pairing_clear"""
+        if getattr(self, "_h", None):
+            lib.pbc_b200_pairing_clear(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.clear()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_devices(self, count: int):
+        if lib.pbc_b200_set_devices(self._h, count):
+            raise PairingError(last_error())
+
+    # -- element_pairing over a batch -------------------------------------------------------
+    def apply(self, in1: bytes, in2: bytes, n=None) -> bytes:
+        if n is None:
+            n = len(in1) // self.g1_len
+        if len(in1) < n * self.g1_len or len(in2) < n * self.g2_len:
+            raise ValueError("input buffers shorter than n elements")
+        out = C.create_string_buffer(max(1, n * self.gt_len))
+        if lib.pbc_b200_pairings_apply(self._h, C.addressof(out), _addr(in1), _addr(in2), n):
+            raise PairingError(last_error())
+        return out.raw[:n * self.gt_len]
+
+    def apply_into(self, out, in1, in2, n: int):
+        """Host buffers given by address-bearing objects (pinned torch tensors, numpy arrays)."""
+        if lib.pbc_b200_pairings_apply(self._h, _addr(out), _addr(in1), _addr(in2), n):
+            raise PairingError(last_error())
+
+    def apply_device(self, d_out: int, d_in1: int, d_in2: int, n: int, stream: int = 0):
+        """Device pointers (e.g. torch.Tensor.data_ptr()), asynchronous on `stream`."""
+        if lib.pbc_b200_pairings_apply_device(self._h, d_out, d_in1, d_in2, n, stream):
+            raise PairingError(last_error())
+
+    # -- element_prod_pairing -----------------------------------------------------------------
+    def prod_apply(self, in1: bytes, in2: bytes, k: int, n_out=None) -> bytes:
+        if n_out is None:
+            n_out = len(in1) // (self.g1_len * k)
+        out = C.create_string_buffer(max(1, n_out * self.gt_len))
+        if lib.pbc_b200_prod_pairings_apply(self._h, C.addressof(out), _addr(in1), _addr(in2), k, n_out):
+            raise PairingError(last_error())
+        return out.raw[:n_out * self.gt_len]
+
+    def prod_apply_device(self, d_out, d_in1, d_in2, k, n_out, stream=0):
+        if lib.pbc_b200_prod_pairings_apply_device(self._h, d_out, d_in1, d_in2, k, n_out, stream):
+            raise PairingError(last_error())
+
+    # -- pairing_pp_init / pairing_pp_apply -------------------------------------------------------
+    def pp_apply(self, in1: bytes, in2: bytes, n=None) -> bytes:
+        if n is None:
+            n = len(in2) // self.g2_len
+        out = C.create_string_buffer(max(1, n * self.gt_len))
+        if lib.pbc_b200_pp_pairings_apply(self._h, C.addressof(out), _addr(in1), _addr(in2), n):
+            raise PairingError(last_error())
+        return out.raw[:n * self.gt_len]
+
+    # -- test / bench hooks -----------------------------------------------------------------------
+    def fp_op(self, op: int, a: bytes, b, n: int) -> bytes:
+        wb = 64 if self.type == "a" else 20
+        out = C.create_string_buffer(n * wb)
+        if lib.pbc_b200_fp_op(self._h, op, C.addressof(out), _addr(a), _addr(b), n):
+            raise PairingError(last_error())
+        return out.raw
+
+    def bench_fpmul(self, mode: int, blocks: int, iters: int, reps: int) -> float:
+        ms = lib.pbc_b200_bench_fpmul(self._h, mode, blocks, iters, reps)
+        if ms < 0:
+            raise PairingError(last_error())
+        return ms
+
+
+def pairing_init_set_str(param_text) -> Pairing:
+    return Pairing(param_text)
+
+
+def kernel_launches() -> int:
+    return int(lib.pbc_b200_kernel_launches())
+
+
+def bench_imad(blocks: int, threads: int, iters: int, reps: int) -> float:
+    ms = lib.pbc_b200_bench_imad(blocks, threads, iters, reps)
+    if ms < 0:
+        raise PairingError(last_error())
+    return ms
