@@ -96,15 +96,25 @@ const char *pbc_b200_last_error(void);
 /* ---- integer-pipe roofline probes (bench.py) -------------------------------------
  * All return elapsed milliseconds (CUDA events on the launching stream) or a negative value.
  *   fpmul: every thread runs `iters` dependent Montgomery multiplications modulo this pairing's
- *          base-field prime; mode 0 = operands in registers, 1 = through the shared-memory slot
- *          machine the pairing kernels use.  muls = threads * iters.
- *   imad : dependency-free IMAD.WIDE.U32 stream, 32 * iters instructions per thread. */
+ *          base-field prime; mode 0 = operand-scanning multiplier in registers, 1 = the multiplier
+ *          the kernels use, through the shared-memory slot machine, 2 = product-scanning
+ *          multiplier in registers, 3 = product-scanning squaring in registers.  muls = threads * iters.
+ *   imad : IMAD.WIDE.U32 issue-rate probe, 32 * iters instructions per thread (four independent
+ *          carry chains of eight, data-dependent multiplicands). */
 double pbc_b200_bench_fpmul(pbc_b200_pairing_t *p, int mode, int blocks, int iters, int reps);
 double pbc_b200_bench_imad(int blocks, int threads, int iters, int reps);
 
+/* Per-stage device timing of the device-buffer path (bench.py roofline): when enabled,
+ * pbc_b200_pairings_apply_device records CUDA events on the launching stream around its three
+ * kernels; after synchronising, pbc_b200_stage_times returns their durations in milliseconds
+ * {main kernel (Miller loop), batch inversion, final exponentiation}. */
+int pbc_b200_set_stage_profiling(pbc_b200_pairing_t *p, int on);
+int pbc_b200_stage_times(pbc_b200_pairing_t *p, float *ms3);
+
 /* F_p differential-test hook (guru/fp_test.c, guru/checkfp.c analogue): out[i] = a[i] op b[i]
  * in F_q on the device; operands and results are canonical big-endian F_q wire bytes.
- * op: 0 = mul, 1 = add, 2 = sub, 3 = invert a (b ignored), 4 = halve a, 5 = neg a. */
+ * op: 0 = mul, 1 = add, 2 = sub, 3 = invert a (b ignored), 4 = halve a, 5 = neg a,
+ * 6 = square a, 7 = a*b - b. */
 int pbc_b200_fp_op(pbc_b200_pairing_t *p, int op, unsigned char *out, const unsigned char *a,
                    const unsigned char *b, size_t n);
 

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpbc_b200.so")
+LIB_PATH = os.environ.get("PBC_B200_LIB") or os.path.join(_HERE, "libpbc_b200.so")  # env: A/B builds only
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -41,6 +41,8 @@ lib.pbc_b200_bench_fpmul.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int]
 lib.pbc_b200_bench_fpmul.restype = C.c_double
 lib.pbc_b200_bench_imad.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
 lib.pbc_b200_bench_imad.restype = C.c_double
+lib.pbc_b200_set_stage_profiling.argtypes = [_P, C.c_int]
+lib.pbc_b200_stage_times.argtypes = [_P, C.POINTER(C.c_float)]
 lib.pbc_b200_fp_op.argtypes = [_P, C.c_int, _P, _P, _P, C.c_size_t]
 
 

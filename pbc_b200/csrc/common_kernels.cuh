@@ -54,14 +54,18 @@ k_batch_invert(void* __restrict__ d, void* __restrict__ prefix, size_t n, size_t
 
 // ---- micro-kernels for the integer-pipe roofline --------------------------------------------
 // Dependent chain of `iters` Montgomery multiplications per thread, operands in registers.
-template <int N, bool FULL>
+template <int N, bool FULL, int IMPL>
 __global__ void k_fpmul_chain(uint32_t* __restrict__ out, const uint32_t* __restrict__ in,
                               int iters) {
   size_t T = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t a[N], b[N];
 #pragma unroll
   for (int k = 0; k < N; k++) { a[k] = in[(2 * k) * T + t]; b[k] = in[(2 * k + 1) * T + t]; }
-  for (int i = 0; i < iters; i++) mont_mul<N, FULL>(a, a, b);
+  for (int i = 0; i < iters; i++) {
+    if (IMPL == 0) mont_mul<N, FULL>(a, a, b);
+    else if (IMPL == 1) mont_mul_ps<N, FULL>(a, a, b);
+    else mont_sqr_ps<N, FULL>(a, a);
+  }
 #pragma unroll
   for (int k = 0; k < N; k++) out[k * T + t] = a[k];
 }
@@ -82,25 +86,35 @@ k_fpmul_slots(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, int i
   for (int k = 0; k < N; k++) out[k * T + t] = a[k];
 }
 
-// Dependency-free IMAD.WIDE.U32 stream: 8 independent 64-bit accumulators per thread.
-// Measures the issue-rate ceiling that bounds every kernel above ("measure peak
-// IMAD/s with a dependency-free microkernel").
+// IMAD.WIDE.U32 issue-rate probe: four independent carry chains of eight IMAD.WIDE.U32(.X) per
+// thread and step -- the instruction the multipliers above are made of (32 per step).  The
+// multiplicand of every link is data dependent, so nothing can be hoisted or strength-reduced
+// (a first version with loop-invariant operands was folded into 64-bit adds by ptxas and
+// over-reported the ceiling by 2x).  SURVEY 8d: "measure peak IMAD/s with a dependency-free
+// microkernel" -- this is that denominator.
 __global__ void k_imad_peak(uint64_t* __restrict__ out, uint32_t seed, int iters) {
-  uint32_t x = seed + threadIdx.x, y = seed * 3u + blockIdx.x;
-  uint64_t acc[8];
+  uint32_t y = seed * 3u + blockIdx.x + threadIdx.x;
+  uint32_t a[4][16];
 #pragma unroll
-  for (int k = 0; k < 8; k++) acc[k] = k;
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[c][k] = seed + 16 * c + k;
   for (int i = 0; i < iters; i++) {
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int c = 0; c < 4; c++) {
+      asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
+                   : "+r"(a[c][0]), "+r"(a[c][1]) : "r"(a[c][15]), "r"(y));
 #pragma unroll
-      for (int k = 0; k < 8; k++)
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(x + k), "r"(y));
+      for (int k = 2; k < 16; k += 2)
+        asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
+                     : "+r"(a[c][k]), "+r"(a[c][k + 1]) : "r"(a[c][k - 1]), "r"(y));
     }
   }
-  uint64_t s = 0;
+  uint32_t s = 0;
 #pragma unroll
-  for (int k = 0; k < 8; k++) s ^= acc[k];
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int k = 0; k < 16; k++) s ^= a[c][k];
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 

@@ -81,6 +81,8 @@ struct DevCtx {
   // device-API workspace
   void* ws_dev = nullptr;
   size_t cap_dev = 0;
+  // optional per-stage timing of the device-API path (bench.py roofline)
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 struct pbc_b200_pairing_s {
@@ -91,6 +93,7 @@ struct pbc_b200_pairing_s {
   FpConsts fp;
   AConsts a;
   int ndev = 1;
+  bool profile = false;        // record CUDA events between the kernels of the device-API path
   std::vector<DevCtx> ctx;     // indexed by device ordinal
   std::mutex mu;
   uint64_t id;
@@ -210,6 +213,7 @@ static void ctx_release(DevCtx& c) {
     if (c.stream[s]) cudaStreamDestroy(c.stream[s]);
   }
   cudaFree(c.ws_dev);
+  for (int i = 0; i < 4; i++) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
   c = DevCtx();
 }
 
@@ -217,23 +221,29 @@ static void ctx_release(DevCtx& c) {
 // enqueue one batch of n pairings, device buffers, on `st`.  ws: ws_bytes_per_pairing * n bytes.
 // ------------------------------------------------------------------------------------------
 static int enqueue_pairings(pbc_b200_pairing_s* p, uint8_t* d_out, const uint8_t* d_in1,
-                            const uint8_t* d_in2, size_t n, void* ws, cudaStream_t st) {
+                            const uint8_t* d_in2, size_t n, void* ws, cudaStream_t st,
+                            cudaEvent_t* ev = nullptr) {
   if (n == 0) return 0;
+#define STAGE(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
   if (p->type == 'a') {
     uint4* f = (uint4*)ws;                       // [2][4][n]
     uint4* dprod = f + 8 * n;                    // [4][n]
     uint4* prefix = dprod + 4 * n;               // [4][n]
     uint4* save = prefix + 4 * n;                // [5][4][n]
     unsigned gm = (unsigned)((n + kBlockMiller - 1) / kBlockMiller);
+    STAGE(0);
     k_a_miller<kBlockMiller><<<gm, kBlockMiller, kSmemAMiller, st>>>(d_in1, d_in2, f, dprod, save, n);
     LAUNCHED();
+    STAGE(1);
     size_t T = n < (size_t)148 * 256 ? n : (size_t)148 * 256;
     unsigned gi = (unsigned)((T + kBlockInv - 1) / kBlockInv);
     k_batch_invert<kNA, true, kBlockInv><<<gi, kBlockInv, kSmemInv16, st>>>(dprod, prefix, n, T);
     LAUNCHED();
+    STAGE(2);
     unsigned gf = (unsigned)((n + kBlockFinal - 1) / kBlockFinal);
     k_a_finalexp<kBlockFinal><<<gf, kBlockFinal, kSmemAFinal, st>>>(f, dprod, d_out, n);
     LAUNCHED();
+    STAGE(3);
     CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -373,8 +383,27 @@ int pbc_b200_pairings_apply_device(pbc_b200_pairing_t* p, void* d_out, const voi
     CUDA_OK(cudaMalloc(&c.ws_dev, n * ws_bytes_per_pairing(p)));
     c.cap_dev = n;
   }
+  if (p->profile && !c.ev[0])
+    for (int i = 0; i < 4; i++) CUDA_OK(cudaEventCreate(&c.ev[i]));
   return enqueue_pairings(p, (uint8_t*)d_out, (const uint8_t*)d_in1, (const uint8_t*)d_in2, n,
-                          c.ws_dev, (cudaStream_t)stream);
+                          c.ws_dev, (cudaStream_t)stream, p->profile ? c.ev : nullptr);
+}
+
+int pbc_b200_set_stage_profiling(pbc_b200_pairing_t* p, int on) {
+  if (!p) return fail("null argument");
+  p->profile = on != 0;
+  return 0;
+}
+
+/* milliseconds of the three stages (main kernel, batch inversion, final exponentiation) of the
+ * LAST pbc_b200_pairings_apply_device call on the current device; caller must have synchronised. */
+int pbc_b200_stage_times(pbc_b200_pairing_t* p, float* ms3) {
+  if (!p || !ms3) return fail("null argument");
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  if ((int)p->ctx.size() <= dev || !p->ctx[dev].ev[0]) return fail("stage profiling was not enabled");
+  for (int i = 0; i < 3; i++) CUDA_OK(cudaEventElapsedTime(&ms3[i], p->ctx[dev].ev[i], p->ctx[dev].ev[i + 1]));
+  return 0;
 }
 
 int pbc_b200_prod_pairings_apply(pbc_b200_pairing_t*, unsigned char*, const unsigned char*,
@@ -423,7 +452,9 @@ double pbc_b200_bench_fpmul(pbc_b200_pairing_t* p, int mode, int blocks, int ite
   cudaStream_t st = p->ctx[dev].stream[0];
   auto launch = [&]() {
     if (p->type == 'a') {
-      if (mode == 0) k_fpmul_chain<kNA, true><<<blocks, threads, 0, st>>>(out, in, iters);
+      if (mode == 0) k_fpmul_chain<kNA, true, 0><<<blocks, threads, 0, st>>>(out, in, iters);
+      else if (mode == 2) k_fpmul_chain<kNA, true, 1><<<blocks, threads, 0, st>>>(out, in, iters);
+      else if (mode == 3) k_fpmul_chain<kNA, true, 2><<<blocks, threads, 0, st>>>(out, in, iters);
       else k_fpmul_slots<kNA, true, 128><<<blocks, threads, 2 * 64 * 128, st>>>(out, in, iters);
     }
     LAUNCHED();
@@ -490,6 +521,8 @@ k_fp_op(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a, const 
     case 3: O::set_const(2, c_fp.one); slot_fermat_inverse<O, N>(3, 0, 2); O::copy(0, 3); break;
     case 4: O::halve(0, 0); break;
     case 5: O::neg(0, 0); break;
+    case 6: O::sqr(0, 0); break;
+    case 7: O::mulsub(0, 0, 1, 1); break;
   }
   O::ld(x, 0);
   mont_mul<N, FULL>(x, x, one);

@@ -161,6 +161,128 @@ __device__ __forceinline__ void mont_mul(uint32_t* r, const uint32_t* a, const u
 }
 
 // ---------------------------------------------------------------------------------------------
+// Product-scanning (column-wise) variant.  Every 32x32 product is one IMAD.WIDE.U32 with
+// carry-OUT only (no carry-in: the .X form issues at half rate on sm_100a, measured), the carry
+// is absorbed by an IADD3.X on the ALU pipe, so the FMA and ALU pipes alternate.  Two
+// independent 96-bit accumulators (a*b and m*p) per column keep two dependency chains in flight.
+// ---------------------------------------------------------------------------------------------
+#define PBC_MAC3(t0, t1, t2, x, y)                                                           \
+  PBC_ASM("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, %2, 0;" \
+          : "+r"(t0), "+r"(t1), "+r"(t2) : "r"(x), "r"(y))
+
+template <int N, bool FULL>
+__device__ __forceinline__ void mont_mul_ps(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint32_t m[N], t[N];
+  uint32_t u0 = 0, u1 = 0, u2 = 0, v0 = 0, v1 = 0, v2 = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+#pragma unroll
+    for (int j = 0; j < i; j++) {
+      PBC_MAC3(u0, u1, u2, a[j], b[i - j]);
+      PBC_MAC3(v0, v1, v2, m[j], c_fp.p[i - j]);
+    }
+    PBC_MAC3(u0, u1, u2, a[i], b[0]);
+    // v += u
+    PBC_ASM("add.cc.u32 %0, %0, %3; addc.cc.u32 %1, %1, %4; addc.u32 %2, %2, %5;"
+            : "+r"(v0), "+r"(v1), "+r"(v2) : "r"(u0), "r"(u1), "r"(u2));
+    m[i] = v0 * c_fp.np0;
+    PBC_MAC3(v0, v1, v2, m[i], c_fp.p[0]);   // v0 == 0 now
+    v0 = v1; v1 = v2; v2 = 0;
+    u0 = 0; u1 = 0; u2 = 0;
+  }
+#pragma unroll
+  for (int i = N; i < 2 * N - 1; i++) {
+#pragma unroll
+    for (int j = i - N + 1; j < N; j++) {
+      PBC_MAC3(u0, u1, u2, a[j], b[i - j]);
+      PBC_MAC3(v0, v1, v2, m[j], c_fp.p[i - j]);
+    }
+    PBC_ASM("add.cc.u32 %0, %0, %3; addc.cc.u32 %1, %1, %4; addc.u32 %2, %2, %5;"
+            : "+r"(v0), "+r"(v1), "+r"(v2) : "r"(u0), "r"(u1), "r"(u2));
+    t[i - N] = v0;
+    v0 = v1; v1 = v2; v2 = 0;
+    u0 = 0; u1 = 0; u2 = 0;
+  }
+  t[N - 1] = v0;
+  uint32_t top = v1;
+  uint32_t d[N], borrow;
+  PBC_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(d[0]) : "r"(t[0]), "r"(c_fp.p[0]));
+#pragma unroll
+  for (int k = 1; k < N; k++)
+    PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(d[k]) : "r"(t[k]), "r"(c_fp.p[k]));
+  PBC_ASM("subc.u32 %0, 0, 0;" : "=r"(borrow));
+  bool use_d = FULL ? (top != 0 || borrow == 0) : (borrow == 0);
+#pragma unroll
+  for (int k = 0; k < N; k++) r[k] = use_d ? d[k] : t[k];
+}
+
+// Squaring, product scanning: cross products a_j a_{i-j} (j < i-j) are accumulated once and
+// doubled, the diagonal a_{i/2}^2 is added after.  N(N+1)/2 + N^2 products instead of 2 N^2.
+template <int N, bool FULL>
+__device__ __forceinline__ void mont_sqr_ps(uint32_t* r, const uint32_t* a) {
+  uint32_t m[N], t[N];
+  uint32_t u0 = 0, u1 = 0, u2 = 0, v0 = 0, v1 = 0, v2 = 0;
+#pragma unroll
+  for (int i = 0; i < 2 * N - 1; i++) {
+    const int lo = i < N ? 0 : i - N + 1;
+#pragma unroll
+    for (int j = lo; 2 * j < i; j++) PBC_MAC3(u0, u1, u2, a[j], a[i - j]);
+#pragma unroll
+    for (int j = lo; j <= (i < N ? i - 1 : N - 1); j++) PBC_MAC3(v0, v1, v2, m[j], c_fp.p[i - j]);
+    // u = 2u (+ a_{i/2}^2), v += u
+    PBC_ASM("add.cc.u32 %0, %0, %0; addc.cc.u32 %1, %1, %1; addc.u32 %2, %2, %2;"
+            : "+r"(u0), "+r"(u1), "+r"(u2));
+    if ((i & 1) == 0) PBC_MAC3(u0, u1, u2, a[i / 2], a[i / 2]);
+    PBC_ASM("add.cc.u32 %0, %0, %3; addc.cc.u32 %1, %1, %4; addc.u32 %2, %2, %5;"
+            : "+r"(v0), "+r"(v1), "+r"(v2) : "r"(u0), "r"(u1), "r"(u2));
+    if (i < N) {
+      m[i] = v0 * c_fp.np0;
+      PBC_MAC3(v0, v1, v2, m[i], c_fp.p[0]);
+    } else {
+      t[i - N] = v0;
+    }
+    v0 = v1; v1 = v2; v2 = 0;
+    u0 = 0; u1 = 0; u2 = 0;
+  }
+  t[N - 1] = v0;
+  uint32_t top = v1;
+  uint32_t d[N], borrow;
+  PBC_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(d[0]) : "r"(t[0]), "r"(c_fp.p[0]));
+#pragma unroll
+  for (int k = 1; k < N; k++)
+    PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(d[k]) : "r"(t[k]), "r"(c_fp.p[k]));
+  PBC_ASM("subc.u32 %0, 0, 0;" : "=r"(borrow));
+  bool use_d = FULL ? (top != 0 || borrow == 0) : (borrow == 0);
+#pragma unroll
+  for (int k = 0; k < N; k++) r[k] = use_d ? d[k] : t[k];
+}
+
+// The multiplier the kernels use.  Measured on B200 (profiles/r1_ubench.jsonl): IMAD.WIDE.U32
+// issues at 32/clk/SM with or without carries, so the two multipliers execute the same number of
+// multiplier-pipe slots; operand scanning has ~25% fewer ALU instructions and wins for a*b, product
+// scanning wins for a^2 (408 instead of 528 IMAD.WIDE).  PBC_MULT_IMPL: 2 = that hybrid (default),
+// 1 = product scanning for both, 0 = operand scanning for both (A/B builds in profiles/).
+#ifndef PBC_MULT_IMPL
+#define PBC_MULT_IMPL 2
+#endif
+template <int N, bool FULL>
+__device__ __forceinline__ void fp_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if PBC_MULT_IMPL == 1
+  mont_mul_ps<N, FULL>(r, a, b);
+#else
+  mont_mul<N, FULL>(r, a, b);
+#endif
+}
+template <int N, bool FULL>
+__device__ __forceinline__ void fp_sqr(uint32_t* r, const uint32_t* a) {
+#if PBC_MULT_IMPL >= 1
+  mont_sqr_ps<N, FULL>(r, a);
+#else
+  mont_mul<N, FULL>(r, a, a);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
 // additive operations (arith/montfp.c:220-330), branch-free conditional correction
 // ---------------------------------------------------------------------------------------------
 template <int N, bool FULL>

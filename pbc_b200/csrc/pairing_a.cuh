@@ -212,7 +212,7 @@ k_a_finalexp(const uint4* __restrict__ f, const uint4* __restrict__ dinv, uint8_
     bool bit = j > 0 && ((c_a.h[j >> 5] >> (j & 31)) & 1u);   // last step takes the clear branch
     int d = bit ? fV0 : fV1, s = bit ? fV1 : fV0;
     O::mulsub(d, fV0, fV1, fP);
-    O::mulsub(s, s, s, fTWO);
+    O::sqrsub(s, s, fTWO);
   }
   // out0 = V_h / 2;  out1 = (2 V_{h+1} - P V_h) N^2 Dinv / 8
   O::dbl(fV1, fV1);

@@ -58,15 +58,29 @@ struct Ops {
   static __device__ __noinline__ void mul(int d, int a, int b) {
     uint32_t x[N], y[N];
     ld(x, a); ld(y, b);
-    mont_mul<N, FULL>(x, x, y);
+    fp_mul<N, FULL>(x, x, y);
     st(d, x);
   }
-  static __device__ __forceinline__ void sqr(int d, int a) { mul(d, a, a); }
+  static __device__ __noinline__ void sqr(int d, int a) {
+    uint32_t x[N];
+    ld(x, a);
+    fp_sqr<N, FULL>(x, x);
+    st(d, x);
+  }
   // d = a*b - c
   static __device__ __noinline__ void mulsub(int d, int a, int b, int c) {
     uint32_t x[N], y[N];
     ld(x, a); ld(y, b);
-    mont_mul<N, FULL>(x, x, y);
+    fp_mul<N, FULL>(x, x, y);
+    ld(y, c);
+    fp_sub<N>(x, x, y);
+    st(d, x);
+  }
+  // d = a^2 - c
+  static __device__ __noinline__ void sqrsub(int d, int a, int c) {
+    uint32_t x[N], y[N];
+    ld(x, a);
+    fp_sqr<N, FULL>(x, x);
     ld(y, c);
     fp_sub<N>(x, x, y);
     st(d, x);

@@ -117,6 +117,17 @@ class Pairing:
             raise PairingError(last_error())
         return out.raw
 
+    def set_stage_profiling(self, on: bool):
+        if lib.pbc_b200_set_stage_profiling(self._h, 1 if on else 0):
+            raise PairingError(last_error())
+
+    def stage_times(self):
+        """ms of (main kernel, batch inversion, final exponentiation) of the last apply_device"""
+        ms = (C.c_float * 3)()
+        if lib.pbc_b200_stage_times(self._h, ms):
+            raise PairingError(last_error())
+        return list(ms)
+
     def bench_fpmul(self, mode: int, blocks: int, iters: int, reps: int) -> float:
         ms = lib.pbc_b200_bench_fpmul(self._h, mode, blocks, iters, reps)
         if ms < 0:

@@ -27,7 +27,7 @@ def _cat(xs):
 
 
 # ---- F_p layer: differential test against exact integer arithmetic (guru/fp_test.c:44-85) ----
-@pytest.mark.parametrize("op", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("op", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_fp_ops_match_integers(dev, orc, op):
     q = orc.q
     rnd = random.Random(1234 + op)
@@ -46,7 +46,8 @@ def test_fp_ops_match_integers(dev, orc, op):
     got = dev.fp_op(op, A, B, n)
     f = {0: lambda x, y: x * y % q, 1: lambda x, y: (x + y) % q, 2: lambda x, y: (x - y) % q,
          3: lambda x, y: pow(x, -1, q), 4: lambda x, y: x * pow(2, -1, q) % q,
-         5: lambda x, y: (-x) % q}[op]
+         5: lambda x, y: (-x) % q, 6: lambda x, y: x * x % q,
+         7: lambda x, y: (x * y - y) % q}[op]
     want = b"".join(f(x, y).to_bytes(64, "big") for x, y in zip(a, b))
     assert got == want
 

@@ -16,12 +16,12 @@ def main():
         n = sm * blocks_per_sm * threads * 32 * iters
         print(json.dumps({"probe": "imad_wide_peak", "blocks_per_sm": blocks_per_sm, "threads": threads,
                           "ms": ms, "imad_per_s": n / (ms * 1e-3)}))
-    for mode in (0, 1):
-        for bps in (1, 2, 4, 8, 16):
+    for mode in (0, 2, 3, 1):
+        for bps in (1, 2, 3, 4, 8):
             iters = 2000
             ms = pr.bench_fpmul(mode, sm * bps, iters, 3)
             muls = sm * bps * 128 * iters
-            print(json.dumps({"probe": "fpmul512", "mode": "regs" if mode == 0 else "slots", "blocks_per_sm": bps,
+            print(json.dumps({"probe": "fpmul512", "mode": {0: "regs_operand_scan", 1: "slots_kernel_mult", 2: "regs_product_scan", 3: "regs_product_scan_sqr"}[mode], "blocks_per_sm": bps,
                               "warps_per_sm": bps * 4, "ms": ms, "mulmod_per_s": muls / (ms * 1e-3),
                               "imad_equiv_per_s": 528 * muls / (ms * 1e-3)}))
     g = json.load(open(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "a.json")))["pairing"]
