@@ -78,6 +78,8 @@ int pbc_b200_prod_pairings_apply_device(pbc_b200_pairing_t *p, void *d_out, cons
  *   out[i] = e(in1, in2[i]). */
 int pbc_b200_pp_pairings_apply(pbc_b200_pairing_t *p, unsigned char *out, const unsigned char *in1,
                                const unsigned char *in2, size_t n);
+int pbc_b200_pp_pairings_apply_device(pbc_b200_pairing_t *p, void *d_out, const void *d_in1,
+                                      const void *d_in2, size_t n, void *stream);
 
 /* Multi-GPU fan-out for the host-buffer entry points: use devices [0, count).  count = 0 means
  * every visible device.  Default is 1 (the current device). */

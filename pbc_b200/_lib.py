@@ -30,6 +30,7 @@ lib.pbc_b200_pairings_apply_device.argtypes = [_P, _P, _P, _P, C.c_size_t, _P]
 lib.pbc_b200_prod_pairings_apply.argtypes = [_P, _P, _P, _P, C.c_size_t, C.c_size_t]
 lib.pbc_b200_prod_pairings_apply_device.argtypes = [_P, _P, _P, _P, C.c_size_t, C.c_size_t, _P]
 lib.pbc_b200_pp_pairings_apply.argtypes = [_P, _P, _P, _P, C.c_size_t]
+lib.pbc_b200_pp_pairings_apply_device.argtypes = [_P, _P, _P, _P, C.c_size_t, _P]
 lib.pbc_b200_set_devices.argtypes = [_P, C.c_int]
 lib.pbc_b200_host_alloc.argtypes = [C.c_size_t]
 lib.pbc_b200_host_alloc.restype = _P

@@ -77,10 +77,10 @@ struct DevCtx {
   uint8_t* d_in2[2] = {nullptr, nullptr};
   uint8_t* d_out[2] = {nullptr, nullptr};
   void* ws[2] = {nullptr, nullptr};
-  size_t cap[2] = {0, 0};      // pairings the staging/workspace of stream s can hold
+  size_t cap_in1[2] = {0, 0}, cap_in2[2] = {0, 0}, cap_out[2] = {0, 0}, cap_ws[2] = {0, 0};   // bytes
   // device-API workspace
   void* ws_dev = nullptr;
-  size_t cap_dev = 0;
+  size_t cap_dev = 0;          // bytes
   // optional per-stage timing of the device-API path (bench.py roofline)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -108,9 +108,28 @@ static constexpr int kBlockMiller = 128;
 static constexpr int kBlockFinal = 128;
 static constexpr int kBlockInv = 128;
 
-static size_t ws_bytes_per_pairing(const pbc_b200_pairing_s* p) {
-  if (p->type == 'a') return (size_t)(2 + 1 + 1 + 5) * 64;
+// The three reference operations that reach the GPU (include/pbc_pairing.h:141-171, :54-89).
+enum Mode { kSingle = 0, kProd = 1, kPP = 2 };
+struct Job {
+  Mode mode = kSingle;
+  size_t k = 1;                // kProd: pairings per output
+};
+
+// workspace bytes for n_out outputs of `job`
+static size_t ws_bytes(const pbc_b200_pairing_s* p, const Job& job, size_t n_out) {
+  if (p->type == 'a') {
+    const size_t fq = 64;
+    if (job.mode == kSingle) return n_out * (2 + 1 + 1 + 5) * fq;
+    if (job.mode == kProd) return n_out * job.k * (2 + 1 + 5) * fq + n_out * (2 + 1 + 1) * fq;
+    return n_out * (2 + 1 + 1) * fq + (size_t)(3 * (p->a.exp2 + 1) * kNA + 4) * 4;
+  }
   return 0;
+}
+static size_t in1_elems(const Job& job, size_t n_out) {
+  return job.mode == kProd ? n_out * job.k : (job.mode == kPP ? 1 : n_out);
+}
+static size_t in2_elems(const Job& job, size_t n_out) {
+  return job.mode == kProd ? n_out * job.k : n_out;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -176,6 +195,10 @@ static cudaError_t allow_smem(K kernel, size_t bytes) {
 static constexpr size_t kSmemAMiller = (size_t)kASlots * 64 * kBlockMiller;
 static constexpr size_t kSmemAFinal = (size_t)kAFSlots * 64 * kBlockFinal;
 static constexpr size_t kSmemInv16 = (size_t)5 * 64 * kBlockInv;
+static constexpr int kBlockProd = 128;
+static constexpr size_t kSmemAProd = (size_t)kAPSlots * 64 * kBlockProd;
+static constexpr size_t kSmemAPPInit = (size_t)kASlots * 64 * 32;
+static constexpr size_t kSmemAPPApply = (size_t)kAPPSlots * 64 * kBlockMiller;
 
 static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
   if ((int)p->ctx.size() <= dev) p->ctx.resize(dev + 1);
@@ -189,6 +212,9 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
       CUDA_OK(allow_smem(k_a_finalexp<kBlockFinal>, kSmemAFinal));
       CUDA_OK(allow_smem(k_batch_invert<kNA, true, kBlockInv>, kSmemInv16));
       CUDA_OK(allow_smem(k_fpmul_slots<kNA, true, 128>, 2 * 64 * 128));
+      CUDA_OK(allow_smem(k_a_prod<kBlockProd>, kSmemAProd));
+      CUDA_OK(allow_smem(k_a_pp_init<32>, kSmemAPPInit));
+      CUDA_OK(allow_smem(k_a_pp_apply<kBlockMiller>, kSmemAPPApply));
     }
     c.ready = true;
   }
@@ -218,22 +244,49 @@ static void ctx_release(DevCtx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
-// enqueue one batch of n pairings, device buffers, on `st`.  ws: ws_bytes_per_pairing * n bytes.
+// enqueue one batch of n_out outputs of `job`, device buffers, on `st`.  ws: ws_bytes() bytes.
 // ------------------------------------------------------------------------------------------
-static int enqueue_pairings(pbc_b200_pairing_s* p, uint8_t* d_out, const uint8_t* d_in1,
+static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_out, const uint8_t* d_in1,
                             const uint8_t* d_in2, size_t n, void* ws, cudaStream_t st,
                             cudaEvent_t* ev = nullptr) {
   if (n == 0) return 0;
 #define STAGE(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
   if (p->type == 'a') {
-    uint4* f = (uint4*)ws;                       // [2][4][n]
-    uint4* dprod = f + 8 * n;                    // [4][n]
-    uint4* prefix = dprod + 4 * n;               // [4][n]
-    uint4* save = prefix + 4 * n;                // [5][4][n]
-    unsigned gm = (unsigned)((n + kBlockMiller - 1) / kBlockMiller);
+    uint4 *f, *dprod, *prefix;
     STAGE(0);
-    k_a_miller<kBlockMiller><<<gm, kBlockMiller, kSmemAMiller, st>>>(d_in1, d_in2, f, dprod, save, n);
-    LAUNCHED();
+    if (job.mode == kSingle) {
+      f = (uint4*)ws;                            // [2][4][n]
+      dprod = f + 8 * n;                         // [4][n]
+      prefix = dprod + 4 * n;                    // [4][n]
+      uint4* save = prefix + 4 * n;              // [5][4][n]
+      unsigned gm = (unsigned)((n + kBlockMiller - 1) / kBlockMiller);
+      k_a_miller<kBlockMiller><<<gm, kBlockMiller, kSmemAMiller, st>>>(d_in1, d_in2, f, dprod, save, n);
+      LAUNCHED();
+    } else if (job.mode == kProd) {
+      size_t m = n * job.k;
+      uint4* fi = (uint4*)ws;                    // [2][4][m]
+      uint4* di = fi + 8 * m;                    // [4][m]
+      uint4* save = di + 4 * m;                  // [5][4][m]
+      f = save + 20 * m;                         // [2][4][n]
+      dprod = f + 8 * n;
+      prefix = dprod + 4 * n;
+      unsigned gm = (unsigned)((m + kBlockMiller - 1) / kBlockMiller);
+      k_a_miller<kBlockMiller><<<gm, kBlockMiller, kSmemAMiller, st>>>(d_in1, d_in2, fi, di, save, m);
+      LAUNCHED();
+      unsigned gp = (unsigned)((n + kBlockProd - 1) / kBlockProd);
+      k_a_prod<kBlockProd><<<gp, kBlockProd, kSmemAProd, st>>>(fi, di, f, dprod, job.k, n, m);
+      LAUNCHED();
+    } else {
+      f = (uint4*)ws;
+      dprod = f + 8 * n;
+      prefix = dprod + 4 * n;
+      uint32_t* tab = (uint32_t*)(prefix + 4 * n);
+      k_a_pp_init<32><<<1, 32, kSmemAPPInit, st>>>(d_in1, tab);
+      LAUNCHED();
+      unsigned gm = (unsigned)((n + kBlockMiller - 1) / kBlockMiller);
+      k_a_pp_apply<kBlockMiller><<<gm, kBlockMiller, kSmemAPPApply, st>>>(tab, d_in2, f, dprod, n);
+      LAUNCHED();
+    }
     STAGE(1);
     size_t T = n < (size_t)148 * 256 ? n : (size_t)148 * 256;
     unsigned gi = (unsigned)((T + kBlockInv - 1) / kBlockInv);
@@ -251,24 +304,27 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, uint8_t* d_out, const uint8_t
 }
 
 // ------------------------------------------------------------------------------------------
-// host-buffer pipeline for one device: slice [0, n) of this device, chunked over two streams
+// host-buffer pipeline for one device: outputs [0, n) of this device's slice, chunked over two
+// streams (H2D of chunk k+1 overlaps the kernels of chunk k)
 // ------------------------------------------------------------------------------------------
-static int run_slice(pbc_b200_pairing_s* p, int dev, unsigned char* out, const unsigned char* in1,
-                     const unsigned char* in2, size_t n) {
+static int run_slice(pbc_b200_pairing_s* p, int dev, const Job& job, unsigned char* out,
+                     const unsigned char* in1, const unsigned char* in2, size_t n) {
   if (ctx_prepare(p, dev)) return 1;
   DevCtx& c = p->ctx[dev];
-  size_t chunk = n < kChunk ? n : kChunk;
-  size_t wsb = ws_bytes_per_pairing(p);
+  size_t per_out = job.mode == kProd ? job.k : 1;
+  size_t max_chunk = kChunk / per_out ? kChunk / per_out : 1;
+  size_t chunk = n < max_chunk ? n : max_chunk;
+  size_t b1 = in1_elems(job, chunk) * p->g1_len, b2 = in2_elems(job, chunk) * p->g2_len;
+  size_t bo = chunk * p->gt_len, bw = ws_bytes(p, job, chunk);
   for (int s = 0; s < 2; s++) {
-    if (c.cap[s] < chunk) {
-      cudaFree(c.d_in1[s]); cudaFree(c.d_in2[s]); cudaFree(c.d_out[s]); cudaFree(c.ws[s]);
-      c.d_in1[s] = c.d_in2[s] = c.d_out[s] = nullptr; c.ws[s] = nullptr; c.cap[s] = 0;
-      CUDA_OK(cudaMalloc(&c.d_in1[s], chunk * p->g1_len));
-      CUDA_OK(cudaMalloc(&c.d_in2[s], chunk * p->g2_len));
-      CUDA_OK(cudaMalloc(&c.d_out[s], chunk * p->gt_len));
-      CUDA_OK(cudaMalloc(&c.ws[s], chunk * wsb));
-      c.cap[s] = chunk;
-    }
+    if (c.cap_in1[s] < b1) { cudaFree(c.d_in1[s]); c.d_in1[s] = nullptr; c.cap_in1[s] = 0;
+      CUDA_OK(cudaMalloc(&c.d_in1[s], b1)); c.cap_in1[s] = b1; }
+    if (c.cap_in2[s] < b2) { cudaFree(c.d_in2[s]); c.d_in2[s] = nullptr; c.cap_in2[s] = 0;
+      CUDA_OK(cudaMalloc(&c.d_in2[s], b2)); c.cap_in2[s] = b2; }
+    if (c.cap_out[s] < bo) { cudaFree(c.d_out[s]); c.d_out[s] = nullptr; c.cap_out[s] = 0;
+      CUDA_OK(cudaMalloc(&c.d_out[s], bo)); c.cap_out[s] = bo; }
+    if (c.cap_ws[s] < bw) { cudaFree(c.ws[s]); c.ws[s] = nullptr; c.cap_ws[s] = 0;
+      CUDA_OK(cudaMalloc(&c.ws[s], bw)); c.cap_ws[s] = bw; }
     if (n <= chunk) break;   // a single chunk only ever uses stream 0
   }
   int k = 0;
@@ -276,14 +332,68 @@ static int run_slice(pbc_b200_pairing_s* p, int dev, unsigned char* out, const u
     size_t m = n - off < chunk ? n - off : chunk;
     int s = k & 1;
     cudaStream_t st = c.stream[s];
-    CUDA_OK(cudaMemcpyAsync(c.d_in1[s], in1 + off * p->g1_len, m * p->g1_len, cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemcpyAsync(c.d_in2[s], in2 + off * p->g2_len, m * p->g2_len, cudaMemcpyHostToDevice, st));
-    if (enqueue_pairings(p, c.d_out[s], c.d_in1[s], c.d_in2[s], m, c.ws[s], st)) return 1;
+    size_t o1 = job.mode == kPP ? 0 : in1_elems(job, off) * p->g1_len;
+    CUDA_OK(cudaMemcpyAsync(c.d_in1[s], in1 + o1, in1_elems(job, m) * p->g1_len, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(c.d_in2[s], in2 + in2_elems(job, off) * p->g2_len, in2_elems(job, m) * p->g2_len,
+                            cudaMemcpyHostToDevice, st));
+    if (enqueue_pairings(p, job, c.d_out[s], c.d_in1[s], c.d_in2[s], m, c.ws[s], st)) return 1;
     CUDA_OK(cudaMemcpyAsync(out + off * p->gt_len, c.d_out[s], m * p->gt_len, cudaMemcpyDeviceToHost, st));
   }
   CUDA_OK(cudaStreamSynchronize(c.stream[0]));
   CUDA_OK(cudaStreamSynchronize(c.stream[1]));
   return 0;
+}
+
+// contiguous slices of the outputs, one host thread per device, results written at the slice offset
+static int run_host(pbc_b200_pairing_s* p, const Job& job, unsigned char* out, const unsigned char* in1,
+                    const unsigned char* in2, size_t n) {
+  if (!p || (!out && n) || (!in1 && n) || (!in2 && n)) return fail("null argument");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(p->mu);
+  int cur = 0;
+  CUDA_OK(cudaGetDevice(&cur));
+  if (p->ndev <= 1) return run_slice(p, cur, job, out, in1, in2, n);
+  int nd = p->ndev;
+  std::vector<int> rc(nd, 0);
+  std::vector<std::string> msg(nd);
+  std::vector<std::thread> th;
+  size_t per = (n + nd - 1) / nd;
+  for (int d = 0; d < nd; d++) {
+    size_t lo = (size_t)d * per, hi = lo + per < n ? lo + per : n;
+    if (lo >= hi) continue;
+    th.emplace_back([=, &rc, &msg]() {
+      size_t o1 = job.mode == kPP ? 0 : in1_elems(job, lo) * p->g1_len;
+      rc[d] = run_slice(p, d, job, out + lo * p->gt_len, in1 + o1, in2 + in2_elems(job, lo) * p->g2_len, hi - lo);
+      if (rc[d]) msg[d] = g_err;
+    });
+  }
+  for (auto& t : th) t.join();
+  cudaSetDevice(cur);
+  for (int d = 0; d < nd; d++) if (rc[d]) return fail("device %d: %s", d, msg[d].c_str());
+  return 0;
+}
+
+static int run_device(pbc_b200_pairing_s* p, const Job& job, void* d_out, const void* d_in1,
+                      const void* d_in2, size_t n, void* stream) {
+  if (!p) return fail("null argument");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(p->mu);
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  if (ctx_prepare(p, dev)) return 1;
+  DevCtx& c = p->ctx[dev];
+  size_t need = ws_bytes(p, job, n);
+  if (c.cap_dev < need) {
+    CUDA_OK(cudaDeviceSynchronize());
+    cudaFree(c.ws_dev);
+    c.ws_dev = nullptr; c.cap_dev = 0;
+    CUDA_OK(cudaMalloc(&c.ws_dev, need));
+    c.cap_dev = need;
+  }
+  if (p->profile && !c.ev[0])
+    for (int i = 0; i < 4; i++) CUDA_OK(cudaEventCreate(&c.ev[i]));
+  return enqueue_pairings(p, job, (uint8_t*)d_out, (const uint8_t*)d_in1, (const uint8_t*)d_in2, n,
+                          c.ws_dev, (cudaStream_t)stream, p->profile ? c.ev : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -341,52 +451,34 @@ int pbc_b200_set_devices(pbc_b200_pairing_t* p, int count) {
 
 int pbc_b200_pairings_apply(pbc_b200_pairing_t* p, unsigned char* out, const unsigned char* in1,
                             const unsigned char* in2, size_t n) {
-  if (!p || (!out && n) || (!in1 && n) || (!in2 && n)) return fail("null argument");
-  if (n == 0) return 0;
-  std::lock_guard<std::mutex> lk(p->mu);
-  int cur = 0;
-  CUDA_OK(cudaGetDevice(&cur));
-  if (p->ndev <= 1) return run_slice(p, cur, out, in1, in2, n);
-  // contiguous slices, one host thread per device, results written at the slice offset
-  int nd = p->ndev;
-  std::vector<int> rc(nd, 0);
-  std::vector<std::string> msg(nd);
-  std::vector<std::thread> th;
-  size_t per = (n + nd - 1) / nd;
-  for (int d = 0; d < nd; d++) {
-    size_t lo = (size_t)d * per, hi = lo + per < n ? lo + per : n;
-    if (lo >= hi) continue;
-    th.emplace_back([=, &rc, &msg]() {
-      rc[d] = run_slice(p, d, out + lo * p->gt_len, in1 + lo * p->g1_len, in2 + lo * p->g2_len, hi - lo);
-      if (rc[d]) msg[d] = g_err;
-    });
-  }
-  for (auto& t : th) t.join();
-  cudaSetDevice(cur);
-  for (int d = 0; d < nd; d++) if (rc[d]) return fail("device %d: %s", d, msg[d].c_str());
-  return 0;
+  return run_host(p, Job{kSingle, 1}, out, in1, in2, n);
 }
 
 int pbc_b200_pairings_apply_device(pbc_b200_pairing_t* p, void* d_out, const void* d_in1,
                                    const void* d_in2, size_t n, void* stream) {
-  if (!p) return fail("null argument");
-  if (n == 0) return 0;
-  std::lock_guard<std::mutex> lk(p->mu);
-  int dev = 0;
-  CUDA_OK(cudaGetDevice(&dev));
-  if (ctx_prepare(p, dev)) return 1;
-  DevCtx& c = p->ctx[dev];
-  if (c.cap_dev < n) {
-    CUDA_OK(cudaDeviceSynchronize());
-    cudaFree(c.ws_dev);
-    c.ws_dev = nullptr; c.cap_dev = 0;
-    CUDA_OK(cudaMalloc(&c.ws_dev, n * ws_bytes_per_pairing(p)));
-    c.cap_dev = n;
-  }
-  if (p->profile && !c.ev[0])
-    for (int i = 0; i < 4; i++) CUDA_OK(cudaEventCreate(&c.ev[i]));
-  return enqueue_pairings(p, (uint8_t*)d_out, (const uint8_t*)d_in1, (const uint8_t*)d_in2, n,
-                          c.ws_dev, (cudaStream_t)stream, p->profile ? c.ev : nullptr);
+  return run_device(p, Job{kSingle, 1}, d_out, d_in1, d_in2, n, stream);
+}
+
+int pbc_b200_prod_pairings_apply(pbc_b200_pairing_t* p, unsigned char* out, const unsigned char* in1,
+                                 const unsigned char* in2, size_t k, size_t n_out) {
+  if (k == 0) return fail("prod_pairings: k must be positive");
+  return run_host(p, Job{kProd, k}, out, in1, in2, n_out);
+}
+
+int pbc_b200_prod_pairings_apply_device(pbc_b200_pairing_t* p, void* d_out, const void* d_in1,
+                                        const void* d_in2, size_t k, size_t n_out, void* stream) {
+  if (k == 0) return fail("prod_pairings: k must be positive");
+  return run_device(p, Job{kProd, k}, d_out, d_in1, d_in2, n_out, stream);
+}
+
+int pbc_b200_pp_pairings_apply(pbc_b200_pairing_t* p, unsigned char* out, const unsigned char* in1,
+                               const unsigned char* in2, size_t n) {
+  return run_host(p, Job{kPP, 1}, out, in1, in2, n);
+}
+
+int pbc_b200_pp_pairings_apply_device(pbc_b200_pairing_t* p, void* d_out, const void* d_in1,
+                                      const void* d_in2, size_t n, void* stream) {
+  return run_device(p, Job{kPP, 1}, d_out, d_in1, d_in2, n, stream);
 }
 
 int pbc_b200_set_stage_profiling(pbc_b200_pairing_t* p, int on) {
@@ -404,19 +496,6 @@ int pbc_b200_stage_times(pbc_b200_pairing_t* p, float* ms3) {
   if ((int)p->ctx.size() <= dev || !p->ctx[dev].ev[0]) return fail("stage profiling was not enabled");
   for (int i = 0; i < 3; i++) CUDA_OK(cudaEventElapsedTime(&ms3[i], p->ctx[dev].ev[i], p->ctx[dev].ev[i + 1]));
   return 0;
-}
-
-int pbc_b200_prod_pairings_apply(pbc_b200_pairing_t*, unsigned char*, const unsigned char*,
-                                 const unsigned char*, size_t, size_t) {
-  return fail("prod_pairings: not built yet");
-}
-int pbc_b200_prod_pairings_apply_device(pbc_b200_pairing_t*, void*, const void*, const void*, size_t,
-                                        size_t, void*) {
-  return fail("prod_pairings: not built yet");
-}
-int pbc_b200_pp_pairings_apply(pbc_b200_pairing_t*, unsigned char*, const unsigned char*,
-                               const unsigned char*, size_t) {
-  return fail("pp_pairings: not built yet");
 }
 
 void* pbc_b200_host_alloc(size_t bytes) {

@@ -180,6 +180,184 @@ k_a_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4* 
   O::st_global(dprod, 0, n, idx, aT0);
 }
 
+// ---------------------------------------------------------------------------------------------
+// element_prod_pairing (include/pbc_pairing.h:153-171 -> a_pairings_affine, ecc/a_param.c:1283-1383).
+// The reference shares one accumulator f between the k Miller loops; here every (P_j, Q_j) pair
+// runs its own k_a_miller thread (k times more parallelism for a 2^16-output batch) and the k
+// Miller values of one output are multiplied afterwards.  prod_j f_j differs from the reference's
+// shared accumulator only by factors in F_q^*, which the final exponentiation kills.
+//   f_in [2][4][n_in], d_in [4][n_in]  (n_in = n_out * k; d = 0 marks an O / off-curve input),
+//   f_out[2][4][n_out], d_out[4][n_out] = N(F) F0 F1, or 0: ANY bad input -> the whole product is 1.
+// ---------------------------------------------------------------------------------------------
+enum APSlot { pF0, pF1, pL0, pL1, pT0, pT1, pT2, kAPSlots };
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_a_prod(const uint4* __restrict__ f_in, const uint4* __restrict__ d_in, uint4* __restrict__ f_out,
+         uint4* __restrict__ d_out, size_t k, size_t n_out, size_t n_in) {
+  using O = Ops<kNA, true, BLOCK>;
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n_out) return;
+  bool valid = true;
+  uint32_t zero[kNA] = {0};
+  O::set_const(pF0, c_fp.one);
+  O::st(pF1, zero);
+  for (size_t j = 0; j < k; j++) {
+    size_t src = idx * k + j;
+    O::ld_global(pL0, f_in, 0, n_in, src);
+    O::ld_global(pL1, f_in, 1, n_in, src);
+    O::ld_global(pT0, d_in, 0, n_in, src);
+    valid = valid && !O::is_zero(pT0);
+    a_fmul<O>(pF0, pF1, pL0, pL1, pT0, pT1, pT2);
+  }
+  O::sqr(pT0, pF0);
+  O::sqr(pT1, pF1);
+  O::add(pT0, pT0, pT1);
+  O::mul(pT1, pF0, pF1);
+  O::mul(pT0, pT0, pT1);
+  if (!valid) O::st(pT0, zero);
+  O::st_global(f_out, 0, n_out, idx, pF0);
+  O::st_global(f_out, 1, n_out, idx, pF1);
+  O::st_global(d_out, 0, n_out, idx, pT0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pairing_pp_init / pairing_pp_apply (ecc/a_param.c:149-220, 317-360): one fixed first argument.
+// k_a_pp_init walks V = P, 2P, 4P, ... once (one thread; Jacobian, inversion-free) and stores the
+// line coefficients (a, b, c) of every tangent plus the final chord, each scaled by some element of
+// F_q^* (the reference stores the affine ones; the scale dies in the final exponentiation):
+//   tab[(3 i + {0,1,2}) * 16 ..]  i < exp2: tangent at 2^i P;  i = exp2: chord through V, V1
+//   tab[3 (exp2 + 1) * 16]        1 if P decoded to a finite point on the curve, else 0.
+// k_a_pp_apply then costs 7 multiplications per bit instead of 19:
+//   f <- f^2 (c - a Qx + i b Qy).
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_a_pp_init(const uint8_t* __restrict__ P, uint32_t* __restrict__ tab) {
+  using O = Ops<kNA, true, BLOCK>;
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  // slots: aX aY aZ aZ2 = V; aQX aQY aF0 = V1 (X1, Y1, Z1); aT0..aT5 scratch
+  bool okP = a_load_point<O>(aX, aY, aT0, aT1, P);
+  O::set_const(aZ, c_fp.one);
+  O::set_const(aZ2, c_fp.one);
+  const int exp1 = c_a.exp1, exp2 = c_a.exp2;
+  uint32_t x[kNA];
+  auto emit = [&](int row, int slot) {
+    O::ld(x, slot);
+#pragma unroll
+    for (int k = 0; k < kNA; k++) tab[(size_t)row * kNA + k] = x[k];
+  };
+  for (int i = 0; i < exp2; i++) {
+    if (i == exp1) {
+      O::copy(aQX, aX);
+      if (c_a.sign1 < 0) O::neg(aQY, aY); else O::copy(aQY, aY);
+      O::copy(aF0, aZ);
+    }
+    // tangent (compute_abc_tangent_proj, ecc/a_param.c:86-112), sign-flipped as a whole:
+    //   a = M Z^2, b = 2 Y Z^3, c = X M - 2 Y^2     with M = 3 X^2 + Z^4;  line = c + a Qx... see apply
+    O::sqr(aT0, aX);
+    O::sqr(aT1, aZ2);
+    O::dbl(aT2, aT0);
+    O::add(aT0, aT0, aT2);
+    O::add(aT0, aT0, aT1);          // M
+    O::sqr(aT1, aY);                // Y^2
+    O::mul(aT3, aT0, aZ2);          // a = M Z^2
+    emit(3 * i + 0, aT3);
+    O::mul(aT5, aX, aT0);
+    O::sub(aT5, aT5, aT1);
+    O::sub(aT5, aT5, aT1);          // c = X M - 2 Y^2
+    emit(3 * i + 2, aT5);
+    O::mul(aT2, aX, aT1);
+    O::dbl(aT2, aT2, 2);            // S = 4 X Y^2
+    O::mul(aZ, aY, aZ);
+    O::dbl(aZ, aZ);                 // Z' = 2 Y Z
+    O::mul(aT3, aZ, aZ2);           // b = Z' Z^2
+    emit(3 * i + 1, aT3);
+    O::sqr(aZ2, aZ);
+    O::sqr(aT5, aT0);
+    O::sub(aX, aT5, aT2);
+    O::sub(aX, aX, aT2);            // X' = M^2 - 2 S
+    O::sqr(aT1, aT1);
+    O::dbl(aT1, aT1, 3);            // 8 Y^4
+    O::sub(aT2, aT2, aX);
+    O::mulsub(aY, aT0, aT2, aT1);   // Y' = M (S - X') - 8 Y^4
+  }
+  // chord through V = (X, Y, Z) and V1 = (X1, Y1, Z1), scaled by Z^3 Z1^3 (compute_abc_line :114-130)
+  //   a = Y Z1^3 - Y1 Z^3,  b = X1 Z1 Z^3 - X Z Z1^3,  c = X Z Y1 - Y X1 Z1
+  O::mul(aT1, aZ2, aZ);             // Z^3
+  O::sqr(aT2, aF0);
+  O::mul(aT2, aT2, aF0);            // Z1^3
+  O::mul(aT3, aX, aZ);              // X Z
+  O::mul(aT4, aQX, aF0);            // X1 Z1
+  O::mul(aT0, aT3, aQY);            // X Z Y1
+  O::mul(aT5, aY, aT4);             // Y X1 Z1
+  O::sub(aT0, aT0, aT5);            // c
+  emit(3 * exp2 + 2, aT0);
+  O::mul(aT4, aT4, aT1);
+  O::mul(aT3, aT3, aT2);
+  O::sub(aT4, aT4, aT3);            // b
+  emit(3 * exp2 + 1, aT4);
+  O::mul(aT2, aY, aT2);
+  O::mul(aT1, aQY, aT1);
+  O::sub(aT2, aT2, aT1);            // a
+  emit(3 * exp2 + 0, aT2);
+  tab[(size_t)3 * (exp2 + 1) * kNA] = okP ? 1u : 0u;
+}
+
+enum APPSlot { qF0, qF1, qQX, qQY, qS0, qS1, qT0, qT1, qT2, qT3, qT4, kAPPSlots };
+
+// tangent rows hold (a, b, c) with line value  (c + a Qx) + i (b Qy);  the chord row holds the
+// reference's (a, b, c) with line value (c - a Qx) + i (b Qy)   (a_miller_evalfn :306-315).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_a_pp_apply(const uint32_t* __restrict__ tab, const uint8_t* __restrict__ Q, uint4* __restrict__ f,
+             uint4* __restrict__ dprod, size_t n) {
+  using O = Ops<kNA, true, BLOCK>;
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  bool live = idx < n;
+  size_t src = live ? idx : 0;
+  bool okQ = a_load_point<O>(qQX, qQY, qT0, qT1, Q + src * (2 * kWA));
+  const int exp1 = c_a.exp1, exp2 = c_a.exp2;
+  bool valid = okQ && tab[(size_t)3 * (exp2 + 1) * kNA] != 0;
+  uint32_t zero[kNA] = {0};
+  O::set_const(qF0, c_fp.one);
+  O::st(qF1, zero);
+  for (int i = 0; i <= exp2; i++) {
+    const uint32_t* row = tab + (size_t)3 * i * kNA;
+    if (i == exp1) {
+      O::copy(qS0, qF0);
+      if (c_a.sign1 < 0) O::neg(qS1, qF1); else O::copy(qS1, qF1);
+    }
+    if (i < exp2) {
+      // f = f^2
+      O::add(qT0, qF0, qF1);
+      O::sub(qT1, qF0, qF1);
+      O::mul(qF1, qF0, qF1);
+      O::dbl(qF1, qF1);
+      O::mul(qF0, qT0, qT1);
+    } else {
+      a_fmul<O>(qF0, qF1, qS0, qS1, qT0, qT1, qT2);   // f *= f1
+    }
+    O::set_const(qT0, row);                  // a
+    O::mul(qT0, qT0, qQX);
+    O::set_const(qT1, row + 2 * kNA);        // c
+    if (i < exp2) O::add(qT0, qT1, qT0); else O::sub(qT0, qT1, qT0);
+    O::set_const(qT1, row + kNA);            // b
+    O::mul(qT1, qT1, qQY);
+    a_fmul<O>(qF0, qF1, qT0, qT1, qT2, qT3, qT4);
+  }
+  if (!live) return;
+  O::sqr(qT0, qF0);
+  O::sqr(qT1, qF1);
+  O::add(qT0, qT0, qT1);
+  O::mul(qT1, qF0, qF1);
+  O::mul(qT0, qT0, qT1);
+  if (!valid) O::st(qT0, zero);
+  O::st_global(f, 0, n, idx, qF0);
+  O::st_global(f, 1, n, idx, qF1);
+  O::st_global(dprod, 0, n, idx, qT0);
+}
+
 // slot map of the final-exponentiation kernel
 enum AFSlot { fF0, fF1, fD, fN, fP, fV0, fV1, fT0, fTWO, kAFSlots };
 

@@ -139,3 +139,81 @@ def test_device_pointer_entry(dev, golden):
     dev.apply_device(out.data_ptr(), P.data_ptr(), Q.data_ptr(), n, st.cuda_stream)
     st.synchronize()
     assert bytes(out.cpu().numpy().tobytes()) == _cat(g["e"])
+
+
+# ---- element_prod_pairing (ecc/a_param.c:1283-1383) ----
+def test_prod_reference_fixtures(dev, golden):
+    g = golden["a"]["prod"]
+    k, n_out = g["k"], len(g["e"])
+    assert dev.prod_apply(_cat(g["P"]), _cat(g["Q"]), k, n_out) == _cat(g["e"])
+
+
+def test_prod_matches_oracle_and_product_of_singles(dev, orc, golden):
+    g = golden["a"]["pairing"]
+    k, n_out = 5, 4                       # 20 of the 24 fixture pairs, k not a power of two
+    P, Q = _cat(g["P"][:k * n_out]), _cat(g["Q"][:k * n_out])
+    got = dev.prod_apply(P, Q, k, n_out)
+    for i in range(n_out):
+        want = O.prod_pairing_bytes(orc, [bytes.fromhex(x) for x in g["P"][i * k:(i + 1) * k]],
+                                    [bytes.fromhex(x) for x in g["Q"][i * k:(i + 1) * k]])
+        assert got[i * 128:(i + 1) * 128] == want
+        acc = orc.GT.one
+        for j in range(i * k, (i + 1) * k):
+            acc = orc.GT.mul(acc, orc.GT.from_bytes(bytes.fromhex(g["e"][j])))
+        assert want == orc.GT.to_bytes(acc)
+
+
+def test_prod_any_infinite_input_gives_identity(dev, golden):
+    # include/pbc_pairing.h:161-168: one O anywhere makes the whole product 1
+    g = golden["a"]
+    k = g["prod"]["k"]
+    P, Q = [bytes.fromhex(x) for x in g["prod"]["P"]], [bytes.fromhex(x) for x in g["prod"]["Q"]]
+    P[1] = bytes.fromhex(g["offcurve"]["badP"])          # poisons output 0 only
+    Q[2 * k + 3] = bytes.fromhex(g["offcurve"]["badQ"])  # poisons output 2 only
+    got = dev.prod_apply(b"".join(P), b"".join(Q), k, 3)
+    ident = bytes.fromhex(g["offcurve"]["identity"])
+    assert got[:128] == ident and got[256:] == ident
+    assert got[128:256] == bytes.fromhex(g["prod"]["e"][1])
+
+
+def test_prod_k1_equals_single_and_empty(dev, golden):
+    g = golden["a"]["pairing"]
+    assert dev.prod_apply(_cat(g["P"]), _cat(g["Q"]), 1, len(g["e"])) == _cat(g["e"])
+    assert dev.prod_apply(b"", b"", 4, 0) == b""
+
+
+def test_prod_large_batch_tiles(dev, golden):
+    """2^12+5 outputs of k = 16 (config 5 shape) built by tiling the fixture pairs: crosses the
+    host pipeline's chunk boundary; every output must equal the oracle product of its 16 pairs."""
+    g = golden["a"]["pairing"]
+    m = len(g["e"])                       # 24 pairs: period lcm(24,16)=48 pairs = 3 outputs
+    k, n_out = 16, (1 << 14) + 5
+    reps = k * n_out // m + 1
+    P, Q = (_cat(g["P"]) * reps)[:k * n_out * 128], (_cat(g["Q"]) * reps)[:k * n_out * 128]
+    got = dev.prod_apply(P, Q, k, n_out)
+    first = dev.prod_apply(P[:48 * 128], Q[:48 * 128], k, 3)
+    assert got == (first * (n_out // 3 + 1))[:n_out * 128]
+
+
+# ---- pairing_pp_init / pairing_pp_apply (ecc/a_param.c:149-220, 317-360) ----
+def test_pp_reference_fixtures(dev, golden):
+    g = golden["a"]
+    n = len(g["pp"]["e"])
+    got = dev.pp_apply(bytes.fromhex(g["pp"]["P"]), _cat(g["pairing"]["Q"][:n]), n)
+    assert got == _cat(g["pp"]["e"])
+
+
+def test_pp_equals_plain_pairing(dev, golden):
+    g = golden["a"]["pairing"]
+    n = len(g["e"])
+    P3 = bytes.fromhex(g["P"][3])
+    assert dev.pp_apply(P3, _cat(g["Q"]), n) == dev.apply(P3 * n, _cat(g["Q"]), n)
+
+
+def test_pp_offcurve(dev, golden):
+    g = golden["a"]
+    ident = bytes.fromhex(g["offcurve"]["identity"])
+    Q = _cat(g["pairing"]["Q"][:2]) + bytes.fromhex(g["offcurve"]["badQ"])
+    got = dev.pp_apply(bytes.fromhex(g["pp"]["P"]), Q, 3)
+    assert got[256:] == ident and got[:256] == _cat(g["pp"]["e"][:2])
+    assert dev.pp_apply(bytes.fromhex(g["offcurve"]["badP"]), Q, 3) == ident * 3
