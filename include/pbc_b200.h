@@ -113,6 +113,14 @@ double pbc_b200_bench_imad(int blocks, int threads, int iters, int reps);
 int pbc_b200_set_stage_profiling(pbc_b200_pairing_t *p, int on);
 int pbc_b200_stage_times(pbc_b200_pairing_t *p, float *ms3);
 
+/* Test hook for the one-time constant derivation (f_init_pairing ecc/f_param.c:408-444,
+ * d_init_pairing ecc/d_param.c:1035-1049): writes the canonical residues of the named derived
+ * constant, each as `width` big-endian bytes, and returns the byte count (negative on failure).
+ * type f: xi, xi_inv, twist_b, xpowq2, xpowq6, xpowq8 (2 coordinates each), tateexp (1);
+ * type d: xpwr3, xpwr4, xpowq, xpowq2 (3 each), nqrinv, nqrinv2, phikonr (1).  Host only. */
+int pbc_b200_derived_constant(const pbc_b200_pairing_t *p, const char *name, unsigned char *out,
+                              size_t width, size_t cap);
+
 /* F_p differential-test hook (guru/fp_test.c, guru/checkfp.c analogue): out[i] = a[i] op b[i]
  * in F_q on the device; operands and results are canonical big-endian F_q wire bytes.
  * op: 0 = mul, 1 = add, 2 = sub, 3 = invert a (b ignored), 4 = halve a, 5 = neg a,

@@ -20,8 +20,14 @@
 #include "../../include/pbc_b200.h"
 #include "common_kernels.cuh"
 #include "host_bigint.hpp"
+#include "host_fields.hpp"
 #include "pairing_a.cuh"
+#include "pairing_d.cuh"
+#include "pairing_f.cuh"
 
+namespace pbcb200 {
+__global__ void k_fqmul_chain(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, int iters, int mode);
+}
 using namespace pbcb200;
 
 // ------------------------------------------------------------------------------------------
@@ -92,9 +98,13 @@ struct pbc_b200_pairing_s {
   bool full = false;
   FpConsts fp;
   AConsts a;
+  CCConsts cc;
+  FConsts f;
+  DConsts d;
   int ndev = 1;
   bool profile = false;        // record CUDA events between the kernels of the device-API path
   std::vector<DevCtx> ctx;     // indexed by device ordinal
+  std::map<std::string, std::vector<BigUInt>> derived;   // canonical values of the derived constants (tests)
   std::mutex mu;
   uint64_t id;
 };
@@ -107,6 +117,7 @@ static constexpr size_t kChunk = 1u << 18;      // pairings per pipeline chunk (
 static constexpr int kBlockMiller = 128;
 static constexpr int kBlockFinal = 128;
 static constexpr int kBlockInv = 128;
+static constexpr int kBlockCC = 128;           // types f, d: threads per block
 
 // The three reference operations that reach the GPU (include/pbc_pairing.h:141-171, :54-89).
 enum Mode { kSingle = 0, kProd = 1, kPP = 2 };
@@ -123,7 +134,12 @@ static size_t ws_bytes(const pbc_b200_pairing_s* p, const Job& job, size_t n_out
     if (job.mode == kProd) return n_out * job.k * (2 + 1 + 5) * fq + n_out * (2 + 1 + 1) * fq;
     return n_out * (2 + 1 + 1) * fq + (size_t)(3 * (p->a.exp2 + 1) * kNA + 4) * 4;
   }
-  return 0;
+  // types f, d: Miller values [W][n] words + one flag word each; products add the reduced arrays
+  size_t W = p->type == 'f' ? kF12Words : kF6DWords;
+  size_t n_in = job.mode == kProd ? n_out * job.k : n_out;
+  size_t bytes = n_in * (W + 1) * 4;
+  if (job.mode == kProd) bytes += n_out * (W + 1) * 4;
+  return bytes;
 }
 static size_t in1_elems(const Job& job, size_t n_out) {
   return job.mode == kProd ? n_out * job.k : (job.mode == kPP ? 1 : n_out);
@@ -184,6 +200,114 @@ static int init_type_a(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   return 0;
 }
 
+// x -> x * 2^(32 n) mod q, as n little-endian words
+static void to_mont(uint32_t* out, const BigUInt& x, const BigUInt& q, int n) {
+  ((x % q).shl(32 * (size_t)n) % q).to_words(out, n);
+}
+static void fill_cc(CCConsts* c, const BigUInt& A, const BigUInt& B, const BigUInt& r, const BigUInt& q) {
+  memset(c, 0, sizeof *c);
+  to_mont(c->A, A, q, kNS);
+  to_mont(c->B, B, q, kNS);
+  r.to_words(c->r, kNS);
+  c->rbits = (uint32_t)r.bits();
+  c->a_is_zero = (A % q).is_zero() ? 1u : 0u;
+}
+
+// f_init_pairing (ecc/f_param.c:335-447)
+static int init_type_f(pbc_b200_pairing_s* p, const std::map<std::string, std::string>& tab) {
+  BigUInt q, r, b, beta, a0, a1;
+  if (!get_big(tab, "q", &q) || !get_big(tab, "r", &r) || !get_big(tab, "b", &b) ||
+      !get_big(tab, "beta", &beta) || !get_big(tab, "alpha0", &a0) || !get_big(tab, "alpha1", &a1)) return 1;
+  if (q.bits() > 159 || q.bits() < 129) return fail("type f: this build supports 129..159-bit q (got %zu)", q.bits());
+  if (r.bits() > 160 || r.bits() < 3) return fail("type f: bad group order");
+  BigUInt six(6);
+  if (!((q % six) == BigUInt(1))) return fail("type f: q must be 1 mod 6");
+  p->type = 'f';
+  p->nlimbs = kNS;
+  p->full = false;
+  p->g1_len = 2 * kWS; p->g2_len = 4 * kWS; p->gt_len = 12 * kWS;
+  fill_fp_consts(&p->fp, q, kNS);
+  fill_cc(&p->cc, BigUInt(), b, r, q);
+  HostF2Field K{q, beta % q};
+  HostF2 alpha{a0 % q, a1 % q};
+  HostF2 xi = K.neg(alpha);
+  if (xi.a.is_zero() && xi.b.is_zero()) return fail("type f: alpha is zero");
+  HostF2 xi_inv = K.inv(xi);
+  HostF2 tb = K.scale(xi, b % q);
+  BigUInt q2 = q * q, q6 = q2 * q2 * q2, q8 = q6 * q2, one(1);
+  HostF2 x2 = K.pow(xi, (q2 - one) / six), x6 = K.pow(xi, (q6 - one) / six), x8 = K.pow(xi, (q8 - one) / six);
+  FConsts& c = p->f;
+  memset(&c, 0, sizeof c);
+  to_mont(c.beta, K.beta, q, kNS);
+  auto put2 = [&](uint32_t dst[2][kNS], const HostF2& v) { to_mont(dst[0], v.a, q, kNS); to_mont(dst[1], v.b, q, kNS); };
+  put2(c.xi, xi); put2(c.xi_inv, xi_inv); put2(c.twist_b, tb);
+  put2(c.xpowq2, x2); put2(c.xpowq6, x6); put2(c.xpowq8, x8);
+  auto rec2 = [&](const char* name, const HostF2& v) { p->derived[name] = {v.a, v.b}; };
+  rec2("xi", xi); rec2("xi_inv", xi_inv); rec2("twist_b", tb);
+  rec2("xpowq2", x2); rec2("xpowq6", x6); rec2("xpowq8", x8);
+  BigUInt num = (q2 * q2 + one) - q2, te, rem;
+  BigUInt::divmod(num, r, &te, &rem);
+  if (!rem.is_zero()) return fail("type f: r does not divide q^4 - q^2 + 1");
+  if (te.bits() > 512) return fail("type f: final exponent too large");
+  te.to_words(c.tateexp, 16);
+  p->derived["tateexp"] = {te};
+  c.tatebits = (uint32_t)te.bits();
+  return 0;
+}
+
+// d_init_pairing (ecc/d_param.c:993-1095), k = 6
+static int init_type_d(pbc_b200_pairing_s* p, const std::map<std::string, std::string>& tab) {
+  BigUInt q, r, a, b, nqr, c0, c1, c2;
+  int k = 0;
+  if (!get_big(tab, "q", &q) || !get_big(tab, "r", &r) || !get_big(tab, "a", &a) || !get_big(tab, "b", &b) ||
+      !get_int(tab, "k", &k) || !get_big(tab, "nqr", &nqr) || !get_big(tab, "coeff0", &c0) ||
+      !get_big(tab, "coeff1", &c1) || !get_big(tab, "coeff2", &c2)) return 1;
+  if (k != 6) return fail("type d: only embedding degree 6 is on the B200 hot path (got k = %d)", k);
+  if (q.bits() > 159 || q.bits() < 129) return fail("type d: this build supports 129..159-bit q (got %zu)", q.bits());
+  if (r.bits() > 160 || r.bits() < 3) return fail("type d: bad group order");
+  p->type = 'd';
+  p->nlimbs = kNS;
+  p->full = false;
+  p->g1_len = 2 * kWS; p->g2_len = 6 * kWS; p->gt_len = 6 * kWS;
+  fill_fp_consts(&p->fp, q, kNS);
+  fill_cc(&p->cc, a, b, r, q);
+  DConsts& c = p->d;
+  memset(&c, 0, sizeof c);
+  BigUInt v = nqr % q, vinv = BigUInt::invmod(v, q), one(1);
+  BigUInt v2 = BigUInt::mulmod(v, v, q);
+  to_mont(c.nqr, v, q, kNS);
+  to_mont(c.nqrinv, vinv, q, kNS);
+  to_mont(c.nqrinv2, BigUInt::mulmod(vinv, vinv, q), q, kNS);
+  to_mont(c.twist_a, BigUInt::mulmod(a % q, v2, q), q, kNS);
+  to_mont(c.twist_b, BigUInt::mulmod(b % q, BigUInt::mulmod(v2, v, q), q), q, kNS);
+  to_mont(c.two, BigUInt(2), q, kNS);
+  HostF3Field K{q, {c0 % q, c1 % q, c2 % q}};
+  HostF3 x;
+  x.c[1] = one;
+  HostF3 x3 = K.mul(K.mul(x, x), x), x4 = K.mul(x3, x);
+  HostF3 xq = K.pow(x, q), xq2 = K.mul(xq, xq);
+  for (int i = 0; i < 3; i++) {
+    to_mont(c.xpwr3[i], x3.c[i], q, kNS);
+    to_mont(c.xpwr4[i], x4.c[i], q, kNS);
+    to_mont(c.xpowq[i], xq.c[i], q, kNS);
+    to_mont(c.xpowq2[i], xq2.c[i], q, kNS);
+  }
+  BigUInt num = (q * q + one) - q, ph, rem;
+  BigUInt::divmod(num, r, &ph, &rem);
+  if (!rem.is_zero()) return fail("type d: r does not divide q^2 - q + 1");
+  if (ph.bits() > 256) return fail("type d: final exponent too large");
+  ph.to_words(c.phikonr, 8);
+  p->derived["phikonr"] = {ph};
+  p->derived["xpwr3"] = {x3.c[0], x3.c[1], x3.c[2]};
+  p->derived["xpwr4"] = {x4.c[0], x4.c[1], x4.c[2]};
+  p->derived["xpowq"] = {xq.c[0], xq.c[1], xq.c[2]};
+  p->derived["xpowq2"] = {xq2.c[0], xq2.c[1], xq2.c[2]};
+  p->derived["nqrinv"] = {vinv};
+  p->derived["nqrinv2"] = {BigUInt::mulmod(vinv, vinv, q)};
+  c.phibits = (uint32_t)ph.bits();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // device contexts
 // ------------------------------------------------------------------------------------------
@@ -224,6 +348,9 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
     CUDA_OK(cudaDeviceSynchronize());
     CUDA_OK(cudaMemcpyToSymbol(c_fp, &p->fp, sizeof(FpConsts)));
     if (p->type == 'a') CUDA_OK(cudaMemcpyToSymbol(c_a, &p->a, sizeof(AConsts)));
+    if (p->type == 'f' || p->type == 'd') CUDA_OK(cudaMemcpyToSymbol(c_cc, &p->cc, sizeof(CCConsts)));
+    if (p->type == 'f') CUDA_OK(cudaMemcpyToSymbol(c_f, &p->f, sizeof(FConsts)));
+    if (p->type == 'd') CUDA_OK(cudaMemcpyToSymbol(c_d, &p->d, sizeof(DConsts)));
     CUDA_OK(cudaDeviceSynchronize());
     g_const_owner[dev] = p->id;
   }
@@ -295,6 +422,37 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
     STAGE(2);
     unsigned gf = (unsigned)((n + kBlockFinal - 1) / kBlockFinal);
     k_a_finalexp<kBlockFinal><<<gf, kBlockFinal, kSmemAFinal, st>>>(f, dprod, d_out, n);
+    LAUNCHED();
+    STAGE(3);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  if (p->type == 'f' || p->type == 'd') {
+    const bool isf = p->type == 'f';
+    const size_t W = isf ? kF12Words : kF6DWords;
+    size_t m = job.mode == kProd ? n * job.k : n;
+    uint32_t* mv = (uint32_t*)ws;                // [W][m]
+    uint32_t* flag = mv + W * m;                 // [m]
+    size_t stride1 = job.mode == kPP ? 0 : (size_t)p->g1_len;
+    unsigned gm = (unsigned)((m + kBlockCC - 1) / kBlockCC);
+    STAGE(0);
+    if (isf) k_f_miller<kBlockCC><<<gm, kBlockCC, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1);
+    else k_d_miller<kBlockCC><<<gm, kBlockCC, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1);
+    LAUNCHED();
+    STAGE(1);
+    if (job.mode == kProd) {
+      uint32_t* mvo = flag + m;                  // [W][n]
+      uint32_t* flago = mvo + W * n;
+      unsigned gp = (unsigned)((n + kBlockCC - 1) / kBlockCC);
+      if (isf) k_f_prod<kBlockCC><<<gp, kBlockCC, 0, st>>>(mv, flag, mvo, flago, job.k, n, m);
+      else k_d_prod<kBlockCC><<<gp, kBlockCC, 0, st>>>(mv, flag, mvo, flago, job.k, n, m);
+      LAUNCHED();
+      mv = mvo; flag = flago;
+    }
+    STAGE(2);
+    unsigned gf = (unsigned)((n + kBlockCC - 1) / kBlockCC);
+    if (isf) k_f_finalexp<kBlockCC><<<gf, kBlockCC, 0, st>>>(mv, flag, d_out, n);
+    else k_d_finalexp<kBlockCC><<<gf, kBlockCC, 0, st>>>(mv, flag, d_out, n);
     LAUNCHED();
     STAGE(3);
     CUDA_OK(cudaGetLastError());
@@ -414,7 +572,9 @@ int pbc_b200_pairing_init_set_buf(pbc_b200_pairing_t** out, const char* param, s
   p->id = g_next_id.fetch_add(1);
   int rc;
   if (it->second == "a") rc = init_type_a(p, tab);
-  else rc = fail("pairing type `%s' is not on the B200 hot path (supported: a)", it->second.c_str());
+  else if (it->second == "f") rc = init_type_f(p, tab);
+  else if (it->second == "d") rc = init_type_d(p, tab);
+  else rc = fail("pairing type `%s' is not on the B200 hot path (supported: a, d with k = 6, f)", it->second.c_str());
   if (rc) { delete p; return 1; }
   *out = p;
   return 0;
@@ -439,6 +599,25 @@ int pbc_b200_pairing_length_in_bytes_G1(const pbc_b200_pairing_t* p) { return p-
 int pbc_b200_pairing_length_in_bytes_G2(const pbc_b200_pairing_t* p) { return p->g2_len; }
 int pbc_b200_pairing_length_in_bytes_GT(const pbc_b200_pairing_t* p) { return p->gt_len; }
 int pbc_b200_pairing_type(const pbc_b200_pairing_t* p) { return p->type; }
+
+int pbc_b200_derived_constant(const pbc_b200_pairing_t* p, const char* name, unsigned char* out,
+                              size_t width, size_t cap) {
+  if (!p || !name || !out || !width) { fail("null argument"); return -1; }
+  auto it = p->derived.find(name);
+  if (it == p->derived.end()) { fail("no derived constant `%s'", name); return -1; }
+  size_t need = it->second.size() * width;
+  if (need > cap) { fail("buffer too small"); return -1; }
+  size_t o = 0;
+  for (const BigUInt& v : it->second) {
+    if (v.bits() > 8 * width) { fail("constant wider than %zu bytes", width); return -1; }
+    for (size_t i = 0; i < width; i++) {
+      size_t byte = width - 1 - i;                       // big-endian
+      out[o + i] = (unsigned char)(v.word(byte / 4) >> (8 * (byte % 4)));
+    }
+    o += width;
+  }
+  return (int)need;
+}
 
 int pbc_b200_set_devices(pbc_b200_pairing_t* p, int count) {
   int have = 0;
@@ -535,6 +714,8 @@ double pbc_b200_bench_fpmul(pbc_b200_pairing_t* p, int mode, int blocks, int ite
       else if (mode == 2) k_fpmul_chain<kNA, true, 1><<<blocks, threads, 0, st>>>(out, in, iters);
       else if (mode == 3) k_fpmul_chain<kNA, true, 2><<<blocks, threads, 0, st>>>(out, in, iters);
       else k_fpmul_slots<kNA, true, 128><<<blocks, threads, 2 * 64 * 128, st>>>(out, in, iters);
+    } else {
+      k_fqmul_chain<<<blocks, threads, 0, st>>>(out, in, iters, mode == 3 ? 1 : 0);
     }
     LAUNCHED();
   };
@@ -607,6 +788,38 @@ k_fp_op(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a, const 
   mont_mul<N, FULL>(x, x, one);
   limbs_to_be<N, WB>(out + idx * WB, x);
 }
+// same hook for the five-limb field of types f and d
+__global__ void k_fq_op(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a,
+                        const uint8_t* __restrict__ b, size_t n) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  Fq x, y;
+  fq_from_wire(x, a + idx * kWS);
+  fq_from_wire(y, b + idx * kWS);
+  switch (op) {
+    case 0: fq_mul(x, x, y); break;
+    case 1: fq_add(x, x, y); break;
+    case 2: fq_sub(x, x, y); break;
+    case 3: fq_inv(&x, &x); break;
+    case 4: fq_halve(x, x); break;
+    case 5: fq_neg(x, x); break;
+    case 6: fq_sqr(x, x); break;
+    case 7: fq_mul(x, x, y); fq_sub(x, x, y); break;
+  }
+  fq_to_wire(out + idx * kWS, x);
+}
+
+// dependent chain of five-limb Montgomery multiplications (mode 0) / squarings (mode 1)
+__global__ void k_fqmul_chain(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, int iters, int mode) {
+  size_t T = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  Fq a, b;
+#pragma unroll
+  for (int k = 0; k < kNS; k++) { a.v[k] = in[(2 * k) * T + t]; b.v[k] = in[(2 * k + 1) * T + t]; }
+  if (mode == 0) for (int i = 0; i < iters; i++) fq_mul(a, a, b);
+  else for (int i = 0; i < iters; i++) fq_sqr(a, a);
+#pragma unroll
+  for (int k = 0; k < kNS; k++) out[k * T + t] = a.v[k];
+}
 }  // namespace pbcb200
 
 extern "C" int pbc_b200_fp_op(pbc_b200_pairing_t* p, int op, unsigned char* out,
@@ -627,6 +840,8 @@ extern "C" int pbc_b200_fp_op(pbc_b200_pairing_t* p, int op, unsigned char* out,
   if (p->type == 'a') {
     CUDA_OK(allow_smem(k_fp_op<kNA, true, 64, 128>, 4 * 64 * 128));
     k_fp_op<kNA, true, 64, 128><<<g, 128, 4 * 64 * 128>>>(op, dout, da, db, n);
+  } else {
+    k_fq_op<<<g, 128>>>(op, dout, da, db, n);
   }
   LAUNCHED();
   CUDA_OK(cudaDeviceSynchronize());

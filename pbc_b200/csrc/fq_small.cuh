@@ -1,0 +1,77 @@
+// fq_small.cuh -- the 158/159-bit base field of the Type F and Type D curves on five 32-bit limbs.
+//
+// Device replacement for arith/montfp.c on 3 x 64-bit limbs (the reference's F_q for f.param and
+// d159.param): values are held as x * 2^160 mod q on FIVE 32-bit words (the reference rounds up to
+// 192 bits; 25 instead of 36 word products per multiplication).  q < 2^159, so one conditional
+// subtraction keeps everything canonical (FULL = false in fp.cuh).  Multiplication is the
+// product-scanning Montgomery form of fp.cuh (works for odd limb counts).
+//
+// Tower elements (F_q^2, F_q^3, F_q^6, F_q^12) are plain structs of Fq; the compiler keeps the
+// ones that are passed by pointer to the out-of-line tower routines in the per-thread local
+// frame (LDL/STL, warp-interleaved 128-byte lines, L1-resident) -- the same role the explicit
+// shared-memory slots play for the 512-bit field of Type A.
+#pragma once
+#include "slots.cuh"
+
+namespace pbcb200 {
+
+constexpr int kNS = 5;         // 32-bit limbs
+constexpr int kWS = 20;        // wire bytes per coordinate (arith/montfp.c:577)
+
+struct Fq { uint32_t v[kNS]; };
+
+__device__ __forceinline__ void fq_mul(Fq& r, const Fq& a, const Fq& b) { mont_mul_ps<kNS, false>(r.v, a.v, b.v); }
+__device__ __forceinline__ void fq_sqr(Fq& r, const Fq& a) { mont_sqr_ps<kNS, false>(r.v, a.v); }
+__device__ __forceinline__ void fq_add(Fq& r, const Fq& a, const Fq& b) { fp_add<kNS, false>(r.v, a.v, b.v); }
+__device__ __forceinline__ void fq_sub(Fq& r, const Fq& a, const Fq& b) { fp_sub<kNS>(r.v, a.v, b.v); }
+__device__ __forceinline__ void fq_dbl(Fq& r, const Fq& a) { fp_add<kNS, false>(r.v, a.v, a.v); }
+__device__ __forceinline__ void fq_neg(Fq& r, const Fq& a) { fp_neg<kNS>(r.v, a.v); }
+__device__ __forceinline__ void fq_halve(Fq& r, const Fq& a) { fp_halve<kNS, false>(r.v, a.v); }
+__device__ __forceinline__ bool fq_is_zero(const Fq& a) { return fp_is_zero<kNS>(a.v); }
+__device__ __forceinline__ bool fq_eq(const Fq& a, const Fq& b) { return fp_eq<kNS>(a.v, b.v); }
+__device__ __forceinline__ void fq_zero(Fq& r) {
+#pragma unroll
+  for (int k = 0; k < kNS; k++) r.v[k] = 0;
+}
+__device__ __forceinline__ void fq_set(Fq& r, const uint32_t* c) {
+#pragma unroll
+  for (int k = 0; k < kNS; k++) r.v[k] = c[k];
+}
+__device__ __forceinline__ void fq_one(Fq& r) { fq_set(r, c_fp.one); }
+
+// wire bytes (big-endian, 20 per coordinate) -> Montgomery form (arith/montfp.c:498-517 reduces mod q)
+__device__ __forceinline__ void fq_from_wire(Fq& r, const uint8_t* p) {
+  limbs_from_be<kNS, kWS>(r.v, p);
+  mont_mul_ps<kNS, false>(r.v, r.v, c_fp.r2);
+}
+// Montgomery form -> canonical residue -> wire bytes (arith/montfp.c:64-80, :487-496)
+__device__ __forceinline__ void fq_to_wire(uint8_t* p, const Fq& a) {
+  uint32_t one[kNS] = {1}, x[kNS];
+  mont_mul_ps<kNS, false>(x, a.v, one);
+  limbs_to_be<kNS, kWS>(p, x);
+}
+
+// a^(q-2) (the reference calls mpz_invert, arith/montfp.c:401-422; the value is the same)
+__device__ __noinline__ void fq_inv(Fq* r, const Fq* a) {
+  Fq x = *a, acc;
+  fq_one(acc);
+  int top = kNS * 32 - 1;
+  while (top > 0 && !((c_fp.pm2[top >> 5] >> (top & 31)) & 1u)) top--;
+  for (int j = top; j >= 0; j--) {
+    fq_sqr(acc, acc);
+    if ((c_fp.pm2[j >> 5] >> (j & 31)) & 1u) fq_mul(acc, acc, x);
+  }
+  *r = acc;
+}
+
+// limb-major batch arrays in global memory: word w of element e of item idx at g[(e*kNS + w)*n + idx]
+__device__ __forceinline__ void fq_st_global(uint32_t* g, int e, size_t n, size_t idx, const Fq& a) {
+#pragma unroll
+  for (int k = 0; k < kNS; k++) g[((size_t)e * kNS + k) * n + idx] = a.v[k];
+}
+__device__ __forceinline__ void fq_ld_global(Fq& a, const uint32_t* g, int e, size_t n, size_t idx) {
+#pragma unroll
+  for (int k = 0; k < kNS; k++) a.v[k] = g[((size_t)e * kNS + k) * n + idx];
+}
+
+}  // namespace pbcb200

@@ -1,0 +1,123 @@
+// miller_cc.cuh -- the Miller loop shared by the Type F and Type D pairings.
+//
+// Device replacement for cc_miller_no_denom (ecc/f_param.c:97-248) and
+// cc_miller_no_denom_affine (ecc/d_param.c:321-422): same loop shape over the bits of r (tangent,
+// double, optional chord + add, square), but the multiples of P are kept in Jacobian coordinates so
+// no step needs a field inversion (the reference inverts once per tangent and once per chord).
+// Each line a X + b Y + c is therefore scaled by some element of F_q^*; the final exponent is a
+// multiple of q - 1, so the reduced pairing is unchanged (tools/proto_fd.py checks exactly this
+// against the oracle).
+//
+//   tangent at V = (X, Y, Z):  M = 3 X^2 + A Z^4
+//        a = -M Z^2,  b = 2 Y Z^3,  c = M X - 2 Y^2                       (affine line times Z^6)
+//   chord through V and P = (xP, yP):
+//        a = Y - yP Z^3,  b = (xP Z^2 - X) Z,  c = yP Z X - xP Y          (affine line times Z^3)
+//   V <- 2V: dbl-2007-bl style with general A;  V <- V + P: mixed Jacobian + affine addition.
+#pragma once
+#include "fq_small.cuh"
+
+namespace pbcb200 {
+
+struct CCConsts {
+  uint32_t A[kNS], B[kNS];     // curve y^2 = x^3 + A x + B over F_q (Montgomery form)
+  uint32_t r[kNS];             // group order (plain integer, little-endian words)
+  uint32_t rbits;
+  uint32_t a_is_zero;
+};
+__constant__ CCConsts c_cc;
+
+// y^2 == x^3 + A x + B  (ecc/curve.c:57-76)
+__device__ __forceinline__ bool cc_on_curve(const Fq& x, const Fq& y) {
+  Fq t, u, A, B;
+  fq_set(A, c_cc.A);
+  fq_set(B, c_cc.B);
+  fq_sqr(t, x);
+  fq_add(t, t, A);
+  fq_mul(t, t, x);
+  fq_add(t, t, B);
+  fq_sqr(u, y);
+  return fq_eq(t, u);
+}
+
+// T supplies:  struct Acc;  struct Ctx;
+//   static void mul_line(Acc* v, const Fq* a, const Fq* b, const Fq* c, const Ctx* ctx);   v *= line
+//   static void sqr(Acc* v);                                                               v  = v^2
+template <class T>
+__device__ __forceinline__ void miller_cc(typename T::Acc* v, const Fq& xP, const Fq& yP,
+                                          const typename T::Ctx* ctx) {
+  Fq X = xP, Y = yP, Z, a, b, c, M, Y2, Z2, t, u;
+  fq_one(Z);
+  int m = (int)c_cc.rbits - 2;
+  for (;;) {
+    // ---- tangent at V ----
+    fq_sqr(Z2, Z);
+    fq_sqr(t, X);
+    fq_dbl(M, t);
+    fq_add(M, M, t);                       // 3 X^2
+    if (!c_cc.a_is_zero) {
+      fq_sqr(u, Z2);
+      fq_set(t, c_cc.A);
+      fq_mul(u, u, t);
+      fq_add(M, M, u);                     // + A Z^4
+    }
+    fq_sqr(Y2, Y);
+    fq_mul(a, M, Z2);
+    fq_neg(a, a);                          // a = -M Z^2
+    fq_mul(u, Y, Z);
+    fq_dbl(u, u);                          // Z' = 2 Y Z
+    fq_mul(b, u, Z2);                      // b = Z' Z^2
+    fq_mul(c, M, X);
+    fq_sub(c, c, Y2);
+    fq_sub(c, c, Y2);                      // c = M X - 2 Y^2
+    T::mul_line(v, &a, &b, &c, ctx);
+    if (m == 0) break;
+    // ---- V = 2 V ----
+    fq_mul(t, X, Y2);
+    fq_dbl(t, t);
+    fq_dbl(t, t);                          // S = 4 X Y^2
+    Z = u;
+    fq_sqr(X, M);
+    fq_sub(X, X, t);
+    fq_sub(X, X, t);                       // X' = M^2 - 2 S
+    fq_sqr(Y2, Y2);
+    fq_dbl(Y2, Y2);
+    fq_dbl(Y2, Y2);
+    fq_dbl(Y2, Y2);                        // 8 Y^4
+    fq_sub(t, t, X);
+    fq_mul(Y, M, t);
+    fq_sub(Y, Y, Y2);                      // Y' = M (S - X') - 8 Y^4
+    if ((c_cc.r[m >> 5] >> (m & 31)) & 1u) {
+      // ---- chord through V and P, then V = V + P ----
+      Fq H, R;
+      fq_sqr(Z2, Z);
+      fq_mul(t, Z2, Z);                    // Z^3
+      fq_mul(H, xP, Z2);
+      fq_sub(H, H, X);                     // H = xP Z^2 - X
+      fq_mul(R, yP, t);
+      fq_sub(a, Y, R);                     // a = Y - yP Z^3
+      fq_sub(R, R, Y);                     // R = yP Z^3 - Y
+      fq_mul(b, H, Z);                     // b = H Z = Z of the sum
+      fq_mul(t, yP, Z);
+      fq_mul(t, t, X);
+      fq_mul(u, xP, Y);
+      fq_sub(c, t, u);                     // c = yP Z X - xP Y
+      T::mul_line(v, &a, &b, &c, ctx);
+      fq_sqr(t, H);                        // H^2
+      fq_mul(u, t, H);                     // H^3
+      fq_mul(t, t, X);                     // X H^2
+      fq_sqr(X, R);
+      fq_sub(X, X, u);
+      fq_sub(X, X, t);
+      fq_sub(X, X, t);                     // X3 = R^2 - H^3 - 2 X H^2
+      fq_sub(t, t, X);
+      fq_mul(t, t, R);
+      fq_mul(u, u, Y);
+      fq_sub(Y, t, u);                     // Y3 = R (X H^2 - X3) - Y H^3
+      Z = b;
+    }
+    m--;
+    T::sqr(v);
+  }
+}
+
+}  // namespace pbcb200

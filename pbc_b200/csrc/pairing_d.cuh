@@ -1,0 +1,359 @@
+// pairing_d.cuh -- Type D pairing kernels (MNT curve y^2 = x^3 + a x + b, k = 6, 159-bit q).
+//
+// Device replacement for ecc/d_param.c: cc_pairing (:570-587), cc_miller_no_denom_affine
+// (:321-422), d_miller_evalfn (:99-111), cc_tatepower (:505-564), lucas_even (:441-502),
+// cc_pairings_affine (:710-736), on the tower F_q^3 = F_q[x]/(x^3 + c2 x^2 + c1 x + c0)
+// (arith/poly.c:870-930, 1049-1089, 1302-1333) and F_q^6 = F_q^3[w]/(w^2 - v), v in F_q
+// (arith/fieldquadratic.c:197-309).  Same representation as the reference (the 120 output bytes are
+// the coefficients as they stand); the Miller loop is inversion-free (miller_cc.cuh) and the
+// extension-field inversions go down to a single F_q inversion each by way of the Frobenius
+// constants x^q, x^(2q) the reference already computes (ecc/d_param.c:1043-1049).
+#pragma once
+#include "miller_cc.cuh"
+
+namespace pbcb200 {
+
+struct F3 { Fq c[3]; };            // c0 + c1 x + c2 x^2
+struct F6D { F3 a, b; };           // a + b w,  w^2 = v
+
+struct DConsts {
+  uint32_t xpwr3[3][kNS];          // x^3 mod the field polynomial (arith/poly.c:1302-1333)
+  uint32_t xpwr4[3][kNS];          // x^4
+  uint32_t xpowq[3][kNS];          // x^q      (ecc/d_param.c:1043-1049)
+  uint32_t xpowq2[3][kNS];         // x^(2q)
+  uint32_t nqr[kNS];               // v
+  uint32_t nqrinv[kNS];            // 1/v    : untwisting factors (ecc/d_param.c:576-582)
+  uint32_t nqrinv2[kNS];           // 1/v^2
+  uint32_t twist_a[kNS];           // a v^2, b v^3: G2 curve over F_q^3 (ecc/curve.c:885-892)
+  uint32_t twist_b[kNS];
+  uint32_t two[kNS];               // Montgomery 2
+  uint32_t phikonr[8];             // (q^2 - q + 1)/r, plain integer (ecc/d_param.c:1035-1041)
+  uint32_t phibits;
+  uint32_t pad[3];
+};
+__constant__ DConsts c_d;
+
+// ---------------------------------------------------------------------------------------------
+// F_q^3
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void f3_add(F3& r, const F3& x, const F3& y) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) fq_add(r.c[i], x.c[i], y.c[i]);
+}
+__device__ __forceinline__ void f3_sub(F3& r, const F3& x, const F3& y) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) fq_sub(r.c[i], x.c[i], y.c[i]);
+}
+__device__ __forceinline__ void f3_neg(F3& r, const F3& x) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) fq_neg(r.c[i], x.c[i]);
+}
+__device__ __forceinline__ void f3_zero(F3& r) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) fq_zero(r.c[i]);
+}
+__device__ __forceinline__ void f3_set(F3& r, const uint32_t c[3][kNS]) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) fq_set(r.c[i], c[i]);
+}
+__device__ __forceinline__ bool f3_eq(const F3& x, const F3& y) {
+  return fq_eq(x.c[0], y.c[0]) && fq_eq(x.c[1], y.c[1]) && fq_eq(x.c[2], y.c[2]);
+}
+__device__ __forceinline__ void f3_scale(F3& r, const F3& x, const Fq& k) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) fq_mul(r.c[i], x.c[i], k);
+}
+
+// degree-4 product d0..d4 folded with the x^3, x^4 rows (polymod_mul_degree3, arith/poly.c:870-930)
+__device__ __forceinline__ void f3_reduce(F3* r, const Fq& d0, const Fq& d1, const Fq& d2, const Fq& d3,
+                                          const Fq& d4) {
+  Fq t, k;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const Fq& lo = i == 0 ? d0 : (i == 1 ? d1 : d2);
+    fq_set(k, c_d.xpwr3[i]);
+    fq_mul(t, d3, k);
+    fq_add(r->c[i], lo, t);
+    fq_set(k, c_d.xpwr4[i]);
+    fq_mul(t, d4, k);
+    fq_add(r->c[i], r->c[i], t);
+  }
+}
+__device__ __noinline__ void f3_mul(F3* r, const F3* x, const F3* y) {
+  Fq d0, d1, d2, d3, d4, m1, s, t;
+  fq_mul(d0, x->c[0], y->c[0]);
+  fq_mul(m1, x->c[1], y->c[1]);
+  fq_mul(d4, x->c[2], y->c[2]);
+  fq_add(s, x->c[0], x->c[1]);
+  fq_add(t, y->c[0], y->c[1]);
+  fq_mul(d1, s, t);
+  fq_sub(d1, d1, d0);
+  fq_sub(d1, d1, m1);
+  fq_add(s, x->c[1], x->c[2]);
+  fq_add(t, y->c[1], y->c[2]);
+  fq_mul(d3, s, t);
+  fq_sub(d3, d3, m1);
+  fq_sub(d3, d3, d4);
+  fq_add(s, x->c[0], x->c[2]);
+  fq_add(t, y->c[0], y->c[2]);
+  fq_mul(d2, s, t);
+  fq_sub(d2, d2, d0);
+  fq_sub(d2, d2, d4);
+  fq_add(d2, d2, m1);
+  f3_reduce(r, d0, d1, d2, d3, d4);
+}
+__device__ __noinline__ void f3_sqr(F3* r, const F3* x) {
+  Fq d0, d1, d2, d3, d4, t;
+  fq_sqr(d0, x->c[0]);
+  fq_sqr(d4, x->c[2]);
+  fq_mul(d1, x->c[0], x->c[1]);
+  fq_dbl(d1, d1);
+  fq_mul(d3, x->c[1], x->c[2]);
+  fq_dbl(d3, d3);
+  fq_mul(d2, x->c[0], x->c[2]);
+  fq_dbl(d2, d2);
+  fq_sqr(t, x->c[1]);
+  fq_add(d2, d2, t);
+  f3_reduce(r, d0, d1, d2, d3, d4);
+}
+// (c0 + c1 x + c2 x^2)^q = c0 + c1 x^q + c2 x^(2q)   (ecc/d_param.c:507-513)
+__device__ __forceinline__ void f3_frob(F3& r, const F3& x) {
+  F3 t, u;
+  f3_set(t, c_d.xpowq);
+  f3_scale(t, t, x.c[1]);
+  f3_set(u, c_d.xpowq2);
+  f3_scale(u, u, x.c[2]);
+  f3_add(t, t, u);
+  fq_add(r.c[0], t.c[0], x.c[0]);
+  r.c[1] = t.c[1];
+  r.c[2] = t.c[2];
+}
+// 1/x = x^q x^(q^2) / N(x)   (the reference runs a polynomial ext-Euclid, arith/poly.c:454-536)
+__device__ __noinline__ void f3_inv(F3* r, const F3* x) {
+  F3 t, u;
+  f3_frob(t, *x);
+  f3_frob(u, t);
+  f3_mul(&t, &t, &u);
+  f3_mul(&u, &t, x);              // the norm: only coefficient 0 is non-zero
+  Fq n;
+  fq_inv(&n, &u.c[0]);
+  f3_scale(*r, t, n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// F_q^6 = F_q^3[w]/(w^2 - v)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void f3_mul_v(F3& r, const F3& x) {
+  Fq v;
+  fq_set(v, c_d.nqr);
+  f3_scale(r, x, v);
+}
+__device__ __noinline__ void f6d_mul(F6D* r, const F6D* x, const F6D* y) {
+  F3 t0, t1, t2, s;
+  f3_add(t2, x->a, x->b);
+  f3_add(s, y->a, y->b);
+  f3_mul(&t2, &t2, &s);
+  f3_mul(&t0, &x->a, &y->a);
+  f3_mul(&t1, &x->b, &y->b);
+  f3_sub(t2, t2, t0);
+  f3_sub(t2, t2, t1);
+  f3_mul_v(t1, t1);
+  f3_add(r->a, t0, t1);
+  r->b = t2;
+}
+// (a + b w)^2 = (a + b)(a + v b) - ab - v ab + 2ab w
+__device__ __noinline__ void f6d_sqr(F6D* r) {
+  F3 t0, t1, t2;
+  f3_mul(&t0, &r->a, &r->b);
+  f3_mul_v(t1, r->b);
+  f3_add(t1, t1, r->a);
+  f3_add(t2, r->a, r->b);
+  f3_mul(&t2, &t2, &t1);
+  f3_sub(t2, t2, t0);
+  f3_mul_v(t1, t0);
+  f3_sub(r->a, t2, t1);
+  f3_add(r->b, t0, t0);
+}
+__device__ __noinline__ void f6d_inv(F6D* r, const F6D* x) {
+  F3 t0, t1;
+  f3_sqr(&t0, &x->a);
+  f3_sqr(&t1, &x->b);
+  f3_mul_v(t1, t1);
+  f3_sub(t0, t0, t1);
+  f3_inv(&t0, &t0);
+  f3_mul(&r->a, &x->a, &t0);
+  f3_mul(&t1, &x->b, &t0);
+  f3_neg(r->b, t1);
+}
+__device__ __forceinline__ void f6d_one(F6D& r) {
+  f3_zero(r.a);
+  f3_zero(r.b);
+  fq_one(r.a.c[0]);
+}
+
+struct DTower {
+  typedef F6D Acc;
+  struct Ctx { F3 Qx, Qy; };
+  // v *= (a Qx + c) + (b Qy) w   (d_miller_evalfn, ecc/d_param.c:99-111)
+  static __device__ __forceinline__ void mul_line(F6D* v, const Fq* a, const Fq* b, const Fq* c,
+                                                  const Ctx* q) {
+    F6D l;
+    f3_scale(l.a, q->Qx, *a);
+    fq_add(l.a.c[0], l.a.c[0], *c);
+    f3_scale(l.b, q->Qy, *b);
+    f6d_mul(v, v, &l);
+  }
+  static __device__ __forceinline__ void sqr(F6D* v) { f6d_sqr(v); }
+};
+
+constexpr int kF6DWords = 6 * kNS;
+
+__device__ __forceinline__ void f6d_st_global(uint32_t* g, size_t n, size_t idx, const F6D& v) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    fq_st_global(g, i, n, idx, v.a.c[i]);
+    fq_st_global(g, 3 + i, n, idx, v.b.c[i]);
+  }
+}
+__device__ __forceinline__ void f6d_ld_global(F6D& v, const uint32_t* g, size_t n, size_t idx) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    fq_ld_global(v.a.c[i], g, i, n, idx);
+    fq_ld_global(v.b.c[i], g, 3 + i, n, idx);
+  }
+}
+
+// P: 40 bytes each (stride1 = 0 shares one P), Q: n x 120 bytes (x: 3 coefficients, y: 3).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_d_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_t* __restrict__ mv,
+           uint32_t* __restrict__ flag, size_t n, size_t stride1) {
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  Fq xP, yP;
+  const uint8_t* p = P + idx * stride1;
+  fq_from_wire(xP, p);
+  fq_from_wire(yP, p + kWS);
+  bool ok = cc_on_curve(xP, yP);
+  DTower::Ctx ctx;
+  const uint8_t* q = Q + idx * (6 * kWS);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    fq_from_wire(ctx.Qx.c[i], q + i * kWS);
+    fq_from_wire(ctx.Qy.c[i], q + (3 + i) * kWS);
+  }
+  {
+    // Y^2 == X^3 + (a v^2) X + b v^3 over F_q^3 (ecc/curve.c:57-76)
+    F3 t, u;
+    Fq k;
+    f3_sqr(&t, &ctx.Qx);
+    fq_set(k, c_d.twist_a);
+    fq_add(t.c[0], t.c[0], k);
+    f3_mul(&t, &t, &ctx.Qx);
+    fq_set(k, c_d.twist_b);
+    fq_add(t.c[0], t.c[0], k);
+    f3_sqr(&u, &ctx.Qy);
+    ok = ok && f3_eq(t, u);
+    // untwist: Qx / v, Qy / v^2 (ecc/d_param.c:576-582)
+    fq_set(k, c_d.nqrinv);
+    f3_scale(ctx.Qx, ctx.Qx, k);
+    fq_set(k, c_d.nqrinv2);
+    f3_scale(ctx.Qy, ctx.Qy, k);
+  }
+  F6D v;
+  f6d_one(v);
+  if (ok) miller_cc<DTower>(&v, xP, yP, &ctx);
+  f6d_st_global(mv, n, idx, v);
+  flag[idx] = ok ? 1u : 0u;
+}
+
+// cc_pairings_affine (ecc/d_param.c:710-736): product of the k Miller values, one final power.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_d_prod(const uint32_t* __restrict__ mv_in, const uint32_t* __restrict__ flag_in,
+         uint32_t* __restrict__ mv_out, uint32_t* __restrict__ flag_out, size_t k, size_t n_out,
+         size_t n_in) {
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n_out) return;
+  F6D acc, t;
+  f6d_ld_global(acc, mv_in, n_in, idx * k);
+  bool ok = flag_in[idx * k] != 0;
+  for (size_t j = 1; j < k; j++) {
+    f6d_ld_global(t, mv_in, n_in, idx * k + j);
+    ok = ok && flag_in[idx * k + j] != 0;
+    f6d_mul(&acc, &acc, &t);
+  }
+  f6d_st_global(mv_out, n_out, idx, acc);
+  flag_out[idx] = ok ? 1u : 0u;
+}
+
+// cc_tatepower, k = 6 branch (ecc/d_param.c:505-564) + lucas_even (:441-502).
+// out: n x 120 bytes: real half (3 coefficients) then imaginary half.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_d_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
+             uint8_t* __restrict__ out, size_t n) {
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  F6D f, e0, e3;
+  F3 out0, out1;
+  if (flag[idx]) {
+    f6d_ld_global(f, mv, n, idx);
+    f3_frob(e3.a, f.a);
+    f3_frob(e3.b, f.b);                  // qpower(1)
+    e0.a = f.a;
+    f3_neg(e0.b, f.b);                   // conjugate = f^(q^3)
+    f6d_mul(&e3, &e3, &e0);
+    f3_frob(e0.a, f.a);
+    f3_frob(e0.b, f.b);
+    f3_neg(e0.b, e0.b);                  // qpower(-1)
+    f6d_mul(&e0, &e0, &f);
+    f6d_inv(&e0, &e0);
+    f6d_mul(&f, &e3, &e0);
+    // lucas_even on in = f: t0 = 2, t1 = 2 in0
+    F3 t1, v0, v1, tmp, two;
+    f3_zero(two);
+    fq_set(two.c[0], c_d.two);
+    f3_add(t1, f.a, f.a);
+    v0 = two;
+    v1 = t1;
+    for (int j = (int)c_d.phibits - 1; j >= 0; j--) {
+      bool bit = j > 0 && ((c_d.phikonr[j >> 5] >> (j & 31)) & 1u);   // last step: clear branch
+      f3_mul(&tmp, &v0, &v1);
+      f3_sub(tmp, tmp, t1);
+      if (bit) {
+        v0 = tmp;
+        f3_sqr(&v1, &v1);
+        f3_sub(v1, v1, two);
+      } else {
+        v1 = tmp;
+        f3_sqr(&v0, &v0);
+        f3_sub(v0, v0, two);
+      }
+    }
+    f3_add(v0, v0, v0);
+    f3_mul(&tmp, &t1, &v1);
+    f3_sub(tmp, tmp, v0);
+    F3 d;
+    f3_sqr(&d, &t1);
+    f3_sub(d, d, two);
+    f3_sub(d, d, two);
+    f3_inv(&d, &d);
+#pragma unroll
+    for (int i = 0; i < 3; i++) fq_halve(out0.c[i], v1.c[i]);
+    f3_mul(&tmp, &tmp, &d);
+    f3_mul(&out1, &tmp, &f.b);
+  } else {
+    f3_zero(out0);
+    f3_zero(out1);
+    fq_one(out0.c[0]);
+  }
+  uint8_t* o = out + idx * (6 * kWS);
+#pragma unroll 1
+  for (int i = 0; i < 3; i++) {
+    fq_to_wire(o + i * kWS, out0.c[i]);
+    fq_to_wire(o + (3 + i) * kWS, out1.c[i]);
+  }
+}
+
+}  // namespace pbcb200

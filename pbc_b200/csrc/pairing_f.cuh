@@ -1,0 +1,408 @@
+// pairing_f.cuh -- Type F pairing kernels (BN curve y^2 = x^3 + b, k = 12, 158-bit q).
+//
+// Device replacement for ecc/f_param.c: f_pairing (:289-311), cc_miller_no_denom (:97-248),
+// f_tateexp (:250-283) and the tower it runs on -- F_q^2 = F_q[s]/(s^2 - beta)
+// (arith/fieldquadratic.c:197-309) and F_q^12 = F_q^2[x]/(x^6 + alpha) (arith/poly.c:932-1143).
+// Same field representation as the reference (so the 240 output bytes are the coefficients as
+// they stand), different multiplication schedules:
+//   * F_q^12 is multiplied as the quadratic extension F_q^6[x]/(x^2 - y) of
+//     F_q^6 = F_q^2[y]/(y^3 - xi), xi = -alpha, y = x^2: even coefficients form the "real" F_q^6
+//     half, odd coefficients the "imaginary" half.  mul = 3 Karatsuba F_q^6 products, square =
+//     2 (complex squaring).  The reference uses one degree-6 Karatsuba + table reduction (mul) and
+//     a schoolbook square.
+//   * the Miller line c + (b Qy) x^3 + (a Qx) x^4 is multiplied in sparsely: 12 F_q^2 products.
+//   * the Miller loop is inversion-free (miller_cc.cuh); the one F_q^12 inversion of the final
+//     exponentiation goes down the tower to a single F_q inversion.
+// Kernels: k_f_miller (one pairing per thread, Miller value to the workspace), k_f_prod (products
+// of k Miller values), k_f_finalexp.
+#pragma once
+#include "miller_cc.cuh"
+
+namespace pbcb200 {
+
+struct F2 { Fq a, b; };            // a + b s,  s^2 = beta
+struct F12 { F2 c[6]; };           // sum c[i] x^i,  x^6 = xi = -alpha
+
+struct FConsts {
+  uint32_t beta[kNS];              // quadratic non-residue of F_q (Montgomery form)
+  uint32_t xi[2][kNS];             // -alpha in F_q^2
+  uint32_t xi_inv[2][kNS];         // 1 / (-alpha): untwisting factor (ecc/f_param.c:296-303)
+  uint32_t twist_b[2][kNS];        // -alpha * b: G2 curve Y^2 = X^3 + twist_b (:367-378)
+  uint32_t xpowq2[2][kNS];         // x^(q^2) = xpowq2 * x   (:422-444)
+  uint32_t xpowq6[2][kNS];
+  uint32_t xpowq8[2][kNS];
+  uint32_t tateexp[16];            // (q^4 - q^2 + 1) / r   (:408-420), plain integer
+  uint32_t tatebits;
+  uint32_t pad[3];
+};
+__constant__ FConsts c_f;
+
+// ---------------------------------------------------------------------------------------------
+// F_q^2  (arith/fieldquadratic.c:197-309 fq_*)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void f2_set(F2& r, const uint32_t c[2][kNS]) { fq_set(r.a, c[0]); fq_set(r.b, c[1]); }
+__device__ __forceinline__ void f2_add(F2& r, const F2& x, const F2& y) { fq_add(r.a, x.a, y.a); fq_add(r.b, x.b, y.b); }
+__device__ __forceinline__ void f2_sub(F2& r, const F2& x, const F2& y) { fq_sub(r.a, x.a, y.a); fq_sub(r.b, x.b, y.b); }
+__device__ __forceinline__ void f2_dbl(F2& r, const F2& x) { fq_dbl(r.a, x.a); fq_dbl(r.b, x.b); }
+__device__ __forceinline__ void f2_neg(F2& r, const F2& x) { fq_neg(r.a, x.a); fq_neg(r.b, x.b); }
+__device__ __forceinline__ void f2_zero(F2& r) { fq_zero(r.a); fq_zero(r.b); }
+__device__ __forceinline__ bool f2_eq(const F2& x, const F2& y) { return fq_eq(x.a, y.a) && fq_eq(x.b, y.b); }
+
+// (x0 + x1 s)(y0 + y1 s) = x0 y0 + beta x1 y1 + ((x0 + x1)(y0 + y1) - x0 y0 - x1 y1) s
+__device__ __noinline__ void f2_mul(F2* r, const F2* x, const F2* y) {
+  Fq t0, t1, t2, u;
+  fq_add(t2, x->a, x->b);
+  fq_add(u, y->a, y->b);
+  fq_mul(t2, t2, u);
+  fq_mul(t0, x->a, y->a);
+  fq_mul(t1, x->b, y->b);
+  fq_sub(t2, t2, t0);
+  fq_sub(t2, t2, t1);
+  fq_set(u, c_f.beta);
+  fq_mul(t1, t1, u);
+  fq_add(r->a, t0, t1);
+  r->b = t2;
+}
+// x0^2 + beta x1^2 + 2 x0 x1 s
+__device__ __noinline__ void f2_sqr(F2* r, const F2* x) {
+  Fq t0, t1, t2, u;
+  fq_mul(t2, x->a, x->b);
+  fq_sqr(t0, x->a);
+  fq_sqr(t1, x->b);
+  fq_set(u, c_f.beta);
+  fq_mul(t1, t1, u);
+  fq_add(r->a, t0, t1);
+  fq_dbl(r->b, t2);
+}
+// multiplication by an element of F_q
+__device__ __forceinline__ void f2_scale(F2& r, const F2& x, const Fq& k) { fq_mul(r.a, x.a, k); fq_mul(r.b, x.b, k); }
+__device__ __forceinline__ void f2_mul_xi(F2& r, const F2& x) {
+  F2 xi;
+  f2_set(xi, c_f.xi);
+  f2_mul(&r, &x, &xi);
+}
+// 1/(x0 + x1 s) = (x0 - x1 s)/(x0^2 - beta x1^2)   (arith/fieldquadratic.c:290-309)
+__device__ __noinline__ void f2_inv(F2* r, const F2* x) {
+  Fq t0, t1, u;
+  fq_sqr(t0, x->a);
+  fq_sqr(t1, x->b);
+  fq_set(u, c_f.beta);
+  fq_mul(t1, t1, u);
+  fq_sub(t0, t0, t1);
+  fq_inv(&t0, &t0);
+  fq_mul(r->a, x->a, t0);
+  fq_mul(t1, x->b, t0);
+  fq_neg(r->b, t1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// F_q^6 = F_q^2[y]/(y^3 - xi) on three strided coefficients of an F12 (stride 2: y = x^2)
+// ---------------------------------------------------------------------------------------------
+struct F6 { F2 c[3]; };
+
+// Karatsuba: 6 F_q^2 products + 2 multiplications by xi
+__device__ __noinline__ void f6_mul(F6* r, const F6* a, const F6* b) {
+  F2 v0, v1, v2, s, t, u;
+  f2_mul(&v0, &a->c[0], &b->c[0]);
+  f2_mul(&v1, &a->c[1], &b->c[1]);
+  f2_mul(&v2, &a->c[2], &b->c[2]);
+  // c0 = v0 + xi ((a1 + a2)(b1 + b2) - v1 - v2)
+  f2_add(s, a->c[1], a->c[2]);
+  f2_add(t, b->c[1], b->c[2]);
+  f2_mul(&u, &s, &t);
+  f2_sub(u, u, v1);
+  f2_sub(u, u, v2);
+  f2_mul_xi(u, u);
+  F2 c0;
+  f2_add(c0, v0, u);
+  // c1 = (a0 + a1)(b0 + b1) - v0 - v1 + xi v2
+  f2_add(s, a->c[0], a->c[1]);
+  f2_add(t, b->c[0], b->c[1]);
+  f2_mul(&u, &s, &t);
+  f2_sub(u, u, v0);
+  f2_sub(u, u, v1);
+  F2 c1;
+  f2_mul_xi(c1, v2);
+  f2_add(c1, c1, u);
+  // c2 = (a0 + a2)(b0 + b2) - v0 - v2 + v1
+  f2_add(s, a->c[0], a->c[2]);
+  f2_add(t, b->c[0], b->c[2]);
+  f2_mul(&u, &s, &t);
+  f2_sub(u, u, v0);
+  f2_sub(u, u, v2);
+  f2_add(r->c[2], u, v1);
+  r->c[0] = c0;
+  r->c[1] = c1;
+}
+__device__ __forceinline__ void f6_add(F6& r, const F6& a, const F6& b) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) f2_add(r.c[i], a.c[i], b.c[i]);
+}
+__device__ __forceinline__ void f6_sub(F6& r, const F6& a, const F6& b) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) f2_sub(r.c[i], a.c[i], b.c[i]);
+}
+// r = y a:  (a0, a1, a2) -> (xi a2, a0, a1)
+__device__ __forceinline__ void f6_mul_y(F6& r, const F6& a) {
+  F2 t;
+  f2_mul_xi(t, a.c[2]);
+  r.c[2] = a.c[1];
+  r.c[1] = a.c[0];
+  r.c[0] = t;
+}
+// 1/a via the norm to F_q^2:  with A = a0^2 - xi a1 a2, B = xi a2^2 - a0 a1, C = a1^2 - a0 a2,
+//   a (A + B y + C y^2) = a0 A + xi (a2 B + a1 C)  in F_q^2
+__device__ __noinline__ void f6_inv(F6* r, const F6* a) {
+  F2 A, B, C, t, u;
+  f2_sqr(&A, &a->c[0]);
+  f2_mul(&t, &a->c[1], &a->c[2]);
+  f2_mul_xi(t, t);
+  f2_sub(A, A, t);
+  f2_sqr(&B, &a->c[2]);
+  f2_mul_xi(B, B);
+  f2_mul(&t, &a->c[0], &a->c[1]);
+  f2_sub(B, B, t);
+  f2_sqr(&C, &a->c[1]);
+  f2_mul(&t, &a->c[0], &a->c[2]);
+  f2_sub(C, C, t);
+  f2_mul(&t, &a->c[2], &B);
+  f2_mul(&u, &a->c[1], &C);
+  f2_add(t, t, u);
+  f2_mul_xi(t, t);
+  f2_mul(&u, &a->c[0], &A);
+  f2_add(t, t, u);
+  f2_inv(&t, &t);
+  f2_mul(&r->c[0], &A, &t);
+  f2_mul(&r->c[1], &B, &t);
+  f2_mul(&r->c[2], &C, &t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// F_q^12 = F_q^6[x]/(x^2 - y): even coefficients = real half, odd = imaginary half
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void f12_split(F6& re, F6& im, const F12& v) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) { re.c[i] = v.c[2 * i]; im.c[i] = v.c[2 * i + 1]; }
+}
+__device__ __forceinline__ void f12_join(F12& v, const F6& re, const F6& im) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) { v.c[2 * i] = re.c[i]; v.c[2 * i + 1] = im.c[i]; }
+}
+__device__ __forceinline__ void f12_one(F12& v) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) f2_zero(v.c[i]);
+  fq_one(v.c[0].a);
+}
+
+// (A + B x)(C + D x) = AC + y BD + ((A + B)(C + D) - AC - BD) x
+__device__ __noinline__ void f12_mul(F12* r, const F12* p, const F12* q) {
+  F6 A, B, C, D, t0, t1, t2;
+  f12_split(A, B, *p);
+  f12_split(C, D, *q);
+  f6_mul(&t0, &A, &C);
+  f6_mul(&t1, &B, &D);
+  f6_add(A, A, B);
+  f6_add(C, C, D);
+  f6_mul(&t2, &A, &C);
+  f6_sub(t2, t2, t0);
+  f6_sub(t2, t2, t1);
+  f6_mul_y(t1, t1);
+  f6_add(t0, t0, t1);
+  f12_join(*r, t0, t2);
+}
+// (A + B x)^2 = (A + B)(A + y B) - AB - y AB + 2 AB x
+__device__ __noinline__ void f12_sqr(F12* v) {
+  F6 A, B, t0, t1, t2;
+  f12_split(A, B, *v);
+  f6_mul(&t0, &A, &B);
+  f6_mul_y(t1, B);
+  f6_add(t1, t1, A);
+  f6_add(A, A, B);
+  f6_mul(&t2, &A, &t1);
+  f6_sub(t2, t2, t0);
+  f6_mul_y(t1, t0);
+  f6_sub(t2, t2, t1);
+  f6_add(t0, t0, t0);
+  f12_join(*v, t2, t0);
+}
+// 1/(A + B x) = (A - B x)/(A^2 - y B^2)
+__device__ __noinline__ void f12_inv(F12* r, const F12* p) {
+  F6 A, B, t0, t1;
+  f12_split(A, B, *p);
+  f6_mul(&t0, &A, &A);
+  f6_mul(&t1, &B, &B);
+  f6_mul_y(t1, t1);
+  f6_sub(t0, t0, t1);
+  f6_inv(&t0, &t0);
+  f6_mul(&A, &A, &t0);
+  f6_mul(&B, &B, &t0);
+#pragma unroll
+  for (int i = 0; i < 3; i++) f2_neg(B.c[i], B.c[i]);
+  f12_join(*r, A, B);
+}
+
+// v *= c + L3 x^3 + L4 x^4, c in F_q (the Miller line, ecc/f_param.c:109-149)
+//   out_k = c v_k + L3 v_{k-3} + L4 v_{k-4}, indices mod 6, a wrap multiplies by xi
+__device__ __noinline__ void f12_mul_line(F12* v, const Fq* c, const F2* L3, const F2* L4) {
+  F2 X3, X4, t, u;
+  F12 o;
+  f2_mul_xi(X3, *L3);
+  f2_mul_xi(X4, *L4);
+#pragma unroll 1
+  for (int k = 0; k < 6; k++) {
+    int i3 = k >= 3 ? k - 3 : k + 3, i4 = k >= 4 ? k - 4 : k + 2;
+    f2_mul(&t, k >= 3 ? L3 : &X3, &v->c[i3]);
+    f2_mul(&u, k >= 4 ? L4 : &X4, &v->c[i4]);
+    f2_add(t, t, u);
+    f2_scale(u, v->c[k], *c);
+    f2_add(o.c[k], t, u);
+  }
+  *v = o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Miller loop plumbing
+// ---------------------------------------------------------------------------------------------
+struct FTower {
+  typedef F12 Acc;
+  struct Ctx { F2 Qx, Qy; };     // untwisted second argument
+  static __device__ __forceinline__ void mul_line(F12* v, const Fq* a, const Fq* b, const Fq* c,
+                                                  const Ctx* q) {
+    F2 L3, L4;
+    f2_scale(L3, q->Qy, *b);
+    f2_scale(L4, q->Qx, *a);
+    f12_mul_line(v, c, &L3, &L4);
+  }
+  static __device__ __forceinline__ void sqr(F12* v) { f12_sqr(v); }
+};
+
+constexpr int kF12Words = 12 * kNS;    // 60 words per Miller value in the workspace
+
+__device__ __forceinline__ void f12_st_global(uint32_t* g, size_t n, size_t idx, const F12& v) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    fq_st_global(g, 2 * i, n, idx, v.c[i].a);
+    fq_st_global(g, 2 * i + 1, n, idx, v.c[i].b);
+  }
+}
+__device__ __forceinline__ void f12_ld_global(F12& v, const uint32_t* g, size_t n, size_t idx) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    fq_ld_global(v.c[i].a, g, 2 * i, n, idx);
+    fq_ld_global(v.c[i].b, g, 2 * i + 1, n, idx);
+  }
+}
+
+// P: n1 x 40 bytes (stride1 = 0 shares one P: pairing_pp_*), Q: n x 80 bytes.
+// mv: [60][n] words, flag[n]: 1 = both inputs finite points on their curves.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_f_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_t* __restrict__ mv,
+           uint32_t* __restrict__ flag, size_t n, size_t stride1) {
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  Fq xP, yP;
+  const uint8_t* p = P + idx * stride1;
+  fq_from_wire(xP, p);
+  fq_from_wire(yP, p + kWS);
+  bool ok = cc_on_curve(xP, yP);
+  FTower::Ctx ctx;
+  const uint8_t* q = Q + idx * (4 * kWS);
+  fq_from_wire(ctx.Qx.a, q);
+  fq_from_wire(ctx.Qx.b, q + kWS);
+  fq_from_wire(ctx.Qy.a, q + 2 * kWS);
+  fq_from_wire(ctx.Qy.b, q + 3 * kWS);
+  {
+    // Y^2 == X^3 + twist_b on the twist (ecc/curve.c:57-76 over F_q^2)
+    F2 t, u, tb;
+    f2_sqr(&t, &ctx.Qx);
+    f2_mul(&t, &t, &ctx.Qx);
+    f2_set(tb, c_f.twist_b);
+    f2_add(t, t, tb);
+    f2_sqr(&u, &ctx.Qy);
+    ok = ok && f2_eq(t, u);
+    // untwist (ecc/f_param.c:296-303)
+    f2_set(tb, c_f.xi_inv);
+    f2_mul(&ctx.Qx, &ctx.Qx, &tb);
+    f2_mul(&ctx.Qy, &ctx.Qy, &tb);
+  }
+  F12 v;
+  f12_one(v);
+  if (ok) miller_cc<FTower>(&v, xP, yP, &ctx);
+  f12_st_global(mv, n, idx, v);
+  flag[idx] = ok ? 1u : 0u;
+}
+
+// generic_prod_pairings (ecc/pairing.c:35-46) multiplies k complete pairings; the final
+// exponentiation is a homomorphism, so the k Miller values are multiplied here and exponentiated
+// once.  Any O input -> identity (include/pbc_pairing.h:161-168).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_f_prod(const uint32_t* __restrict__ mv_in, const uint32_t* __restrict__ flag_in,
+         uint32_t* __restrict__ mv_out, uint32_t* __restrict__ flag_out, size_t k, size_t n_out,
+         size_t n_in) {
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n_out) return;
+  F12 acc, t;
+  bool ok = true;
+  f12_ld_global(acc, mv_in, n_in, idx * k);
+  ok = flag_in[idx * k] != 0;
+  for (size_t j = 1; j < k; j++) {
+    f12_ld_global(t, mv_in, n_in, idx * k + j);
+    ok = ok && flag_in[idx * k + j] != 0;
+    f12_mul(&acc, &acc, &t);
+  }
+  f12_st_global(mv_out, n_out, idx, acc);
+  flag_out[idx] = ok ? 1u : 0u;
+}
+
+// coefficient i scaled by e^i (ecc/f_param.c:257-268 qpower)
+__device__ __forceinline__ void f12_qpower(F12& r, const F12& f, const uint32_t e[2][kNS]) {
+  F2 ep, e1;
+  f2_set(e1, e);
+  ep = e1;
+  r.c[0] = f.c[0];
+#pragma unroll 1
+  for (int i = 1; i < 6; i++) {
+    f2_mul(&r.c[i], &f.c[i], &ep);
+    if (i < 5) f2_mul(&ep, &ep, &e1);
+  }
+}
+
+// f_tateexp (ecc/f_param.c:250-283): f^((q^6 - 1)(q^2 + 1)) by Frobenius constants and one
+// inversion, then the 472-bit power (q^4 - q^2 + 1)/r.  out: n x 240 bytes, coefficient order
+// x^0..x^5, each (re, im) (arith/poly.c:718-727, arith/fieldquadratic.c:323-329).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_f_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
+             uint8_t* __restrict__ out, size_t n) {
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  F12 f, x, y, acc;
+  if (flag[idx]) {
+    f12_ld_global(f, mv, n, idx);
+    f12_qpower(y, f, c_f.xpowq8);
+    f12_qpower(x, f, c_f.xpowq6);
+    f12_mul(&y, &y, &x);                 // f^(q^8 + q^6)
+    f12_qpower(x, f, c_f.xpowq2);
+    f12_mul(&x, &x, &f);                 // f^(q^2 + 1)
+    f12_inv(&x, &x);
+    f12_mul(&f, &y, &x);
+    // generic_pow_mpz's sliding window (arith/field.c:14-126) computes the same power
+    acc = f;
+    for (int j = (int)c_f.tatebits - 2; j >= 0; j--) {
+      f12_sqr(&acc);
+      if ((c_f.tateexp[j >> 5] >> (j & 31)) & 1u) f12_mul(&acc, &acc, &f);
+    }
+  } else {
+    f12_one(acc);
+  }
+  uint8_t* o = out + idx * (12 * kWS);
+#pragma unroll 1
+  for (int i = 0; i < 6; i++) {
+    fq_to_wire(o + (2 * i) * kWS, acc.c[i].a);
+    fq_to_wire(o + (2 * i + 1) * kWS, acc.c[i].b);
+  }
+}
+
+}  // namespace pbcb200

@@ -64,3 +64,38 @@ def test_no_gpu_means_loud_failure(built):
     p = built.Pairing(PARAMS["a"])
     with pytest.raises(built.PairingError, match="CUDA"):
         p.apply(b"\0" * 128, b"\0" * 128, 1)
+
+
+def test_init_types_f_and_d_lengths(built):
+    from pbc_b200.params import PARAMS
+    f = built.Pairing(PARAMS["f"])
+    assert (f.type, f.g1_len, f.g2_len, f.gt_len) == ("f", 40, 80, 240)
+    d = built.Pairing(PARAMS["d159"])
+    assert (d.type, d.g1_len, d.g2_len, d.gt_len) == ("d", 40, 120, 120)
+    with pytest.raises(built.PairingError, match="k = "):
+        built.Pairing(PARAMS["d159"].replace("\nk 6\n", "\nk 4\n"))
+
+
+def test_derived_constants_match_oracle(built):
+    """f_init_pairing / d_init_pairing constants (ecc/f_param.c:408-444, ecc/d_param.c:1035-1049)
+    derived by the library's own host big-integer code vs the oracle's restatement."""
+    from pbc_b200.params import PARAMS
+    from oracle import pbc_oracle as O
+    f, of = built.Pairing(PARAMS["f"]), O.pairing_from_param(PARAMS["f"])
+    assert tuple(f.derived_constant("xi", 20)) == of.negalpha
+    assert tuple(f.derived_constant("xi_inv", 20)) == of.negalphainv
+    assert tuple(f.derived_constant("twist_b", 20)) == of.Et.b
+    assert tuple(f.derived_constant("xpowq2", 20)) == of.xpowq2
+    assert tuple(f.derived_constant("xpowq6", 20)) == of.xpowq6
+    assert tuple(f.derived_constant("xpowq8", 20)) == of.xpowq8
+    assert f.derived_constant("tateexp", 64) == [of.tateexp]
+    d, od = built.Pairing(PARAMS["d159"]), O.pairing_from_param(PARAMS["d159"])
+    x = (0, 1, 0)
+    x3 = od.Fq3.mul(od.Fq3.mul(x, x), x)
+    assert tuple(d.derived_constant("xpwr3", 20)) == x3
+    assert tuple(d.derived_constant("xpwr4", 20)) == od.Fq3.mul(x3, x)
+    assert tuple(d.derived_constant("xpowq", 20)) == od.xpowq
+    assert tuple(d.derived_constant("xpowq2", 20)) == od.xpowq2
+    assert d.derived_constant("nqrinv", 20) == [od.nqrinv[0]]
+    assert d.derived_constant("nqrinv2", 20) == [od.nqrinv2[0]]
+    assert d.derived_constant("phikonr", 32) == [od.phikonr]
