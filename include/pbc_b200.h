@@ -128,6 +128,13 @@ int pbc_b200_derived_constant(const pbc_b200_pairing_t *p, const char *name, uns
 int pbc_b200_fp_op(pbc_b200_pairing_t *p, int op, unsigned char *out, const unsigned char *a,
                    const unsigned char *b, size_t n);
 
+/* Extension-tower differential-test hook (types f and d), GT wire format in and out:
+ * op 0 = a*b, 1 = a^2, 2 = 1/a, 3 = final exponentiation of a (f_tateexp ecc/f_param.c:250-283,
+ * cc_tatepower ecc/d_param.c:505-564); type f: 4 = a times the sparse Miller line held in b's
+ * coefficients 0, 3, 4; type d: 5 = F_q^3 product of the real halves, 6 = F_q^3 inverse. */
+int pbc_b200_tower_op(pbc_b200_pairing_t *p, int op, unsigned char *out, const unsigned char *a,
+                      const unsigned char *b, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

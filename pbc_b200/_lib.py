@@ -45,6 +45,7 @@ lib.pbc_b200_bench_imad.restype = C.c_double
 lib.pbc_b200_set_stage_profiling.argtypes = [_P, C.c_int]
 lib.pbc_b200_stage_times.argtypes = [_P, C.POINTER(C.c_float)]
 lib.pbc_b200_derived_constant.argtypes = [_P, C.c_char_p, _P, C.c_size_t, C.c_size_t]
+lib.pbc_b200_tower_op.argtypes = [_P, C.c_int, _P, _P, _P, C.c_size_t]
 lib.pbc_b200_fp_op.argtypes = [_P, C.c_int, _P, _P, _P, C.c_size_t]
 
 

@@ -849,3 +849,30 @@ extern "C" int pbc_b200_fp_op(pbc_b200_pairing_t* p, int op, unsigned char* out,
   cudaFree(da); cudaFree(db); cudaFree(dout);
   return 0;
 }
+
+/* GT-sized differential-test hook for the extension towers of types f and d (see k_f_tower_op,
+ * k_d_tower_op): operands and results in GT wire format. */
+extern "C" int pbc_b200_tower_op(pbc_b200_pairing_t* p, int op, unsigned char* out,
+                                 const unsigned char* a, const unsigned char* b, size_t n) {
+  if (!p) return fail("null argument");
+  if (p->type != 'f' && p->type != 'd') return fail("tower_op: types f and d only");
+  if (n == 0) return 0;
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  if (ctx_prepare(p, dev)) return 1;
+  size_t wb = (size_t)p->gt_len;
+  uint8_t *da, *db, *dout;
+  CUDA_OK(cudaMalloc(&da, n * wb));
+  CUDA_OK(cudaMalloc(&db, n * wb));
+  CUDA_OK(cudaMalloc(&dout, n * wb));
+  CUDA_OK(cudaMemcpy(da, a, n * wb, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(db, b ? b : a, n * wb, cudaMemcpyHostToDevice));
+  unsigned g = (unsigned)((n + 63) / 64);
+  if (p->type == 'f') k_f_tower_op<<<g, 64>>>(op, dout, da, db, n);
+  else k_d_tower_op<<<g, 64>>>(op, dout, da, db, n);
+  LAUNCHED();
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(out, dout, n * wb, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return 0;
+}

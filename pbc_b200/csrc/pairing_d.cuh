@@ -131,11 +131,11 @@ __device__ __forceinline__ void f3_frob(F3& r, const F3& x) {
 // 1/x = x^q x^(q^2) / N(x)   (the reference runs a polynomial ext-Euclid, arith/poly.c:454-536)
 __device__ __noinline__ void f3_inv(F3* r, const F3* x) {
   F3 t, u;
+  Fq n;
   f3_frob(t, *x);
   f3_frob(u, t);
   f3_mul(&t, &t, &u);
   f3_mul(&u, &t, x);              // the norm: only coefficient 0 is non-zero
-  Fq n;
   fq_inv(&n, &u.c[0]);
   f3_scale(*r, t, n);
 }
@@ -195,8 +195,9 @@ struct DTower {
   typedef F6D Acc;
   struct Ctx { F3 Qx, Qy; };
   // v *= (a Qx + c) + (b Qy) w   (d_miller_evalfn, ecc/d_param.c:99-111)
-  static __device__ __forceinline__ void mul_line(F6D* v, const Fq* a, const Fq* b, const Fq* c,
-                                                  const Ctx* q) {
+  // (own frame for the address-taken temporary: see the stack-discipline note in pairing_f.cuh)
+  static __device__ __noinline__ void mul_line(F6D* v, const Fq* a, const Fq* b, const Fq* c,
+                                              const Ctx* q) {
     F6D l;
     f3_scale(l.a, q->Qx, *a);
     fq_add(l.a.c[0], l.a.c[0], *c);
@@ -236,31 +237,29 @@ k_d_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_
   fq_from_wire(yP, p + kWS);
   bool ok = cc_on_curve(xP, yP);
   DTower::Ctx ctx;
+  F3 t, u;
+  F6D v;
+  Fq k;
   const uint8_t* q = Q + idx * (6 * kWS);
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     fq_from_wire(ctx.Qx.c[i], q + i * kWS);
     fq_from_wire(ctx.Qy.c[i], q + (3 + i) * kWS);
   }
-  {
-    // Y^2 == X^3 + (a v^2) X + b v^3 over F_q^3 (ecc/curve.c:57-76)
-    F3 t, u;
-    Fq k;
-    f3_sqr(&t, &ctx.Qx);
-    fq_set(k, c_d.twist_a);
-    fq_add(t.c[0], t.c[0], k);
-    f3_mul(&t, &t, &ctx.Qx);
-    fq_set(k, c_d.twist_b);
-    fq_add(t.c[0], t.c[0], k);
-    f3_sqr(&u, &ctx.Qy);
-    ok = ok && f3_eq(t, u);
-    // untwist: Qx / v, Qy / v^2 (ecc/d_param.c:576-582)
-    fq_set(k, c_d.nqrinv);
-    f3_scale(ctx.Qx, ctx.Qx, k);
-    fq_set(k, c_d.nqrinv2);
-    f3_scale(ctx.Qy, ctx.Qy, k);
-  }
-  F6D v;
+  // Y^2 == X^3 + (a v^2) X + b v^3 over F_q^3 (ecc/curve.c:57-76)
+  f3_sqr(&t, &ctx.Qx);
+  fq_set(k, c_d.twist_a);
+  fq_add(t.c[0], t.c[0], k);
+  f3_mul(&t, &t, &ctx.Qx);
+  fq_set(k, c_d.twist_b);
+  fq_add(t.c[0], t.c[0], k);
+  f3_sqr(&u, &ctx.Qy);
+  ok = ok && f3_eq(t, u);
+  // untwist: Qx / v, Qy / v^2 (ecc/d_param.c:576-582)
+  fq_set(k, c_d.nqrinv);
+  f3_scale(ctx.Qx, ctx.Qx, k);
+  fq_set(k, c_d.nqrinv2);
+  f3_scale(ctx.Qy, ctx.Qy, k);
   f6d_one(v);
   if (ok) miller_cc<DTower>(&v, xP, yP, &ctx);
   f6d_st_global(mv, n, idx, v);
@@ -287,6 +286,54 @@ k_d_prod(const uint32_t* __restrict__ mv_in, const uint32_t* __restrict__ flag_i
   flag_out[idx] = ok ? 1u : 0u;
 }
 
+// cc_tatepower, k = 6 branch (ecc/d_param.c:505-564) followed by lucas_even (:441-502)
+__device__ __noinline__ void f6d_final_exp(F3& out0, F3& out1, F6D& f) {
+  F6D e0, e3;
+  F3 t1, v0, v1, tmp, two, d;
+  f3_frob(e3.a, f.a);
+  f3_frob(e3.b, f.b);                  // qpower(1)
+  e0.a = f.a;
+  f3_neg(e0.b, f.b);                   // conjugate = f^(q^3)
+  f6d_mul(&e3, &e3, &e0);
+  f3_frob(e0.a, f.a);
+  f3_frob(e0.b, f.b);
+  f3_neg(e0.b, e0.b);                  // qpower(-1)
+  f6d_mul(&e0, &e0, &f);
+  f6d_inv(&e0, &e0);
+  f6d_mul(&f, &e3, &e0);
+  // lucas_even on in = f: t0 = 2, t1 = 2 in0
+  f3_zero(two);
+  fq_set(two.c[0], c_d.two);
+  f3_add(t1, f.a, f.a);
+  v0 = two;
+  v1 = t1;
+  for (int j = (int)c_d.phibits - 1; j >= 0; j--) {
+    bool bit = j > 0 && ((c_d.phikonr[j >> 5] >> (j & 31)) & 1u);   // last step: clear branch
+    f3_mul(&tmp, &v0, &v1);
+    f3_sub(tmp, tmp, t1);
+    if (bit) {
+      v0 = tmp;
+      f3_sqr(&v1, &v1);
+      f3_sub(v1, v1, two);
+    } else {
+      v1 = tmp;
+      f3_sqr(&v0, &v0);
+      f3_sub(v0, v0, two);
+    }
+  }
+  f3_add(v0, v0, v0);
+  f3_mul(&tmp, &t1, &v1);
+  f3_sub(tmp, tmp, v0);
+  f3_sqr(&d, &t1);
+  f3_sub(d, d, two);
+  f3_sub(d, d, two);
+  f3_inv(&d, &d);
+#pragma unroll
+  for (int i = 0; i < 3; i++) fq_halve(out0.c[i], v1.c[i]);
+  f3_mul(&tmp, &tmp, &d);
+  f3_mul(&out1, &tmp, &f.b);
+}
+
 // cc_tatepower, k = 6 branch (ecc/d_param.c:505-564) + lucas_even (:441-502).
 // out: n x 120 bytes: real half (3 coefficients) then imaginary half.
 template <int BLOCK>
@@ -295,54 +342,11 @@ k_d_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
              uint8_t* __restrict__ out, size_t n) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (idx >= n) return;
-  F6D f, e0, e3;
+  F6D f;
   F3 out0, out1;
   if (flag[idx]) {
     f6d_ld_global(f, mv, n, idx);
-    f3_frob(e3.a, f.a);
-    f3_frob(e3.b, f.b);                  // qpower(1)
-    e0.a = f.a;
-    f3_neg(e0.b, f.b);                   // conjugate = f^(q^3)
-    f6d_mul(&e3, &e3, &e0);
-    f3_frob(e0.a, f.a);
-    f3_frob(e0.b, f.b);
-    f3_neg(e0.b, e0.b);                  // qpower(-1)
-    f6d_mul(&e0, &e0, &f);
-    f6d_inv(&e0, &e0);
-    f6d_mul(&f, &e3, &e0);
-    // lucas_even on in = f: t0 = 2, t1 = 2 in0
-    F3 t1, v0, v1, tmp, two;
-    f3_zero(two);
-    fq_set(two.c[0], c_d.two);
-    f3_add(t1, f.a, f.a);
-    v0 = two;
-    v1 = t1;
-    for (int j = (int)c_d.phibits - 1; j >= 0; j--) {
-      bool bit = j > 0 && ((c_d.phikonr[j >> 5] >> (j & 31)) & 1u);   // last step: clear branch
-      f3_mul(&tmp, &v0, &v1);
-      f3_sub(tmp, tmp, t1);
-      if (bit) {
-        v0 = tmp;
-        f3_sqr(&v1, &v1);
-        f3_sub(v1, v1, two);
-      } else {
-        v1 = tmp;
-        f3_sqr(&v0, &v0);
-        f3_sub(v0, v0, two);
-      }
-    }
-    f3_add(v0, v0, v0);
-    f3_mul(&tmp, &t1, &v1);
-    f3_sub(tmp, tmp, v0);
-    F3 d;
-    f3_sqr(&d, &t1);
-    f3_sub(d, d, two);
-    f3_sub(d, d, two);
-    f3_inv(&d, &d);
-#pragma unroll
-    for (int i = 0; i < 3; i++) fq_halve(out0.c[i], v1.c[i]);
-    f3_mul(&tmp, &tmp, &d);
-    f3_mul(&out1, &tmp, &f.b);
+    f6d_final_exp(out0, out1, f);
   } else {
     f3_zero(out0);
     f3_zero(out1);
@@ -354,6 +358,41 @@ k_d_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
     fq_to_wire(o + i * kWS, out0.c[i]);
     fq_to_wire(o + (3 + i) * kWS, out1.c[i]);
   }
+}
+
+__device__ __forceinline__ void f6d_from_wire(F6D& v, const uint8_t* p) {
+#pragma unroll 1
+  for (int i = 0; i < 3; i++) {
+    fq_from_wire(v.a.c[i], p + i * kWS);
+    fq_from_wire(v.b.c[i], p + (3 + i) * kWS);
+  }
+}
+__device__ __forceinline__ void f6d_to_wire(uint8_t* p, const F6D& v) {
+#pragma unroll 1
+  for (int i = 0; i < 3; i++) {
+    fq_to_wire(p + i * kWS, v.a.c[i]);
+    fq_to_wire(p + (3 + i) * kWS, v.b.c[i]);
+  }
+}
+
+// Differential-test hook on GT-sized operands (120 wire bytes): op 0 = a*b, 1 = a^2, 2 = 1/a,
+// 3 = cc_tatepower(a), 5 = F_q^3 product of the real halves, 6 = F_q^3 inverse of a's real half.
+__global__ void k_d_tower_op(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a,
+                             const uint8_t* __restrict__ b, size_t n) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  F6D x, y, r;
+  f6d_from_wire(x, a + idx * (6 * kWS));
+  f6d_from_wire(y, b + idx * (6 * kWS));
+  switch (op) {
+    case 0: f6d_mul(&r, &x, &y); break;
+    case 1: r = x; f6d_sqr(&r); break;
+    case 2: f6d_inv(&r, &x); break;
+    case 3: f6d_final_exp(r.a, r.b, x); break;
+    case 5: f3_mul(&r.a, &x.a, &y.a); f3_zero(r.b); break;
+    default: f3_inv(&r.a, &x.a); f3_zero(r.b); break;
+  }
+  f6d_to_wire(out + idx * (6 * kWS), r);
 }
 
 }  // namespace pbcb200

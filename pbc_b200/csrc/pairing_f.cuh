@@ -76,11 +76,13 @@ __device__ __noinline__ void f2_sqr(F2* r, const F2* x) {
 }
 // multiplication by an element of F_q
 __device__ __forceinline__ void f2_scale(F2& r, const F2& x, const Fq& k) { fq_mul(r.a, x.a, k); fq_mul(r.b, x.b, k); }
-__device__ __forceinline__ void f2_mul_xi(F2& r, const F2& x) {
-  F2 xi;
-  f2_set(xi, c_f.xi);
-  f2_mul(&r, &x, &xi);
-}
+// Stack discipline for everything below (nvcc 12.9 was seen to give two LIVE address-taken
+// temporaries the same stack slot when inlined helpers had left several disjoint-lifetime
+// temporaries behind -- tests/test_gpu_towers.py op 4 caught it): a routine whose locals have their
+// address taken is __noinline__ and declares them at function scope; inlined helpers take no
+// addresses of their own locals.  Constants are passed as pointers into __constant__ memory.
+__device__ __forceinline__ const F2* f2_const(const uint32_t c[2][kNS]) { return reinterpret_cast<const F2*>(c); }
+__device__ __forceinline__ void f2_mul_xi(F2& r, const F2& x) { f2_mul(&r, &x, f2_const(c_f.xi)); }
 // 1/(x0 + x1 s) = (x0 - x1 s)/(x0^2 - beta x1^2)   (arith/fieldquadratic.c:290-309)
 __device__ __noinline__ void f2_inv(F2* r, const F2* x) {
   Fq t0, t1, u;
@@ -102,7 +104,7 @@ struct F6 { F2 c[3]; };
 
 // Karatsuba: 6 F_q^2 products + 2 multiplications by xi
 __device__ __noinline__ void f6_mul(F6* r, const F6* a, const F6* b) {
-  F2 v0, v1, v2, s, t, u;
+  F2 v0, v1, v2, s, t, u, c0, c1;
   f2_mul(&v0, &a->c[0], &b->c[0]);
   f2_mul(&v1, &a->c[1], &b->c[1]);
   f2_mul(&v2, &a->c[2], &b->c[2]);
@@ -113,7 +115,6 @@ __device__ __noinline__ void f6_mul(F6* r, const F6* a, const F6* b) {
   f2_sub(u, u, v1);
   f2_sub(u, u, v2);
   f2_mul_xi(u, u);
-  F2 c0;
   f2_add(c0, v0, u);
   // c1 = (a0 + a1)(b0 + b1) - v0 - v1 + xi v2
   f2_add(s, a->c[0], a->c[1]);
@@ -121,7 +122,6 @@ __device__ __noinline__ void f6_mul(F6* r, const F6* a, const F6* b) {
   f2_mul(&u, &s, &t);
   f2_sub(u, u, v0);
   f2_sub(u, u, v1);
-  F2 c1;
   f2_mul_xi(c1, v2);
   f2_add(c1, c1, u);
   // c2 = (a0 + a2)(b0 + b2) - v0 - v2 + v1
@@ -143,7 +143,7 @@ __device__ __forceinline__ void f6_sub(F6& r, const F6& a, const F6& b) {
   for (int i = 0; i < 3; i++) f2_sub(r.c[i], a.c[i], b.c[i]);
 }
 // r = y a:  (a0, a1, a2) -> (xi a2, a0, a1)
-__device__ __forceinline__ void f6_mul_y(F6& r, const F6& a) {
+__device__ __noinline__ void f6_mul_y(F6& r, const F6& a) {
   F2 t;
   f2_mul_xi(t, a.c[2]);
   r.c[2] = a.c[1];
@@ -244,18 +244,24 @@ __device__ __noinline__ void f12_inv(F12* r, const F12* p) {
 // v *= c + L3 x^3 + L4 x^4, c in F_q (the Miller line, ecc/f_param.c:109-149)
 //   out_k = c v_k + L3 v_{k-3} + L4 v_{k-4}, indices mod 6, a wrap multiplies by xi
 __device__ __noinline__ void f12_mul_line(F12* v, const Fq* c, const F2* L3, const F2* L4) {
-  F2 X3, X4, t, u;
+  // m3[0] = xi L3 (used when the product wraps past x^5), m3[1] = L3; same for L4.  (Indexing an
+  // array instead of selecting between two pointers: nvcc 12.9 merged the stack slots of two live
+  // temporaries when the operand pointer came from a select -- see tests/test_gpu_towers.py op 4.)
+  F2 m3[2], m4[2];
   F12 o;
-  f2_mul_xi(X3, *L3);
-  f2_mul_xi(X4, *L4);
+  m3[1] = *L3;
+  m4[1] = *L4;
+  f2_mul_xi(m3[0], m3[1]);
+  f2_mul_xi(m4[0], m4[1]);
 #pragma unroll 1
   for (int k = 0; k < 6; k++) {
     int i3 = k >= 3 ? k - 3 : k + 3, i4 = k >= 4 ? k - 4 : k + 2;
-    f2_mul(&t, k >= 3 ? L3 : &X3, &v->c[i3]);
-    f2_mul(&u, k >= 4 ? L4 : &X4, &v->c[i4]);
+    F2 t, u, w;
+    f2_mul(&t, &m3[k >= 3 ? 1 : 0], &v->c[i3]);
+    f2_mul(&u, &m4[k >= 4 ? 1 : 0], &v->c[i4]);
+    f2_scale(w, v->c[k], *c);
     f2_add(t, t, u);
-    f2_scale(u, v->c[k], *c);
-    f2_add(o.c[k], t, u);
+    f2_add(o.c[k], t, w);
   }
   *v = o;
 }
@@ -266,8 +272,8 @@ __device__ __noinline__ void f12_mul_line(F12* v, const Fq* c, const F2* L3, con
 struct FTower {
   typedef F12 Acc;
   struct Ctx { F2 Qx, Qy; };     // untwisted second argument
-  static __device__ __forceinline__ void mul_line(F12* v, const Fq* a, const Fq* b, const Fq* c,
-                                                  const Ctx* q) {
+  static __device__ __noinline__ void mul_line(F12* v, const Fq* a, const Fq* b, const Fq* c,
+                                              const Ctx* q) {
     F2 L3, L4;
     f2_scale(L3, q->Qy, *b);
     f2_scale(L4, q->Qx, *a);
@@ -307,26 +313,22 @@ k_f_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_
   fq_from_wire(yP, p + kWS);
   bool ok = cc_on_curve(xP, yP);
   FTower::Ctx ctx;
+  F2 t, u;
+  F12 v;
   const uint8_t* q = Q + idx * (4 * kWS);
   fq_from_wire(ctx.Qx.a, q);
   fq_from_wire(ctx.Qx.b, q + kWS);
   fq_from_wire(ctx.Qy.a, q + 2 * kWS);
   fq_from_wire(ctx.Qy.b, q + 3 * kWS);
-  {
-    // Y^2 == X^3 + twist_b on the twist (ecc/curve.c:57-76 over F_q^2)
-    F2 t, u, tb;
-    f2_sqr(&t, &ctx.Qx);
-    f2_mul(&t, &t, &ctx.Qx);
-    f2_set(tb, c_f.twist_b);
-    f2_add(t, t, tb);
-    f2_sqr(&u, &ctx.Qy);
-    ok = ok && f2_eq(t, u);
-    // untwist (ecc/f_param.c:296-303)
-    f2_set(tb, c_f.xi_inv);
-    f2_mul(&ctx.Qx, &ctx.Qx, &tb);
-    f2_mul(&ctx.Qy, &ctx.Qy, &tb);
-  }
-  F12 v;
+  // Y^2 == X^3 + twist_b on the twist (ecc/curve.c:57-76 over F_q^2)
+  f2_sqr(&t, &ctx.Qx);
+  f2_mul(&t, &t, &ctx.Qx);
+  f2_add(t, t, *f2_const(c_f.twist_b));
+  f2_sqr(&u, &ctx.Qy);
+  ok = ok && f2_eq(t, u);
+  // untwist (ecc/f_param.c:296-303)
+  f2_mul(&ctx.Qx, &ctx.Qx, f2_const(c_f.xi_inv));
+  f2_mul(&ctx.Qy, &ctx.Qy, f2_const(c_f.xi_inv));
   f12_one(v);
   if (ok) miller_cc<FTower>(&v, xP, yP, &ctx);
   f12_st_global(mv, n, idx, v);
@@ -357,15 +359,33 @@ k_f_prod(const uint32_t* __restrict__ mv_in, const uint32_t* __restrict__ flag_i
 }
 
 // coefficient i scaled by e^i (ecc/f_param.c:257-268 qpower)
-__device__ __forceinline__ void f12_qpower(F12& r, const F12& f, const uint32_t e[2][kNS]) {
-  F2 ep, e1;
-  f2_set(e1, e);
-  ep = e1;
+__device__ __noinline__ void f12_qpower(F12& r, const F12& f, const uint32_t e[2][kNS]) {
+  F2 ep;
+  const F2* e1 = f2_const(e);
+  ep = *e1;
   r.c[0] = f.c[0];
 #pragma unroll 1
   for (int i = 1; i < 6; i++) {
     f2_mul(&r.c[i], &f.c[i], &ep);
-    if (i < 5) f2_mul(&ep, &ep, &e1);
+    if (i < 5) f2_mul(&ep, &ep, e1);
+  }
+}
+
+// f_tateexp (ecc/f_param.c:250-283)
+__device__ __noinline__ void f12_final_exp(F12& acc, F12& f) {
+  F12 x, y;
+  f12_qpower(y, f, c_f.xpowq8);
+  f12_qpower(x, f, c_f.xpowq6);
+  f12_mul(&y, &y, &x);                 // f^(q^8 + q^6)
+  f12_qpower(x, f, c_f.xpowq2);
+  f12_mul(&x, &x, &f);                 // f^(q^2 + 1)
+  f12_inv(&x, &x);
+  f12_mul(&f, &y, &x);
+  // generic_pow_mpz's sliding window (arith/field.c:14-126) computes the same power
+  acc = f;
+  for (int j = (int)c_f.tatebits - 2; j >= 0; j--) {
+    f12_sqr(&acc);
+    if ((c_f.tateexp[j >> 5] >> (j & 31)) & 1u) f12_mul(&acc, &acc, &f);
   }
 }
 
@@ -378,22 +398,10 @@ k_f_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
              uint8_t* __restrict__ out, size_t n) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (idx >= n) return;
-  F12 f, x, y, acc;
+  F12 f, acc;
   if (flag[idx]) {
     f12_ld_global(f, mv, n, idx);
-    f12_qpower(y, f, c_f.xpowq8);
-    f12_qpower(x, f, c_f.xpowq6);
-    f12_mul(&y, &y, &x);                 // f^(q^8 + q^6)
-    f12_qpower(x, f, c_f.xpowq2);
-    f12_mul(&x, &x, &f);                 // f^(q^2 + 1)
-    f12_inv(&x, &x);
-    f12_mul(&f, &y, &x);
-    // generic_pow_mpz's sliding window (arith/field.c:14-126) computes the same power
-    acc = f;
-    for (int j = (int)c_f.tatebits - 2; j >= 0; j--) {
-      f12_sqr(&acc);
-      if ((c_f.tateexp[j >> 5] >> (j & 31)) & 1u) f12_mul(&acc, &acc, &f);
-    }
+    f12_final_exp(acc, f);
   } else {
     f12_one(acc);
   }
@@ -403,6 +411,41 @@ k_f_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
     fq_to_wire(o + (2 * i) * kWS, acc.c[i].a);
     fq_to_wire(o + (2 * i + 1) * kWS, acc.c[i].b);
   }
+}
+
+__device__ __forceinline__ void f12_from_wire(F12& v, const uint8_t* p) {
+#pragma unroll 1
+  for (int i = 0; i < 6; i++) {
+    fq_from_wire(v.c[i].a, p + (2 * i) * kWS);
+    fq_from_wire(v.c[i].b, p + (2 * i + 1) * kWS);
+  }
+}
+__device__ __forceinline__ void f12_to_wire(uint8_t* p, const F12& v) {
+#pragma unroll 1
+  for (int i = 0; i < 6; i++) {
+    fq_to_wire(p + (2 * i) * kWS, v.c[i].a);
+    fq_to_wire(p + (2 * i + 1) * kWS, v.c[i].b);
+  }
+}
+
+// Differential-test hook on GT-sized operands (240 wire bytes): op 0 = a*b, 1 = a^2, 2 = 1/a,
+// 3 = f_tateexp(a), 4 = a * line, the line c + L3 x^3 + L4 x^4 taken from b's coefficients 0 (real
+// part only), 3 and 4.
+__global__ void k_f_tower_op(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a,
+                             const uint8_t* __restrict__ b, size_t n) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  F12 x, y, r;
+  f12_from_wire(x, a + idx * (12 * kWS));
+  f12_from_wire(y, b + idx * (12 * kWS));
+  switch (op) {
+    case 0: f12_mul(&r, &x, &y); break;
+    case 1: r = x; f12_sqr(&r); break;
+    case 2: f12_inv(&r, &x); break;
+    case 3: f12_final_exp(r, x); break;
+    default: r = x; f12_mul_line(&r, &y.c[0].a, &y.c[3], &y.c[4]); break;
+  }
+  f12_to_wire(out + idx * (12 * kWS), r);
 }
 
 }  // namespace pbcb200

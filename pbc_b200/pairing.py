@@ -117,6 +117,12 @@ class Pairing:
             raise PairingError(last_error())
         return out.raw
 
+    def tower_op(self, op: int, a: bytes, b, n: int) -> bytes:
+        out = C.create_string_buffer(n * self.gt_len)
+        if lib.pbc_b200_tower_op(self._h, op, C.addressof(out), _addr(a), _addr(b), n):
+            raise PairingError(last_error())
+        return out.raw
+
     def derived_constant(self, name: str, width: int):
         """canonical residues of a constant derived at init time, as a list of ints (tests)"""
         buf = C.create_string_buffer(16 * width)
