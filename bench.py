@@ -38,15 +38,43 @@ from pbc_b200 import synth  # noqa: E402
 
 GRID = 4096                    # inputs are drawn from a GRID x GRID grid of distinct points
 SEED = 20260922
-# --- algorithmic work, SURVEY.md 8(d) / DESIGN.md "work per unit" ---------------------------
-UNIT_OPS_PER_MULMOD = {"a": 528}          # 2(2t)^2 + 2t IMAD.WIDE.U32 for t = 8 64-bit limbs
-REF_MULMODS = {"a": 4394}                 # reference algorithm, whole pairing
-REF_MULMODS_MAIN = {"a": 4394 - 719}      # ... of which Miller loop (final exp = 719)
-# what k_a_miller executes per pairing: 2093 multiplications (528 unit ops) + 961 squarings
-# (408 unit ops: product-scanning squaring) -- DESIGN.md "work per unit"
-EXEC_MULMODS_MAIN = {"a": 2093 + 961}
-EXEC_UNIT_OPS_MAIN = {"a": 2093 * 528 + 961 * 408}
-WIRE_BYTES = {"a": (128, 128, 128)}
+# --- workloads: BASELINE.json configs[1] (default), [2], [3], [4] ---------------------------------
+# unit = one 32x32->64 multiply-accumulate (IMAD.WIDE.U32); a t-limb(64-bit) Montgomery mulmod is
+# 2(2t)^2 + 2t of them: 528 for t = 8 (type a), 78 for t = 3 (types f, d)  -- SURVEY.md 8(d).
+# ref_mulmods = reference-algorithm mulmods per output (SURVEY 8d probes); ref_main = the part the
+# first kernel (Miller loop) stands for.  exec_unit_ops_main = what OUR first kernel executes.
+WORKLOADS = {
+    "a": dict(param="a", mode="single", k=1, n=1 << 20, unit=528, ref_mulmods=4394, ref_main=4394 - 719,
+              exec_unit_ops_main=2093 * 528 + 961 * 408, cpu_rate=1100.0, port_rate=110.0,
+              name="type A (param/a.param) element_pairing, batch 2^20 (P,Q) pairs per GPU, 512-bit F_q",
+              dtype="u32 limbs (16 x 32-bit = 512-bit F_q, exact integer)", kernels=("k_a_miller", "k_batch_invert", "k_a_finalexp")),
+    "f": dict(param="f", mode="single", k=1, n=1 << 20, unit=78, ref_mulmods=98183, ref_main=None,
+              exec_unit_ops_main=None, cpu_rate=70.0, port_rate=3.0,
+              name="type F (param/f.param, BN k=12) element_pairing, batch 2^20 pairs per GPU, 158-bit F_q",
+              dtype="u32 limbs (5 x 32-bit = 160-bit F_q, exact integer)", kernels=("k_f_miller", "-", "k_f_finalexp")),
+    "d": dict(param="d159", mode="single", k=1, n=1 << 18, unit=78, ref_mulmods=23039, ref_main=None,
+              exec_unit_ops_main=None, cpu_rate=350.0, port_rate=10.0,
+              name="type D (param/d159.param, MNT k=6) element_pairing, batch 2^18 pairs per GPU, 159-bit F_q",
+              dtype="u32 limbs (5 x 32-bit = 160-bit F_q, exact integer)", kernels=("k_d_miller", "-", "k_d_finalexp")),
+    "prod16": dict(param="a", mode="prod", k=16, n=1 << 16, unit=528, ref_mulmods=41536, ref_main=41536 - 719,
+                   exec_unit_ops_main=16 * (2093 * 528 + 961 * 408), cpu_rate=130.0, port_rate=8.0,
+                   name="type A element_prod_pairing n=16, 2^16 outputs (2^20 Miller loops) over all GPUs",
+                   dtype="u32 limbs (16 x 32-bit = 512-bit F_q, exact integer)",
+                   kernels=("k_a_miller+k_a_prod", "k_batch_invert", "k_a_finalexp")),
+}
+WIRE = {"a": (128, 128, 128), "f": (40, 80, 240), "d159": (40, 120, 120)}
+
+
+def make_inputs(w, n_out, offset_out=0):
+    """(P, Q) numpy uint8 arrays for outputs offset_out .. offset_out+n_out-1 of workload w."""
+    prm = synth.parse_param(PARAMS[w["param"]])
+    if w["param"] == "a":
+        Pb, Qb = synth.type_a_points(prm, GRID, SEED)
+    else:
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", w["param"] + ".json")))["pairing"]
+        Pb, Qb = synth.type_fd_points(prm, [bytes.fromhex(x) for x in g["P"][:2]],
+                                      [bytes.fromhex(x) for x in g["Q"][:2]], GRID)
+    return synth.build_batch(Pb, Qb, n_out * w["k"], offset_out * w["k"])
 
 
 def env_int(name, default):
@@ -60,20 +88,26 @@ def env_int(name, default):
 # CPU reference leg (oracle/_ref = the unmodified reference; else the Python port)
 # ------------------------------------------------------------------------------------------
 def _ref_worker(args):
-    name, Pb, Qb, n = args
+    name, mode, k, Pb, Qb, n = args
     from oracle import ref as R
     rp = R.RefPairing(PARAMS[name])
     t0 = time.perf_counter()
-    out = rp.pairing(Pb, Qb, n)
+    out = rp.pairing(Pb, Qb, n) if mode == "single" else rp.prod_pairing(Pb, Qb, k, n)
     return out, time.perf_counter() - t0
 
 
 def _port_worker(args):
-    name, Pb, Qb, n = args
+    name, mode, k, Pb, Qb, n = args
     from oracle import pbc_oracle as O
     pr = O.pairing_from_param(PARAMS[name])
     t0 = time.perf_counter()
-    out = O.pairing_batch(pr, Pb, Qb, n)
+    if mode == "single":
+        out = O.pairing_batch(pr, Pb, Qb, n)
+    else:
+        a, b = pr.g1_len, pr.g2_len
+        out = b"".join(O.prod_pairing_bytes(pr, [Pb[(i * k + j) * a:(i * k + j + 1) * a] for j in range(k)],
+                                            [Qb[(i * k + j) * b:(i * k + j + 1) * b] for j in range(k)])
+                       for i in range(n))
     return out, time.perf_counter() - t0
 
 
@@ -87,11 +121,12 @@ def cpu_kind():
     return "port"
 
 
-def cpu_pairings(name, P, Q, n, cores, pool=None):
-    """n pairings on `cores` processes (each with its own pairing_t: the library is not
-    thread-safe).  Returns (bytes, wall seconds)."""
+def cpu_pairings(w, P, Q, n, cores, pool=None):
+    """n outputs of workload w on `cores` processes (each with its own pairing_t: the library is
+    not thread-safe).  Returns (bytes, wall seconds)."""
     import multiprocessing as mp
-    g1, g2, _ = WIRE_BYTES[name]
+    g1, g2, _ = WIRE[w["param"]]
+    k = w["k"]
     kind = cpu_kind()
     worker = _ref_worker if kind == "reference" else _port_worker
     per = (n + cores - 1) // cores
@@ -99,7 +134,8 @@ def cpu_pairings(name, P, Q, n, cores, pool=None):
     for c in range(cores):
         lo, hi = c * per, min(n, (c + 1) * per)
         if lo < hi:
-            jobs.append((name, bytes(P[lo * g1:hi * g1]), bytes(Q[lo * g2:hi * g2]), hi - lo))
+            jobs.append((w["param"], w["mode"], k, bytes(P[lo * k * g1:hi * k * g1]),
+                         bytes(Q[lo * k * g2:hi * k * g2]), hi - lo))
     own = pool is None
     if own:
         pool = mp.get_context("fork").Pool(len(jobs))
@@ -119,8 +155,9 @@ def host_cores():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_rate_guess(name, kind):
-    return {"reference": {"a": 1100.0}, "port": {"a": 110.0}}[kind][name]
+def cpu_rate_guess(w, kind):
+    """outputs per second per core, to size the bounded CPU sample"""
+    return w["cpu_rate"] if kind == "reference" else w["port_rate"]
 
 
 # ------------------------------------------------------------------------------------------
@@ -185,44 +222,41 @@ def reference_arm(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0
-    name = args.workload
-    prm = synth.parse_param(PARAMS[name])
-    Pb, Qb = synth.type_a_points(prm, GRID, SEED)
+    w = WORKLOADS[args.workload]
+    n_full = args.n or w["n"]
     cores = host_cores()
     kind = cpu_kind()
-    per_step = int(min(args.n, max(cores * 64, args.ref_seconds * cpu_rate_guess(name, kind) * cores)))
+    per_step = int(min(n_full, max(cores * 4, args.ref_seconds * cpu_rate_guess(w, kind) * cores)))
     import multiprocessing as mp
-    P, Q = synth.build_batch(Pb, Qb, per_step, 0)
+    P, Q = make_inputs(w, per_step)
     P, Q = P.tobytes(), Q.tobytes()
     pool = mp.get_context("fork").Pool(cores)
     for _ in range(args.warmup):
-        cpu_pairings(name, P, Q, min(per_step, cores * 16), cores, pool)
+        cpu_pairings(w, P, Q, min(per_step, cores * 2), cores, pool)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_pairings(name, P, Q, per_step, cores, pool)
+        cpu_pairings(w, P, Q, per_step, cores, pool)
     wall = time.perf_counter() - t0
     pool.close()
     pool.join()
     val = per_step * args.steps / wall
+    unit = "pairings/s" if w["mode"] == "single" else "outputs/s"
     line = {
-        "impl": "reference", "metric": "pairings/sec", "value": val, "unit": "pairings/s",
+        "impl": "reference", "metric": "pairings/sec", "value": val, "unit": unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32 limbs (512-bit F_q)" if kind == "port" else "u64 limbs (GMP mpn)",
+        "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
+        "scaling": "weak" if w["mode"] == "single" else "strong",
+        "vs_baseline": None, "dtype": w["dtype"] if kind == "port" else "u64 limbs (GMP mpn)",
         "data": "synthetic",
-        "config": {"workload": workload_name(name), "batch_per_step": per_step, "param": name + ".param",
-                   "note": "bounded sample of the 2^20 workload per step; CPU only"},
-        "cpu_baseline": {"value": val, "unit": "pairings/s", "cores": cores, "kind": kind,
-                         "sample": "%d pairings per step x %d steps, %d processes" % (per_step, args.steps, cores)},
-        "e2e": {"value": val, "unit": "pairings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": w["name"], "batch_per_step": per_step, "param": w["param"] + ".param",
+                   "note": "bounded sample of the workload per step; CPU only"},
+        "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": kind,
+                         "sample": "%d outputs per step x %d steps, %d processes" % (per_step, args.steps, cores)},
+        "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
-
-
-def workload_name(name):
-    return {"a": "type A (param/a.param) element_pairing, batch 2^20 (P,Q) pairs per GPU, 512-bit F_q"}[name]
 
 
 def main():
@@ -231,8 +265,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="a", choices=["a"])
-    ap.add_argument("--n", type=int, default=1 << 20, help="pairings per GPU per step")
+    ap.add_argument("--workload", default="a", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="outputs per GPU per step (default: the workload's)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget (rank 0, N=1)")
     ap.add_argument("--ref-seconds", type=float, default=3.0, help="--impl reference: seconds per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -243,14 +277,16 @@ def main():
         return reference_arm(args)
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    name = args.workload
-    n = args.n
-    g1, g2, gt = WIRE_BYTES[name]
+    w = WORKLOADS[args.workload]
+    k, single = w["k"], w["mode"] == "single"
+    # single pairings: every rank owns its own full batch (weak scaling); the product config is a
+    # fixed 2^16 outputs split by output across the ranks (strong scaling)
+    n = args.n or (w["n"] if single else max(1, w["n"] // world))
+    g1, g2, gt = WIRE[w["param"]]
+    unit_name = "pairings/s" if single else "outputs/s"
 
-    # ---- synthetic inputs (host) ----
-    prm = synth.parse_param(PARAMS[name])
-    Pb, Qb = synth.type_a_points(prm, GRID, SEED)
-    Ph, Qh = synth.build_batch(Pb, Qb, n, offset=rank * n)
+    # ---- synthetic inputs (host): this rank's shard ----
+    Ph, Qh = make_inputs(w, n, offset_out=rank * n)
 
     # ---- CPU baseline first (forks before CUDA is initialised) ----
     cpu = None
@@ -259,11 +295,11 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
         kind = cpu_kind()
-        sample_n = int(min(n, max(cores * 32, args.cpu_seconds * cpu_rate_guess(name, kind) * cores)))
-        cpu_out, wall = cpu_pairings(name, Ph[:sample_n * g1].tobytes(), Qh[:sample_n * g2].tobytes(),
+        sample_n = int(min(n, max(cores * 2, args.cpu_seconds * cpu_rate_guess(w, kind) * cores)))
+        cpu_out, wall = cpu_pairings(w, Ph[:sample_n * k * g1].tobytes(), Qh[:sample_n * k * g2].tobytes(),
                                      sample_n, cores)
-        cpu = {"value": sample_n / wall, "unit": "pairings/s", "cores": cores, "kind": kind,
-               "sample": "first %d pairs of the step's batch, %d processes, %.1f s wall" % (sample_n, cores, wall)}
+        cpu = {"value": sample_n / wall, "unit": unit_name, "cores": cores, "kind": kind,
+               "sample": "first %d outputs of the step's batch, %d processes, %.1f s wall" % (sample_n, cores, wall)}
 
     import torch
     import torch.distributed as dist
@@ -273,7 +309,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    pr = Pairing(PARAMS[name])
+    pr = Pairing(PARAMS[w["param"]])
     Pp = torch.from_numpy(Ph.copy()).pin_memory()
     Qp = torch.from_numpy(Qh.copy()).pin_memory()
     Op = torch.empty(n * gt, dtype=torch.uint8).pin_memory()
@@ -282,7 +318,16 @@ def main():
     st = torch.cuda.current_stream()
 
     def step():
-        pr.apply_device(dO.data_ptr(), dP.data_ptr(), dQ.data_ptr(), n, st.cuda_stream)
+        if single:
+            pr.apply_device(dO.data_ptr(), dP.data_ptr(), dQ.data_ptr(), n, st.cuda_stream)
+        else:
+            pr.prod_apply_device(dO.data_ptr(), dP.data_ptr(), dQ.data_ptr(), k, n, st.cuda_stream)
+
+    def host_step():
+        if single:
+            pr.apply_into(Op, Pp, Qp, n)
+        else:
+            pr.prod_apply_into(Op, Pp, Qp, k, n)
 
     def barrier():
         torch.cuda.synchronize()
@@ -308,7 +353,7 @@ def main():
     ms_total = e0.elapsed_time(e1)
     launches = kernel_launches() - launches0
     barrier()
-    # per-kernel durations: one more (untimed-for-value) pass per stage sample, events on the stream
+    # per-kernel durations: CUDA events recorded by the library on the launching stream
     for _ in range(min(3, args.steps)):
         step()
         torch.cuda.synchronize()
@@ -330,29 +375,44 @@ def main():
 
     # ---- end to end: host buffers through the C ABI ----
     for _ in range(2):
-        pr.apply_into(Op, Pp, Qp, n)
+        host_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        pr.apply_into(Op, Pp, Qp, n)
+        host_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t2 = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_val = world * n * args.steps / float(t2.item())
-    e2e_same = bool((Op[:4096 * gt] == dO[:4096 * gt].cpu()).all().item())
+    chk = min(n, 4096) * gt
+    e2e_same = bool((Op[:chk] == dO[:chk].cpu()).all().item())
 
     if rank == 0:
-        # ---- roofline of the dominant kernel (Miller loop) ----
+        # ---- roofline of the dominant kernel ----
         sms = torch.cuda.get_device_properties(local).multi_processor_count
         iters = 3000
         ims = bench_imad(sms * 8, 256, iters, 3)
         peak = sms * 8 * 256 * 32 * iters / (ims * 1e-3)          # IMAD.WIDE.U32 / s, measured live
-        unit = UNIT_OPS_PER_MULMOD[name]
-        main_ms = stage[0]
-        ach_ref = n * REF_MULMODS_MAIN[name] * unit / (main_ms * 1e-3)
-        ach_exec = n * EXEC_UNIT_OPS_MAIN[name] / (main_ms * 1e-3)
+        unit = w["unit"]
+        dom = max(range(3), key=lambda i: stage[i])
+        if w["ref_main"] is not None:
+            # type A: the Miller kernel, reference-equivalent and executed work both known
+            kern, kms = w["kernels"][0], stage[0]
+            ach_ref = n * w["ref_main"] * unit / (kms * 1e-3)
+            ach_exec = n * w["exec_unit_ops_main"] / (kms * 1e-3)
+            work = ("reference-equivalent %d mulmods x %d unit ops per output in this kernel; executed %d unit ops"
+                    % (w["ref_main"], unit, w["exec_unit_ops_main"]))
+        else:
+            # types f, d: SURVEY 8(d) gives the reference's mulmod count for the whole pairing only,
+            # so the roofline is taken over the whole kernel sequence (Miller + final exponentiation)
+            kern, kms = "+".join(x for x in w["kernels"] if x != "-"), sum(stage)
+            ach_ref = n * w["ref_mulmods"] * unit / (kms * 1e-3)
+            ach_exec = None
+            work = ("reference-equivalent %d mulmods x %d unit ops per pairing over the whole kernel sequence; "
+                    "dominant kernel %s = %.0f%% of the step" % (w["ref_mulmods"], unit, w["kernels"][dom],
+                                                                 100 * stage[dom] / max(sum(stage), 1e-9)))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -361,36 +421,43 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))["k_a_miller"]["dram_bytes_per_launch"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))[
+                w["kernels"][0].split("+")[0]]["dram_bytes_per_launch"]
         except Exception:
             pass
-        hbm_ach = n * sum(WIRE_BYTES[name]) / (sum(stage) * 1e-3) / 1e9
+        hbm_ach = n * (k * (g1 + g2) + gt) / (sum(stage) * 1e-3) / 1e9
+        roof = {"bound": "int-mul pipe (IMAD.WIDE.U32 issue; SURVEY 8d)", "kernel": kern,
+                "achieved": ach_ref / 1e12, "peak": peak / 1e12, "unit": "T IMAD.WIDE.U32/s",
+                "frac": ach_ref / peak,
+                "peak_source": "live microkernel k_imad_peak (MEASURED_PEAKS.json has no integer peak)",
+                "work": work, "traffic": traffic,
+                "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": hbm_ach / hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                        "note": "%d wire bytes per output: does not bound the path" % (k * (g1 + g2) + gt)}}
+        if ach_exec is not None:
+            roof["achieved_executed"] = ach_exec / 1e12
+            roof["frac_executed"] = ach_exec / peak
+        ws_per = 576 * k if w["param"] == "a" else (61 * 4 if w["param"] == "f" else 31 * 4)
         line = {
-            "metric": "pairings/sec", "value": value, "unit": "pairings/s", "n_gpus": world,
+            "metric": "pairings/sec", "value": value, "unit": unit_name, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 limbs (16 x 32-bit = 512-bit F_q, exact integer)", "data": "synthetic",
-            "config": {"workload": workload_name(name), "param": name + ".param", "batch_per_gpu": n,
-                       "global_batch": world * n, "parallelism": "shard%d (independent pairs, no collective)" % world,
+            "higher_is_better": True, "scaling": "weak" if single else "strong", "vs_baseline": None,
+            "dtype": w["dtype"], "data": "synthetic",
+            "config": {"workload": w["name"], "param": w["param"] + ".param", "batch_per_gpu": n,
+                       "global_batch": world * n, "pairings_per_output": k,
+                       "parallelism": "shard%d (independent outputs, no collective)" % world,
                        "inputs": "%dx%d grid of seeded subgroup points, all pairs distinct" % (GRID, GRID),
-                       "l2": "inputs+workspace %.0f MB per step > 126 MB L2" % ((n * (g1 + g2 + gt + 576)) / 1e6)},
+                       "l2": "inputs+outputs+workspace %.0f MB per step vs 126 MB L2"
+                             % ((n * (k * (g1 + g2) + gt + ws_per)) / 1e6)},
             "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": "pairings/s", "h2d_bytes_per_step": n * (g1 + g2),
-                    "d2h_bytes_per_step": n * gt, "timer": "perf_counter around the blocking C-ABI call, pinned host buffers",
+            "e2e": {"value": e2e_val, "unit": unit_name, "h2d_bytes_per_step": n * k * (g1 + g2),
+                    "d2h_bytes_per_step": n * gt,
+                    "timer": "perf_counter around the blocking C-ABI call, pinned host buffers",
                     "matches_device_resident_output": e2e_same},
             "gpu_launches": launches,
-            "stage_ms": {"miller": stage[0], "batch_invert": stage[1], "final_exp": stage[2]},
-            "roofline": {"bound": "int-mul pipe (IMAD.WIDE.U32 issue; SURVEY 8d)", "kernel": "k_a_miller",
-                         "achieved": ach_ref / 1e12, "peak": peak / 1e12, "unit": "T IMAD.WIDE.U32/s",
-                         "frac": ach_ref / peak,
-                         "achieved_executed": ach_exec / 1e12, "frac_executed": ach_exec / peak,
-                         "peak_source": "live microkernel k_imad_peak (MEASURED_PEAKS.json has no integer peak)",
-                         "work": "reference-equivalent %d mulmods x %d unit ops per pairing; executed %d mul+sqr = %d unit ops"
-                                 % (REF_MULMODS_MAIN[name], unit, EXEC_MULMODS_MAIN[name], EXEC_UNIT_OPS_MAIN[name]),
-                         "traffic": traffic,
-                         "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": hbm_ach / hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                                 "note": "384 wire bytes per pairing: does not bound the path"}},
+            "stage_ms": dict(zip(("main", "mid", "final_exp"), stage)),
+            "stage_kernels": list(w["kernels"]),
+            "roofline": roof,
             "cpu_baseline": cpu,
             "parity": parity,
         }

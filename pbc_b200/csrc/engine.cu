@@ -251,6 +251,44 @@ static int init_type_f(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   if (te.bits() > 512) return fail("type f: final exponent too large");
   te.to_words(c.tateexp, 16);
   p->derived["tateexp"] = {te};
+  // Frobenius tables frob[k-1][i-1] = xi^(i (q^k - 1)/6), k = 1, 2, 3
+  BigUInt q3 = q2 * q;
+  const BigUInt* qk[3] = {&q, &q2, &q3};
+  for (int k = 0; k < 3; k++) {
+    HostF2 g = K.pow(xi, (*qk[k] - one) / six), acc = g;
+    std::vector<BigUInt> rec;
+    for (int i = 0; i < 5; i++) {
+      put2(c.frob[k][i], acc);
+      rec.push_back(acc.a); rec.push_back(acc.b);
+      acc = K.mul(acc, g);
+    }
+    p->derived[std::string("frob") + char('1' + k)] = rec;
+  }
+  // BN parameter: q = 36u^4 + 36u^3 + 24u^2 + 6u + 1 and r = 36u^4 + 36u^3 + 18u^2 + 6u + 1 for
+  // some integer u of either sign (f_param gen).  |u| < 2^40 here; search |u| by bisection.
+  {
+    auto poly = [](const BigUInt& a, bool neg, uint32_t c2) {
+      // 36a^4 +- 36a^3 + c2 a^2 +- 6a + 1 (all terms kept non-negative by ordering)
+      BigUInt a2 = a * a, a3 = a2 * a, a4 = a2 * a2;
+      BigUInt pos = a4 * BigUInt(36) + a2 * BigUInt(c2) + BigUInt(1);
+      BigUInt odd = a3 * BigUInt(36) + a * BigUInt(6);
+      return neg ? pos - odd : pos + odd;
+    };
+    for (int neg = 0; neg < 2 && !c.bn; neg++) {
+      BigUInt lo(1), hi = BigUInt(1).shl(q.bits() / 4 + 2);
+      while (lo < hi) {
+        BigUInt mid = (lo + hi) / BigUInt(2);
+        if (poly(mid, neg, 24) < q) lo = mid + BigUInt(1); else hi = mid;
+      }
+      if (poly(lo, neg, 24) == q && poly(lo, neg, 18) == r && lo.bits() <= 64) {
+        c.bn = 1;
+        c.u_neg = (uint32_t)neg;
+        c.u_bits = (uint32_t)lo.bits();
+        lo.to_words(c.u_abs, 2);
+        p->derived["bn_u"] = {lo};
+      }
+    }
+  }
   c.tatebits = (uint32_t)te.bits();
   return 0;
 }

@@ -20,8 +20,29 @@ constexpr int kWS = 20;        // wire bytes per coordinate (arith/montfp.c:577)
 
 struct Fq { uint32_t v[kNS]; };
 
+// PBC_FQ_CALL = 1: one out-of-line copy of the multiplier and of the squarer, operands and result
+// by value (five registers each way).  The tower routines contain dozens of products; fully inlined
+// they outgrow the instruction cache (ncu: stall_no_instruction was the top stall of k_d_miller).
+#ifndef PBC_FQ_CALL
+#define PBC_FQ_CALL 1
+#endif
+#if PBC_FQ_CALL
+__device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) {
+  Fq r;
+  mont_mul_ps<kNS, false>(r.v, a.v, b.v);
+  return r;
+}
+__device__ __noinline__ Fq fq_sqr_call(Fq a) {
+  Fq r;
+  mont_sqr_ps<kNS, false>(r.v, a.v);
+  return r;
+}
+__device__ __forceinline__ void fq_mul(Fq& r, const Fq& a, const Fq& b) { r = fq_mul_call(a, b); }
+__device__ __forceinline__ void fq_sqr(Fq& r, const Fq& a) { r = fq_sqr_call(a); }
+#else
 __device__ __forceinline__ void fq_mul(Fq& r, const Fq& a, const Fq& b) { mont_mul_ps<kNS, false>(r.v, a.v, b.v); }
 __device__ __forceinline__ void fq_sqr(Fq& r, const Fq& a) { mont_sqr_ps<kNS, false>(r.v, a.v); }
+#endif
 __device__ __forceinline__ void fq_add(Fq& r, const Fq& a, const Fq& b) { fp_add<kNS, false>(r.v, a.v, b.v); }
 __device__ __forceinline__ void fq_sub(Fq& r, const Fq& a, const Fq& b) { fp_sub<kNS>(r.v, a.v, b.v); }
 __device__ __forceinline__ void fq_dbl(Fq& r, const Fq& a) { fp_add<kNS, false>(r.v, a.v, a.v); }

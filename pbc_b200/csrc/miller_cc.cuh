@@ -16,6 +16,11 @@
 #pragma once
 #include "fq_small.cuh"
 
+// resident blocks per SM the F/D kernels are compiled for (caps registers at 65536 / (BLOCK * this))
+#ifndef PBC_CC_MINBLOCKS
+#define PBC_CC_MINBLOCKS 4
+#endif
+
 namespace pbcb200 {
 
 struct CCConsts {

@@ -226,7 +226,7 @@ __device__ __forceinline__ void f6d_ld_global(F6D& v, const uint32_t* g, size_t 
 
 // P: 40 bytes each (stride1 = 0 shares one P), Q: n x 120 bytes (x: 3 coefficients, y: 3).
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, PBC_CC_MINBLOCKS)
 k_d_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_t* __restrict__ mv,
            uint32_t* __restrict__ flag, size_t n, size_t stride1) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -268,7 +268,7 @@ k_d_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_
 
 // cc_pairings_affine (ecc/d_param.c:710-736): product of the k Miller values, one final power.
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, PBC_CC_MINBLOCKS)
 k_d_prod(const uint32_t* __restrict__ mv_in, const uint32_t* __restrict__ flag_in,
          uint32_t* __restrict__ mv_out, uint32_t* __restrict__ flag_out, size_t k, size_t n_out,
          size_t n_in) {
@@ -337,7 +337,7 @@ __device__ __noinline__ void f6d_final_exp(F3& out0, F3& out1, F6D& f) {
 // cc_tatepower, k = 6 branch (ecc/d_param.c:505-564) + lucas_even (:441-502).
 // out: n x 120 bytes: real half (3 coefficients) then imaginary half.
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, PBC_CC_MINBLOCKS)
 k_d_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
              uint8_t* __restrict__ out, size_t n) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;

@@ -33,7 +33,13 @@ struct FConsts {
   uint32_t xpowq8[2][kNS];
   uint32_t tateexp[16];            // (q^4 - q^2 + 1) / r   (:408-420), plain integer
   uint32_t tatebits;
-  uint32_t pad[3];
+  // BN structure (q = 36u^4 + 36u^3 + 24u^2 + 6u + 1, what f_param gen produces, ecc/f_param.c:449-):
+  uint32_t bn;                     // 1 if u was recovered at init; 0 -> generic 472-bit power
+  uint32_t u_neg;                  // sign of u
+  uint32_t u_bits;
+  uint32_t u_abs[2];               // |u|
+  uint32_t pad[2];
+  uint32_t frob[3][5][2][kNS];     // frob[k-1][i-1] = xi^(i (q^k - 1)/6): x^i -> frob * x^i under q^k
 };
 __constant__ FConsts c_f;
 
@@ -302,7 +308,7 @@ __device__ __forceinline__ void f12_ld_global(F12& v, const uint32_t* g, size_t 
 // P: n1 x 40 bytes (stride1 = 0 shares one P: pairing_pp_*), Q: n x 80 bytes.
 // mv: [60][n] words, flag[n]: 1 = both inputs finite points on their curves.
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, PBC_CC_MINBLOCKS)
 k_f_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_t* __restrict__ mv,
            uint32_t* __restrict__ flag, size_t n, size_t stride1) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -339,7 +345,7 @@ k_f_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_
 // exponentiation is a homomorphism, so the k Miller values are multiplied here and exponentiated
 // once.  Any O input -> identity (include/pbc_pairing.h:161-168).
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, PBC_CC_MINBLOCKS)
 k_f_prod(const uint32_t* __restrict__ mv_in, const uint32_t* __restrict__ flag_in,
          uint32_t* __restrict__ mv_out, uint32_t* __restrict__ flag_out, size_t k, size_t n_out,
          size_t n_in) {
@@ -371,29 +377,98 @@ __device__ __noinline__ void f12_qpower(F12& r, const F12& f, const uint32_t e[2
   }
 }
 
-// f_tateexp (ecc/f_param.c:250-283)
-__device__ __noinline__ void f12_final_exp(F12& acc, F12& f) {
-  F12 x, y;
-  f12_qpower(y, f, c_f.xpowq8);
-  f12_qpower(x, f, c_f.xpowq6);
-  f12_mul(&y, &y, &x);                 // f^(q^8 + q^6)
-  f12_qpower(x, f, c_f.xpowq2);
-  f12_mul(&x, &x, &f);                 // f^(q^2 + 1)
-  f12_inv(&x, &x);
-  f12_mul(&f, &y, &x);
-  // generic_pow_mpz's sliding window (arith/field.c:14-126) computes the same power
-  acc = f;
-  for (int j = (int)c_f.tatebits - 2; j >= 0; j--) {
-    f12_sqr(&acc);
-    if ((c_f.tateexp[j >> 5] >> (j & 31)) & 1u) f12_mul(&acc, &acc, &f);
+// f^(q^6): x -> -x
+__device__ __forceinline__ void f12_conj(F12& r, const F12& f) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    if (i & 1) f2_neg(r.c[i], f.c[i]); else r.c[i] = f.c[i];
   }
+}
+// f^(q^k), k = 1, 2, 3: coefficient i is conjugated in F_q^2 for odd k and scaled by frob[k-1][i-1]
+__device__ __noinline__ void f12_frob(F12& r, const F12& f, int k) {
+  F2 t;
+  r.c[0] = f.c[0];
+  if (k & 1) fq_neg(r.c[0].b, f.c[0].b);
+#pragma unroll 1
+  for (int i = 1; i < 6; i++) {
+    t = f.c[i];
+    if (k & 1) fq_neg(t.b, t.b);
+    f2_mul(&r.c[i], &t, f2_const(c_f.frob[k - 1][i - 1]));
+  }
+}
+// f^u for the BN parameter u (on the cyclotomic subgroup the inverse is the conjugate)
+__device__ __noinline__ void f12_pow_u(F12& r, const F12& f) {
+  F12 acc;
+  acc = f;
+  for (int j = (int)c_f.u_bits - 2; j >= 0; j--) {
+    f12_sqr(&acc);
+    if ((c_f.u_abs[j >> 5] >> (j & 31)) & 1u) f12_mul(&acc, &acc, &f);
+  }
+  if (c_f.u_neg) f12_conj(r, acc); else r = acc;
+}
+
+// f_tateexp (ecc/f_param.c:250-283): f^((q^6 - 1)(q^2 + 1)) then the power (q^4 - q^2 + 1)/r.
+// Same value, different route (tools/proto_f_finalexp.py checks it against the oracle):
+//   easy part  g = conj(f)/f,  f <- g^(q^2) g             (the reference multiplies four q-powers)
+//   hard part  (q^4 - q^2 + 1)/r = l0 + l1 q + l2 q^2 + q^3 with l_i polynomials in the BN
+//              parameter u: three powers by u (39 bits for f.param) and the fixed multiplication
+//              chain of Scott et al. -- about 120 squarings instead of the 472 of the windowed power
+//              the reference runs (arith/field.c:14-126).  Parameter sets that are not of BN form
+//              take the generic square-and-multiply over c_f.tateexp.
+__device__ __noinline__ void f12_final_exp(F12& acc, F12& f) {
+  F12 fu, fu2, fu3, t0, t1, x, y;
+  f12_inv(&x, &f);
+  f12_conj(y, f);
+  f12_mul(&x, &x, &y);                 // f^(q^6 - 1)
+  f12_frob(y, x, 2);
+  f12_mul(&f, &y, &x);                 // ^(q^2 + 1)
+  if (!c_f.bn) {
+    acc = f;
+    for (int j = (int)c_f.tatebits - 2; j >= 0; j--) {
+      f12_sqr(&acc);
+      if ((c_f.tateexp[j >> 5] >> (j & 31)) & 1u) f12_mul(&acc, &acc, &f);
+    }
+    return;
+  }
+  f12_pow_u(fu, f);
+  f12_pow_u(fu2, fu);
+  f12_pow_u(fu3, fu2);
+  f12_frob(x, fu3, 1);
+  f12_mul(&x, &x, &fu3);
+  f12_conj(t0, x);                     // y6 = 1/(f^(u^3) f^(u^3 q))
+  f12_sqr(&t0);
+  f12_frob(x, fu2, 1);
+  f12_mul(&x, &x, &fu);
+  f12_conj(y, x);                      // y4 = 1/(f^u f^(u^2 q))
+  f12_mul(&t0, &t0, &y);
+  f12_conj(y, fu2);                    // y5 = 1/f^(u^2)
+  f12_mul(&t0, &t0, &y);
+  f12_frob(x, fu, 1);
+  f12_conj(t1, x);                     // y3 = 1/f^(u q)
+  f12_mul(&t1, &t1, &y);
+  f12_mul(&t1, &t1, &t0);
+  f12_frob(x, fu2, 2);                 // y2 = f^(u^2 q^2)
+  f12_mul(&t0, &t0, &x);
+  f12_sqr(&t1);
+  f12_mul(&t1, &t1, &t0);
+  f12_sqr(&t1);
+  f12_conj(y, f);                      // y1 = 1/f
+  f12_mul(&t0, &t1, &y);
+  f12_frob(x, f, 1);
+  f12_frob(y, f, 2);
+  f12_mul(&x, &x, &y);
+  f12_frob(y, f, 3);
+  f12_mul(&x, &x, &y);                 // y0 = f^q f^(q^2) f^(q^3)
+  f12_mul(&t1, &t1, &x);
+  f12_sqr(&t0);
+  f12_mul(&acc, &t0, &t1);
 }
 
 // f_tateexp (ecc/f_param.c:250-283): f^((q^6 - 1)(q^2 + 1)) by Frobenius constants and one
 // inversion, then the 472-bit power (q^4 - q^2 + 1)/r.  out: n x 240 bytes, coefficient order
 // x^0..x^5, each (re, im) (arith/poly.c:718-727, arith/fieldquadratic.c:323-329).
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, PBC_CC_MINBLOCKS)
 k_f_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
              uint8_t* __restrict__ out, size_t n) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;

@@ -96,6 +96,10 @@ class Pairing:
             raise PairingError(last_error())
         return out.raw[:n_out * self.gt_len]
 
+    def prod_apply_into(self, out, in1, in2, k: int, n_out: int):
+        if lib.pbc_b200_prod_pairings_apply(self._h, _addr(out), _addr(in1), _addr(in2), k, n_out):
+            raise PairingError(last_error())
+
     def prod_apply_device(self, d_out, d_in1, d_in2, k, n_out, stream=0):
         if lib.pbc_b200_prod_pairings_apply_device(self._h, d_out, d_in1, d_in2, k, n_out, stream):
             raise PairingError(last_error())

@@ -106,3 +106,127 @@ def build_batch(Pb, Qb, n: int, offset: int = 0):
     Qa = np.frombuffer(b"".join(Qb), dtype=np.uint8).reshape(g, lq)
     k = np.arange(offset, offset + n, dtype=np.int64)
     return Pa[k % g].reshape(-1), Qa[(k // g + 7 * k) % g].reshape(-1)
+
+
+# ---------------------------------------------------------------------------------------------
+# Types F and D: grids of G1 / G2 points grown from seed points by repeated affine addition.
+# G2 lives on a twist over F_q^2 (F) or F_q^3 (D); neither field has a cheap square root here
+# (q = 1 mod 4 for d159), so the walks start from points the caller supplies (bench.py passes
+# the committed reference fixtures): P_i = P_0 + i G stays in the subgroup of its seeds.
+# ---------------------------------------------------------------------------------------------
+class _ExtField:
+    """F_q[x]/(x^n + m[n-1] x^(n-1) + ... + m[0]); elements are tuples of n residues."""
+
+    def __init__(self, q, low):
+        self.q, self.low, self.n = q, tuple(c % q for c in low), len(low)
+        self.zero = (0,) * self.n
+        self.one = (1,) + (0,) * (self.n - 1)
+
+    def add(self, a, b):
+        return tuple((x + y) % self.q for x, y in zip(a, b))
+
+    def sub(self, a, b):
+        return tuple((x - y) % self.q for x, y in zip(a, b))
+
+    def mul(self, a, b):
+        q, n = self.q, self.n
+        d = [0] * (2 * n - 1)
+        for i in range(n):
+            for j in range(n):
+                d[i + j] = (d[i + j] + a[i] * b[j]) % q
+        for k in range(2 * n - 2, n - 1, -1):
+            t, d[k] = d[k], 0
+            for i in range(n):
+                d[k - n + i] = (d[k - n + i] - t * self.low[i]) % q
+        return tuple(d[:n])
+
+    def inv(self, a):
+        # solve (multiplication-by-a matrix) y = 1 over F_q
+        q, n = self.q, self.n
+        x = tuple(1 if i == 1 else 0 for i in range(n)) if n > 1 else None
+        cols, cur = [], a
+        for _ in range(n):
+            cols.append(cur)
+            cur = self.mul(cur, x) if n > 1 else cur
+        M = [[cols[j][i] for j in range(n)] + [1 if i == 0 else 0] for i in range(n)]
+        for c in range(n):
+            piv = next(r for r in range(c, n) if M[r][c])
+            M[c], M[piv] = M[piv], M[c]
+            iv = pow(M[c][c], -1, q)
+            M[c] = [v * iv % q for v in M[c]]
+            for r in range(n):
+                if r != c and M[r][c]:
+                    f = M[r][c]
+                    M[r] = [(v - f * w) % q for v, w in zip(M[r], M[c])]
+        return tuple(M[i][n] for i in range(n))
+
+    def embed(self, k):
+        return (k % self.q,) + (0,) * (self.n - 1)
+
+
+class _ExtCurve:
+    """y^2 = x^3 + a x + b over an _ExtField, affine"""
+
+    def __init__(self, K, a, b):
+        self.K, self.a, self.b = K, a, b
+
+    def add(self, P, Q):
+        K = self.K
+        if P is None:
+            return Q
+        if Q is None:
+            return P
+        (x1, y1), (x2, y2) = P, Q
+        if x1 == x2:
+            if K.add(y1, y2) == K.zero:
+                return None
+            x1s = K.mul(x1, x1)
+            lam = K.mul(K.add(K.add(K.add(x1s, x1s), x1s), self.a), K.inv(K.add(y1, y1)))
+        else:
+            lam = K.mul(K.sub(y2, y1), K.inv(K.sub(x2, x1)))
+        x3 = K.sub(K.sub(K.mul(lam, lam), x1), x2)
+        return (x3, K.sub(K.mul(lam, K.sub(x1, x3)), y1))
+
+    def on_curve(self, P):
+        K = self.K
+        x, y = P
+        return K.mul(y, y) == K.add(K.mul(K.add(K.mul(x, x), self.a), x), self.b)
+
+
+def _dec(K, bs, width=20):
+    n = K.n
+    xs = [int.from_bytes(bs[i * width:(i + 1) * width], "big") for i in range(2 * n)]
+    return (tuple(xs[:n]), tuple(xs[n:]))
+
+
+def _enc(P, width=20):
+    return b"".join(c.to_bytes(width, "big") for c in P[0]) + b"".join(c.to_bytes(width, "big") for c in P[1])
+
+
+def _walk(E, start, step, g):
+    out, cur = [], start
+    for _ in range(g):
+        out.append(cur)
+        cur = E.add(cur, step)
+    return out
+
+
+def type_fd_points(param: dict, seeds_g1, seeds_g2, g: int):
+    """2 x g distinct points (wire bytes) for a type f or type d (k = 6) parameter set, grown
+    from two seed points per group (wire bytes, e.g. reference fixtures)."""
+    q = param["q"]
+    Fq = _ExtField(q, [0])           # F_q itself as a degree-1 "extension": tuples of length 1
+    if param["type"] == "f":
+        E1 = _ExtCurve(Fq, Fq.zero, Fq.embed(param["b"]))
+        K2 = _ExtField(q, [-param["beta"], 0])                       # s^2 = beta
+        xi = ((-param["alpha0"]) % q, (-param["alpha1"]) % q)
+        E2 = _ExtCurve(K2, K2.zero, K2.mul(xi, K2.embed(param["b"])))
+    else:
+        E1 = _ExtCurve(Fq, Fq.embed(param["a"]), Fq.embed(param["b"]))
+        K2 = _ExtField(q, [param["coeff0"], param["coeff1"], param["coeff2"]])
+        v = param["nqr"] % q
+        E2 = _ExtCurve(K2, K2.embed(param["a"] * v * v), K2.embed(param["b"] * v * v * v))
+    P0, G = (_dec(Fq, s) for s in seeds_g1[:2])
+    Q0, H = (_dec(K2, s) for s in seeds_g2[:2])
+    assert all(E1.on_curve(p) for p in (P0, G)) and all(E2.on_curve(p) for p in (Q0, H))
+    return [_enc(p) for p in _walk(E1, P0, G, g)], [_enc(p) for p in _walk(E2, Q0, H, g)]

@@ -99,3 +99,21 @@ def test_derived_constants_match_oracle(built):
     assert d.derived_constant("nqrinv", 20) == [od.nqrinv[0]]
     assert d.derived_constant("nqrinv2", 20) == [od.nqrinv2[0]]
     assert d.derived_constant("phikonr", 32) == [od.phikonr]
+
+
+def test_bn_parameter_and_frobenius_tables(built):
+    """Type F init recovers the BN parameter u from q and r and tabulates xi^(i (q^k - 1)/6)."""
+    from pbc_b200.params import PARAMS
+    from oracle import pbc_oracle as O
+    f, of = built.Pairing(PARAMS["f"]), O.pairing_from_param(PARAMS["f"])
+    q, F2 = of.q, of.Fq2
+    (u,) = f.derived_constant("bn_u", 8)
+    assert 36 * u ** 4 + 36 * u ** 3 + 24 * u ** 2 + 6 * u + 1 == q
+    for k in (1, 2, 3):
+        g = F2.pow(of.negalpha, (q ** k - 1) // 6)
+        got = f.derived_constant("frob%d" % k, 20)
+        want = []
+        for i in range(1, 6):
+            want.extend(F2.pow(g, i))
+        assert got == want
+    assert tuple(f.derived_constant("frob2", 20)[:2]) == of.xpowq2
