@@ -71,7 +71,9 @@ __global__ void k_fpmul_chain(uint32_t* __restrict__ out, const uint32_t* __rest
 }
 
 // Same chain through the shared-memory slot machine (what the pairing kernels execute).
-template <int N, bool FULL, int BLOCK>
+// MIX 0: multiplications only; 1: one multiplication + one addition per step as separate calls (the
+// Miller loop's mix is 19 : 22); 2: the same work as one fused call.
+template <int N, bool FULL, int BLOCK, int MIX>
 __global__ void __launch_bounds__(BLOCK)
 k_fpmul_slots(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, int iters) {
   using O = Ops<N, FULL, BLOCK>;
@@ -80,7 +82,11 @@ k_fpmul_slots(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, int i
 #pragma unroll
   for (int k = 0; k < N; k++) { a[k] = in[(2 * k) * T + t]; b[k] = in[(2 * k + 1) * T + t]; }
   O::st(0, a); O::st(1, b);
-  for (int i = 0; i < iters; i++) O::mul(0, 0, 1);
+  for (int i = 0; i < iters; i++) {
+    if (MIX == 0) O::mul(0, 0, 1);
+    else if (MIX == 1) { O::mul(0, 0, 1); O::add(0, 0, 1); }
+    else O::fmul(0, 0, 1, O::F_ADD_C1(1), 0, 0, 1, 0);
+  }
   O::ld(a, 0);
 #pragma unroll
   for (int k = 0; k < N; k++) out[k * T + t] = a[k];

@@ -373,7 +373,7 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
       CUDA_OK(allow_smem(k_a_miller<kBlockMiller>, kSmemAMiller));
       CUDA_OK(allow_smem(k_a_finalexp<kBlockFinal>, kSmemAFinal));
       CUDA_OK(allow_smem(k_batch_invert<kNA, true, kBlockInv>, kSmemInv16));
-      CUDA_OK(allow_smem(k_fpmul_slots<kNA, true, 128>, 2 * 64 * 128));
+      CUDA_OK(allow_smem(k_fpmul_slots<kNA, true, 128, 0>, 2 * 64 * 128));
       CUDA_OK(allow_smem(k_a_prod<kBlockProd>, kSmemAProd));
       CUDA_OK(allow_smem(k_a_pp_init<32>, kSmemAPPInit));
       CUDA_OK(allow_smem(k_a_pp_apply<kBlockMiller>, kSmemAPPApply));
@@ -550,6 +550,7 @@ static int run_host(pbc_b200_pairing_s* p, const Job& job, unsigned char* out, c
   CUDA_OK(cudaGetDevice(&cur));
   if (p->ndev <= 1) return run_slice(p, cur, job, out, in1, in2, n);
   int nd = p->ndev;
+  if ((int)p->ctx.size() < nd) p->ctx.resize(nd);   // sized here: the per-device threads must not resize it
   std::vector<int> rc(nd, 0);
   std::vector<std::string> msg(nd);
   std::vector<std::thread> th;
@@ -751,7 +752,9 @@ double pbc_b200_bench_fpmul(pbc_b200_pairing_t* p, int mode, int blocks, int ite
       if (mode == 0) k_fpmul_chain<kNA, true, 0><<<blocks, threads, 0, st>>>(out, in, iters);
       else if (mode == 2) k_fpmul_chain<kNA, true, 1><<<blocks, threads, 0, st>>>(out, in, iters);
       else if (mode == 3) k_fpmul_chain<kNA, true, 2><<<blocks, threads, 0, st>>>(out, in, iters);
-      else k_fpmul_slots<kNA, true, 128><<<blocks, threads, 2 * 64 * 128, st>>>(out, in, iters);
+      else if (mode == 4) k_fpmul_slots<kNA, true, 128, 1><<<blocks, threads, 2 * 64 * 128, st>>>(out, in, iters);
+      else if (mode == 5) k_fpmul_slots<kNA, true, 128, 2><<<blocks, threads, 2 * 64 * 128, st>>>(out, in, iters);
+      else k_fpmul_slots<kNA, true, 128, 0><<<blocks, threads, 2 * 64 * 128, st>>>(out, in, iters);
     } else {
       k_fqmul_chain<<<blocks, threads, 0, st>>>(out, in, iters, mode == 3 ? 1 : 0);
     }

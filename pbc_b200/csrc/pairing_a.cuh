@@ -26,6 +26,10 @@ struct AConsts {
 };
 __constant__ AConsts c_a;
 
+#ifndef PBC_A_FUSED
+#define PBC_A_FUSED 0
+#endif
+
 constexpr int kNA = 16;        // 32-bit limbs of the 512-bit prime
 constexpr int kWA = 64;        // wire bytes per coordinate
 
@@ -104,6 +108,37 @@ __device__ __forceinline__ void a_double_step() {
   a_fmul<O>(aF0, aF1, aT4, aT3, aT0, aT1, aT2);
 }
 
+// The same step with the additive operations folded into the multiply calls (Ops::fmul / fsqr):
+// 19 multiplier calls + 1 subtraction instead of 19 + 22 separate calls.  Values are identical.
+//   S1 = 2 F0 F1, S0 = (F0+F1)(F0-F1)                      f^2  (F0, F1 are free afterwards)
+//   M = Z2^2 + 3 X^2, Y2 = Y^2, S = 4 X Y2
+//   L0 = (M Z2) Qx + (X M - 2 Y2),  Z' = 2 Y Z,  L1 = (Z' Z2) Qy,  Z2' = Z'^2
+//   X' = M^2 - 2 S,  Y' = M (S - X') - 8 Y2^2
+//   f' = (S0 + i S1)(L0 + i L1)
+template <class O>
+__device__ __forceinline__ void a_double_step_fused() {
+  O::fmul(aT4, aF0, aF1, O::F_DBL(1), 0, 0, 0, 0);                        // S1
+  O::fmul(aT5, aF0, aF0, O::F_ADD_A | O::F_SUB_B, aF1, aF1, 0, 0);        // S0
+  O::fsqr(aT0, aX, 0, 0, 0);                                              // X^2
+  O::fsqr(aT0, aZ2, O::F_ADD_C1(3), aT0, 0);                              // M
+  O::fsqr(aT1, aY, 0, 0, 0);                                              // Y2
+  O::fmul(aT2, aX, aT1, O::F_DBL(2), 0, 0, 0, 0);                         // S
+  O::fmul(aT3, aT0, aZ2, 0, 0, 0, 0, 0);                                  // M Z2
+  O::fmul(aF0, aX, aT0, O::F_SUB_C1(2), 0, 0, aT1, 0);                    // X M - 2 Y2
+  O::fmul(aF0, aT3, aQX, O::F_ADD_C1(1), 0, 0, aF0, 0);                   // L0
+  O::fmul(aZ, aY, aZ, O::F_DBL(1), 0, 0, 0, 0);                           // Z'
+  O::fmul(aT3, aZ, aZ2, 0, 0, 0, 0, 0);
+  O::fmul(aF1, aT3, aQY, 0, 0, 0, 0, 0);                                  // L1
+  O::fsqr(aZ2, aZ, 0, 0, 0);
+  O::fsqr(aX, aT0, O::F_SUB_C1(2), aT2, 0);                               // X'
+  O::fsqr(aT1, aT1, O::F_DBL(3), 0, 0);                                   // 8 Y2^2
+  O::fmul(aY, aT0, aT2, O::F_SUB_B | O::F_SUB_C1(1), 0, aX, aT1, 0);      // Y'
+  O::fmul(aT0, aT5, aF0, 0, 0, 0, 0, 0);                                  // U0 = S0 L0
+  O::fmul(aT3, aT4, aF1, 0, 0, 0, 0, 0);                                  // U1 = S1 L1
+  O::fmul(aF1, aT5, aF0, O::F_ADD_A | O::F_ADD_B | O::F_SUB_C1(1) | O::F_SUB_C2(1), aT4, aF1, aT0, aT3);
+  O::sub(aF0, aT0, aT3);
+}
+
 // f: [2][4][n] uint4 (Montgomery F_q^2), dprod: [4][n] uint4 = N(f) f0 f1 (0 marks "output
 // identity"), save: [5][4][n] uint4 scratch for V1 and f1.
 template <int BLOCK>
@@ -136,7 +171,11 @@ k_a_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4* 
       O::st_global(save, 3, n, idx, aF0);
       O::st_global(save, 4, n, idx, aT1);
     }
+#if PBC_A_FUSED
+    a_double_step_fused<O>();
+#else
     a_double_step<O>();
+#endif
   }
   if (!live) return;
 
