@@ -103,6 +103,8 @@ struct pbc_b200_pairing_s {
   DConsts d;
   int ndev = 1;
   bool profile = false;        // record CUDA events between the kernels of the device-API path
+  bool force_reference_basis = false;   // test switches, from "b200_*" keys of the parameter text
+  bool force_generic_final_exp = false;
   std::vector<DevCtx> ctx;     // indexed by device ordinal
   std::map<std::string, std::vector<BigUInt>> derived;   // canonical values of the derived constants (tests)
   std::mutex mu;
@@ -213,6 +215,72 @@ static void fill_cc(CCConsts* c, const BigUInt& A, const BigUInt& B, const BigUI
   c->a_is_zero = (A % q).is_zero() ? 1u : 0u;
 }
 
+// Internal basis for type F (tools/proto_f_nice_basis.py is the executable specification):
+//   K = F_q[i]/(i^2+1) (q = 3 mod 4), sigma^2 = -beta, phi2(a + b s) = a + sigma b i,
+//   xi' = a' + b' i small with phi2(xi)/xi' a sixth power, tau^6 xi' = phi2(xi).
+// The sixth root: N = q^2 - 1 = S m with S = 2^e2 3^e3, 6 t = 1 + k m; w = c^t has w^6 = c (c^m)^k and the
+// correction lives in the cyclic subgroup of order S generated by phi2(xi)^m (xi is neither a square
+// nor a cube), searched exhaustively (S = 144 for f.param).
+struct FBasis {
+  bool ok = false;
+  BigUInt sigma;
+  uint32_t a = 0, b = 0;
+  HostF2 tau, xi1;
+};
+static FBasis find_f_basis(const BigUInt& q, const BigUInt& beta, const HostF2& xi) {
+  FBasis B;
+  if (q.word(0) % 4 != 3) return B;
+  BigUInt one(1), negbeta = beta.is_zero() ? beta : q - beta;
+  B.sigma = BigUInt::powmod(negbeta, (q + one) / BigUInt(4), q);
+  if (!(BigUInt::mulmod(B.sigma, B.sigma, q) == negbeta)) return B;
+  HostF2Field K{q, q - one};                       // i^2 = -1
+  B.xi1 = HostF2{xi.a, BigUInt::mulmod(B.sigma, xi.b, q)};
+  BigUInt N = q * q - one, m = N, two(2), three(3), six(6);
+  uint64_t S = 1;
+  while ((m % two).is_zero()) { m = m / two; S *= 2; if (S > 4096) return B; }
+  while ((m % three).is_zero()) { m = m / three; S *= 3; if (S > 4096) return B; }
+  uint32_t k = 0;
+  BigUInt t;
+  for (k = 1; k <= 6; k++) {
+    BigUInt num = one + m * BigUInt(k);
+    if ((num % six).is_zero()) { t = num / six; break; }
+  }
+  if (k > 6) return B;
+  HostF2 g = K.pow(B.xi1, m), g6 = K.pow(g, six);
+  HostF2 unit;
+  unit.a = one;
+  BigUInt N6 = N / six;
+  const uint32_t kMaxSmall = 6;
+  for (uint32_t total = 1; total <= 2 * kMaxSmall; total++) {
+    for (uint32_t b = 1; b <= total; b++) {
+      uint32_t a = total - b;
+      if (a > kMaxSmall || b > kMaxSmall) continue;
+      HostF2 xs{BigUInt(a), BigUInt(b)};
+      HostF2 c = K.mul(B.xi1, K.inv(xs));
+      HostF2 chk = K.pow(c, N6);
+      if (!(chk.a == one && chk.b.is_zero())) continue;
+      HostF2 w = K.pow(c, t);
+      HostF2 D = K.inv(K.pow(K.pow(c, m), BigUInt(k)));
+      HostF2 h = unit, h6 = unit;
+      for (uint64_t j = 0; j < S; j++) {
+        if (h6.a == D.a && h6.b == D.b) {
+          B.tau = K.mul(w, h);
+          HostF2 back = K.mul(K.pow(B.tau, six), xs);
+          if (back.a == B.xi1.a && back.b == B.xi1.b) {
+            B.ok = true;
+            B.a = a;
+            B.b = b;
+            return B;
+          }
+        }
+        h = K.mul(h, g);
+        h6 = K.mul(h6, g6);
+      }
+    }
+  }
+  return B;
+}
+
 // f_init_pairing (ecc/f_param.c:335-447)
 static int init_type_f(pbc_b200_pairing_s* p, const std::map<std::string, std::string>& tab) {
   BigUInt q, r, b, beta, a0, a1;
@@ -228,34 +296,71 @@ static int init_type_f(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   p->g1_len = 2 * kWS; p->g2_len = 4 * kWS; p->gt_len = 12 * kWS;
   fill_fp_consts(&p->fp, q, kNS);
   fill_cc(&p->cc, BigUInt(), b, r, q);
-  HostF2Field K{q, beta % q};
+  HostF2Field Kref{q, beta % q};
   HostF2 alpha{a0 % q, a1 % q};
-  HostF2 xi = K.neg(alpha);
+  HostF2 xi = Kref.neg(alpha);
   if (xi.a.is_zero() && xi.b.is_zero()) return fail("type f: alpha is zero");
-  HostF2 xi_inv = K.inv(xi);
-  HostF2 tb = K.scale(xi, b % q);
+  HostF2 xi_inv = Kref.inv(xi);
+  HostF2 tb = Kref.scale(xi, b % q);
   BigUInt q2 = q * q, q6 = q2 * q2 * q2, q8 = q6 * q2, one(1);
-  HostF2 x2 = K.pow(xi, (q2 - one) / six), x6 = K.pow(xi, (q6 - one) / six), x8 = K.pow(xi, (q8 - one) / six);
   FConsts& c = p->f;
   memset(&c, 0, sizeof c);
-  to_mont(c.beta, K.beta, q, kNS);
   auto put2 = [&](uint32_t dst[2][kNS], const HostF2& v) { to_mont(dst[0], v.a, q, kNS); to_mont(dst[1], v.b, q, kNS); };
-  put2(c.xi, xi); put2(c.xi_inv, xi_inv); put2(c.twist_b, tb);
-  put2(c.xpowq2, x2); put2(c.xpowq6, x6); put2(c.xpowq8, x8);
   auto rec2 = [&](const char* name, const HostF2& v) { p->derived[name] = {v.a, v.b}; };
+  // reference-basis constants (ecc/f_param.c:422-444), recorded for the tests
+  HostF2 x2 = Kref.pow(xi, (q2 - one) / six), x6 = Kref.pow(xi, (q6 - one) / six), x8 = Kref.pow(xi, (q8 - one) / six);
+  to_mont(c.beta, Kref.beta, q, kNS);
+  put2(c.xi_inv, xi_inv);
+  put2(c.xpowq2, x2); put2(c.xpowq6, x6); put2(c.xpowq8, x8);
   rec2("xi", xi); rec2("xi_inv", xi_inv); rec2("twist_b", tb);
   rec2("xpowq2", x2); rec2("xpowq6", x6); rec2("xpowq8", x8);
+
+  // the basis the kernels compute in
+  FBasis B;
+  if (!p->force_reference_basis) B = find_f_basis(q, Kref.beta, xi);
+  HostF2Field K = B.ok ? HostF2Field{q, q - one} : Kref;
+  HostF2 xi_use = xi, tb_use = tb, kx = xi_inv, ky = xi_inv, unit;
+  unit.a = one;
+  BigUInt sigma = one, sigma_inv = one;
+  std::vector<HostF2> taup(6, unit), tauinv(6, unit);
+  if (B.ok) {
+    sigma = B.sigma;
+    sigma_inv = BigUInt::invmod(sigma, q);
+    auto phi2 = [&](const HostF2& v) { return HostF2{v.a, BigUInt::mulmod(sigma, v.b, q)}; };
+    xi_use = HostF2{BigUInt(B.a), BigUInt(B.b)};
+    tb_use = phi2(tb);
+    for (int j = 1; j < 6; j++) taup[j] = K.mul(taup[j - 1], B.tau);
+    for (int j = 1; j < 6; j++) tauinv[j] = K.inv(taup[j]);
+    HostF2 xi1inv = K.inv(B.xi1);
+    kx = K.mul(xi1inv, taup[4]);
+    ky = K.mul(xi1inv, taup[3]);
+    c.nice = 1;
+    c.xi_a = B.a;
+    c.xi_b = B.b;
+    p->derived["basis_sigma"] = {sigma};
+    p->derived["basis_xi_small"] = {BigUInt(B.a), BigUInt(B.b)};
+    rec2("basis_tau", B.tau);
+  }
+  put2(c.xi, xi_use);
+  put2(c.twist_b, tb_use);
+  put2(c.kx, kx);
+  put2(c.ky, ky);
+  to_mont(c.sigma, sigma, q, kNS);
+  to_mont(c.sigma_inv, sigma_inv, q, kNS);
+  for (int j = 1; j < 6; j++) { put2(c.tau[j - 1], taup[j]); put2(c.tau_inv[j - 1], tauinv[j]); }
+
   BigUInt num = (q2 * q2 + one) - q2, te, rem;
   BigUInt::divmod(num, r, &te, &rem);
   if (!rem.is_zero()) return fail("type f: r does not divide q^4 - q^2 + 1");
   if (te.bits() > 512) return fail("type f: final exponent too large");
   te.to_words(c.tateexp, 16);
+  c.tatebits = (uint32_t)te.bits();
   p->derived["tateexp"] = {te};
-  // Frobenius tables frob[k-1][i-1] = xi^(i (q^k - 1)/6), k = 1, 2, 3
+  // Frobenius tables frob[k-1][i-1] = xi^(i (q^k - 1)/6), k = 1, 2, 3, in the basis in use
   BigUInt q3 = q2 * q;
   const BigUInt* qk[3] = {&q, &q2, &q3};
   for (int k = 0; k < 3; k++) {
-    HostF2 g = K.pow(xi, (*qk[k] - one) / six), acc = g;
+    HostF2 g = K.pow(xi_use, (*qk[k] - one) / six), acc = g;
     std::vector<BigUInt> rec;
     for (int i = 0; i < 5; i++) {
       put2(c.frob[k][i], acc);
@@ -289,7 +394,7 @@ static int init_type_f(pbc_b200_pairing_s* p, const std::map<std::string, std::s
       }
     }
   }
-  c.tatebits = (uint32_t)te.bits();
+  if (p->force_generic_final_exp) c.bn = 0;
   return 0;
 }
 
@@ -610,6 +715,9 @@ int pbc_b200_pairing_init_set_buf(pbc_b200_pairing_t** out, const char* param, s
   pbc_b200_pairing_s* p = new pbc_b200_pairing_s();
   p->id = g_next_id.fetch_add(1);
   int rc;
+  // test switches (ignored by the reference parser, which only looks up the keys it needs)
+  p->force_reference_basis = tab.count("b200_reference_basis") && tab["b200_reference_basis"] != "0";
+  p->force_generic_final_exp = tab.count("b200_generic_final_exp") && tab["b200_generic_final_exp"] != "0";
   if (it->second == "a") rc = init_type_a(p, tab);
   else if (it->second == "f") rc = init_type_f(p, tab);
   else if (it->second == "d") rc = init_type_d(p, tab);

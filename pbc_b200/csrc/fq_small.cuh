@@ -39,13 +39,38 @@ __device__ __noinline__ Fq fq_sqr_call(Fq a) {
 }
 __device__ __forceinline__ void fq_mul(Fq& r, const Fq& a, const Fq& b) { r = fq_mul_call(a, b); }
 __device__ __forceinline__ void fq_sqr(Fq& r, const Fq& a) { r = fq_sqr_call(a); }
+// the hottest tower routines (F_q^2 / F_q^3 products) may still inline their few products: one
+// copy each, no argument shuffling (PBC_HOT_INLINE)
+#ifndef PBC_HOT_INLINE
+#define PBC_HOT_INLINE 0
+#endif
+__device__ __forceinline__ void fq_mul_hot(Fq& r, const Fq& a, const Fq& b) {
+  if (PBC_HOT_INLINE) mont_mul_ps<kNS, false>(r.v, a.v, b.v); else r = fq_mul_call(a, b);
+}
+__device__ __forceinline__ void fq_sqr_hot(Fq& r, const Fq& a) {
+  if (PBC_HOT_INLINE) mont_sqr_ps<kNS, false>(r.v, a.v); else r = fq_sqr_call(a);
+}
 #else
+__device__ __forceinline__ void fq_mul_hot(Fq& r, const Fq& a, const Fq& b) { mont_mul_ps<kNS, false>(r.v, a.v, b.v); }
+__device__ __forceinline__ void fq_sqr_hot(Fq& r, const Fq& a) { mont_sqr_ps<kNS, false>(r.v, a.v); }
 __device__ __forceinline__ void fq_mul(Fq& r, const Fq& a, const Fq& b) { mont_mul_ps<kNS, false>(r.v, a.v, b.v); }
 __device__ __forceinline__ void fq_sqr(Fq& r, const Fq& a) { mont_sqr_ps<kNS, false>(r.v, a.v); }
 #endif
+// PBC_FQ_ADD_CALL = 1: additions and subtractions out of line as well (code size experiment)
+#ifndef PBC_FQ_ADD_CALL
+#define PBC_FQ_ADD_CALL 0
+#endif
+#if PBC_FQ_ADD_CALL
+__device__ __noinline__ Fq fq_add_call(Fq a, Fq b) { Fq r; fp_add<kNS, false>(r.v, a.v, b.v); return r; }
+__device__ __noinline__ Fq fq_sub_call(Fq a, Fq b) { Fq r; fp_sub<kNS>(r.v, a.v, b.v); return r; }
+__device__ __forceinline__ void fq_add(Fq& r, const Fq& a, const Fq& b) { r = fq_add_call(a, b); }
+__device__ __forceinline__ void fq_sub(Fq& r, const Fq& a, const Fq& b) { r = fq_sub_call(a, b); }
+__device__ __forceinline__ void fq_dbl(Fq& r, const Fq& a) { r = fq_add_call(a, a); }
+#else
 __device__ __forceinline__ void fq_add(Fq& r, const Fq& a, const Fq& b) { fp_add<kNS, false>(r.v, a.v, b.v); }
 __device__ __forceinline__ void fq_sub(Fq& r, const Fq& a, const Fq& b) { fp_sub<kNS>(r.v, a.v, b.v); }
 __device__ __forceinline__ void fq_dbl(Fq& r, const Fq& a) { fp_add<kNS, false>(r.v, a.v, a.v); }
+#endif
 __device__ __forceinline__ void fq_neg(Fq& r, const Fq& a) { fp_neg<kNS>(r.v, a.v); }
 __device__ __forceinline__ void fq_halve(Fq& r, const Fq& a) { fp_halve<kNS, false>(r.v, a.v); }
 __device__ __forceinline__ bool fq_is_zero(const Fq& a) { return fp_is_zero<kNS>(a.v); }

@@ -72,31 +72,31 @@ __device__ __forceinline__ void f3_reduce(F3* r, const Fq& d0, const Fq& d1, con
   for (int i = 0; i < 3; i++) {
     const Fq& lo = i == 0 ? d0 : (i == 1 ? d1 : d2);
     fq_set(k, c_d.xpwr3[i]);
-    fq_mul(t, d3, k);
+    fq_mul_hot(t, d3, k);
     fq_add(r->c[i], lo, t);
     fq_set(k, c_d.xpwr4[i]);
-    fq_mul(t, d4, k);
+    fq_mul_hot(t, d4, k);
     fq_add(r->c[i], r->c[i], t);
   }
 }
 __device__ __noinline__ void f3_mul(F3* r, const F3* x, const F3* y) {
   Fq d0, d1, d2, d3, d4, m1, s, t;
-  fq_mul(d0, x->c[0], y->c[0]);
-  fq_mul(m1, x->c[1], y->c[1]);
-  fq_mul(d4, x->c[2], y->c[2]);
+  fq_mul_hot(d0, x->c[0], y->c[0]);
+  fq_mul_hot(m1, x->c[1], y->c[1]);
+  fq_mul_hot(d4, x->c[2], y->c[2]);
   fq_add(s, x->c[0], x->c[1]);
   fq_add(t, y->c[0], y->c[1]);
-  fq_mul(d1, s, t);
+  fq_mul_hot(d1, s, t);
   fq_sub(d1, d1, d0);
   fq_sub(d1, d1, m1);
   fq_add(s, x->c[1], x->c[2]);
   fq_add(t, y->c[1], y->c[2]);
-  fq_mul(d3, s, t);
+  fq_mul_hot(d3, s, t);
   fq_sub(d3, d3, m1);
   fq_sub(d3, d3, d4);
   fq_add(s, x->c[0], x->c[2]);
   fq_add(t, y->c[0], y->c[2]);
-  fq_mul(d2, s, t);
+  fq_mul_hot(d2, s, t);
   fq_sub(d2, d2, d0);
   fq_sub(d2, d2, d4);
   fq_add(d2, d2, m1);
@@ -104,15 +104,15 @@ __device__ __noinline__ void f3_mul(F3* r, const F3* x, const F3* y) {
 }
 __device__ __noinline__ void f3_sqr(F3* r, const F3* x) {
   Fq d0, d1, d2, d3, d4, t;
-  fq_sqr(d0, x->c[0]);
-  fq_sqr(d4, x->c[2]);
-  fq_mul(d1, x->c[0], x->c[1]);
+  fq_sqr_hot(d0, x->c[0]);
+  fq_sqr_hot(d4, x->c[2]);
+  fq_mul_hot(d1, x->c[0], x->c[1]);
   fq_dbl(d1, d1);
-  fq_mul(d3, x->c[1], x->c[2]);
+  fq_mul_hot(d3, x->c[1], x->c[2]);
   fq_dbl(d3, d3);
-  fq_mul(d2, x->c[0], x->c[2]);
+  fq_mul_hot(d2, x->c[0], x->c[2]);
   fq_dbl(d2, d2);
-  fq_sqr(t, x->c[1]);
+  fq_sqr_hot(t, x->c[1]);
   fq_add(d2, d2, t);
   f3_reduce(r, d0, d1, d2, d3, d4);
 }

@@ -40,6 +40,17 @@ struct FConsts {
   uint32_t u_abs[2];               // |u|
   uint32_t pad[2];
   uint32_t frob[3][5][2][kNS];     // frob[k-1][i-1] = xi^(i (q^k - 1)/6): x^i -> frob * x^i under q^k
+  // Internal basis (q = 3 mod 4 and a small xi' found at init; tools/proto_f_nice_basis.py):
+  //   K = F_q[i]/(i^2 + 1),  F_q^12 = K[z]/(z^6 - xi'),  xi' = xi_a + xi_b i with small integers.
+  //   phi2(a + b s) = a + (sigma b) i;  x -> tau z.  When nice == 0 the reference basis is used as is
+  //   (sigma = 1, tau = 1, kx = ky = 1/xi).  xi, twist_b and frob hold the values of the basis in use.
+  uint32_t nice;
+  uint32_t xi_a, xi_b;
+  uint32_t pad2;
+  uint32_t sigma[kNS], sigma_inv[kNS];
+  uint32_t kx[2][kNS], ky[2][kNS];     // second argument: Qx'' = phi2(Qx) kx, Qy'' = phi2(Qy) ky
+  uint32_t tau[5][2][kNS];             // tau^j,  j = 1..5  (wire -> internal, test hook)
+  uint32_t tau_inv[5][2][kNS];         // tau^-j, j = 1..5  (internal -> wire)
 };
 __constant__ FConsts c_f;
 
@@ -54,30 +65,41 @@ __device__ __forceinline__ void f2_neg(F2& r, const F2& x) { fq_neg(r.a, x.a); f
 __device__ __forceinline__ void f2_zero(F2& r) { fq_zero(r.a); fq_zero(r.b); }
 __device__ __forceinline__ bool f2_eq(const F2& x, const F2& y) { return fq_eq(x.a, y.a) && fq_eq(x.b, y.b); }
 
-// (x0 + x1 s)(y0 + y1 s) = x0 y0 + beta x1 y1 + ((x0 + x1)(y0 + y1) - x0 y0 - x1 y1) s
+// (x0 + x1 s)(y0 + y1 s) = x0 y0 + beta x1 y1 + ((x0 + x1)(y0 + y1) - x0 y0 - x1 y1) s;
+// internal basis: beta = -1, three multiplications.
 __device__ __noinline__ void f2_mul(F2* r, const F2* x, const F2* y) {
   Fq t0, t1, t2, u;
   fq_add(t2, x->a, x->b);
   fq_add(u, y->a, y->b);
-  fq_mul(t2, t2, u);
-  fq_mul(t0, x->a, y->a);
-  fq_mul(t1, x->b, y->b);
+  fq_mul_hot(t2, t2, u);
+  fq_mul_hot(t0, x->a, y->a);
+  fq_mul_hot(t1, x->b, y->b);
   fq_sub(t2, t2, t0);
   fq_sub(t2, t2, t1);
-  fq_set(u, c_f.beta);
-  fq_mul(t1, t1, u);
-  fq_add(r->a, t0, t1);
+  if (c_f.nice) {
+    fq_sub(r->a, t0, t1);
+  } else {
+    fq_set(u, c_f.beta);
+    fq_mul(t1, t1, u);
+    fq_add(r->a, t0, t1);
+  }
   r->b = t2;
 }
-// x0^2 + beta x1^2 + 2 x0 x1 s
+// x0^2 + beta x1^2 + 2 x0 x1 s;  internal basis: (x0 + x1)(x0 - x1) + 2 x0 x1 i
 __device__ __noinline__ void f2_sqr(F2* r, const F2* x) {
   Fq t0, t1, t2, u;
-  fq_mul(t2, x->a, x->b);
-  fq_sqr(t0, x->a);
-  fq_sqr(t1, x->b);
-  fq_set(u, c_f.beta);
-  fq_mul(t1, t1, u);
-  fq_add(r->a, t0, t1);
+  fq_mul_hot(t2, x->a, x->b);
+  if (c_f.nice) {
+    fq_add(t0, x->a, x->b);
+    fq_sub(t1, x->a, x->b);
+    fq_mul_hot(r->a, t0, t1);
+  } else {
+    fq_sqr(t0, x->a);
+    fq_sqr(t1, x->b);
+    fq_set(u, c_f.beta);
+    fq_mul(t1, t1, u);
+    fq_add(r->a, t0, t1);
+  }
   fq_dbl(r->b, t2);
 }
 // multiplication by an element of F_q
@@ -88,15 +110,42 @@ __device__ __forceinline__ void f2_scale(F2& r, const F2& x, const Fq& k) { fq_m
 // address taken is __noinline__ and declares them at function scope; inlined helpers take no
 // addresses of their own locals.  Constants are passed as pointers into __constant__ memory.
 __device__ __forceinline__ const F2* f2_const(const uint32_t c[2][kNS]) { return reinterpret_cast<const F2*>(c); }
-__device__ __forceinline__ void f2_mul_xi(F2& r, const F2& x) { f2_mul(&r, &x, f2_const(c_f.xi)); }
+// k x for a small non-negative integer k (double-and-add)
+__device__ __forceinline__ void fq_mul_small(Fq& r, const Fq& x, uint32_t k) {
+  Fq acc;
+  fq_zero(acc);
+  for (int j = 31 - __clz(k | 1u); j >= 0; j--) {
+    fq_dbl(acc, acc);
+    if ((k >> j) & 1u) fq_add(acc, acc, x);
+  }
+  r = acc;
+}
+// r = xi x.  Internal basis: xi' = a + b i with small integers: (a x0 - b x1) + (b x0 + a x1) i.
+__device__ __noinline__ void f2_mul_xi(F2& r, const F2& x) {
+  if (c_f.nice) {
+    Fq p, q2, s2, t;
+    fq_mul_small(p, x.a, c_f.xi_a);
+    fq_mul_small(q2, x.b, c_f.xi_b);
+    fq_mul_small(s2, x.a, c_f.xi_b);
+    fq_mul_small(t, x.b, c_f.xi_a);
+    fq_sub(r.a, p, q2);
+    fq_add(r.b, s2, t);
+  } else {
+    f2_mul(&r, &x, f2_const(c_f.xi));
+  }
+}
 // 1/(x0 + x1 s) = (x0 - x1 s)/(x0^2 - beta x1^2)   (arith/fieldquadratic.c:290-309)
 __device__ __noinline__ void f2_inv(F2* r, const F2* x) {
   Fq t0, t1, u;
   fq_sqr(t0, x->a);
   fq_sqr(t1, x->b);
-  fq_set(u, c_f.beta);
-  fq_mul(t1, t1, u);
-  fq_sub(t0, t0, t1);
+  if (c_f.nice) {
+    fq_add(t0, t0, t1);                // norm x0^2 + x1^2
+  } else {
+    fq_set(u, c_f.beta);
+    fq_mul(t1, t1, u);
+    fq_sub(t0, t0, t1);
+  }
   fq_inv(&t0, &t0);
   fq_mul(r->a, x->a, t0);
   fq_mul(t1, x->b, t0);
@@ -305,6 +354,27 @@ __device__ __forceinline__ void f12_ld_global(F12& v, const uint32_t* g, size_t 
   }
 }
 
+// internal basis -> reference basis (identity when nice == 0): c_j = phi2^-1(d_j tau^-j)
+__device__ __noinline__ void f12_to_reference(F12& v) {
+  Fq k;
+  if (!c_f.nice) return;
+#pragma unroll 1
+  for (int j = 1; j < 6; j++) f2_mul(&v.c[j], &v.c[j], f2_const(c_f.tau_inv[j - 1]));
+  fq_set(k, c_f.sigma_inv);
+#pragma unroll 1
+  for (int j = 0; j < 6; j++) fq_mul(v.c[j].b, v.c[j].b, k);
+}
+// reference basis -> internal basis (test hook)
+__device__ __noinline__ void f12_to_internal(F12& v) {
+  Fq k;
+  if (!c_f.nice) return;
+  fq_set(k, c_f.sigma);
+#pragma unroll 1
+  for (int j = 0; j < 6; j++) fq_mul(v.c[j].b, v.c[j].b, k);
+#pragma unroll 1
+  for (int j = 1; j < 6; j++) f2_mul(&v.c[j], &v.c[j], f2_const(c_f.tau[j - 1]));
+}
+
 // P: n1 x 40 bytes (stride1 = 0 shares one P: pairing_pp_*), Q: n x 80 bytes.
 // mv: [60][n] words, flag[n]: 1 = both inputs finite points on their curves.
 template <int BLOCK>
@@ -313,7 +383,7 @@ k_f_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_
            uint32_t* __restrict__ flag, size_t n, size_t stride1) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (idx >= n) return;
-  Fq xP, yP;
+  Fq xP, yP, yP2;
   const uint8_t* p = P + idx * stride1;
   fq_from_wire(xP, p);
   fq_from_wire(yP, p + kWS);
@@ -326,15 +396,20 @@ k_f_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_
   fq_from_wire(ctx.Qx.b, q + kWS);
   fq_from_wire(ctx.Qy.a, q + 2 * kWS);
   fq_from_wire(ctx.Qy.b, q + 3 * kWS);
-  // Y^2 == X^3 + twist_b on the twist (ecc/curve.c:57-76 over F_q^2)
+  // into the basis in use: phi2(a + b s) = a + (sigma b) i  (sigma = 1 in the reference basis)
+  fq_set(yP2, c_f.sigma);
+  fq_mul(ctx.Qx.b, ctx.Qx.b, yP2);
+  fq_mul(ctx.Qy.b, ctx.Qy.b, yP2);
+  // Y^2 == X^3 + twist_b on the twist (ecc/curve.c:57-76 over F_q^2; phi2 is a field isomorphism)
   f2_sqr(&t, &ctx.Qx);
   f2_mul(&t, &t, &ctx.Qx);
   f2_add(t, t, *f2_const(c_f.twist_b));
   f2_sqr(&u, &ctx.Qy);
   ok = ok && f2_eq(t, u);
-  // untwist (ecc/f_param.c:296-303)
-  f2_mul(&ctx.Qx, &ctx.Qx, f2_const(c_f.xi_inv));
-  f2_mul(&ctx.Qy, &ctx.Qy, f2_const(c_f.xi_inv));
+  // untwist (ecc/f_param.c:296-303) and scale for the line's x^4 / x^3 positions: kx = tau^4 / xi,
+  // ky = tau^3 / xi  (both 1 / xi in the reference basis)
+  f2_mul(&ctx.Qx, &ctx.Qx, f2_const(c_f.kx));
+  f2_mul(&ctx.Qy, &ctx.Qy, f2_const(c_f.ky));
   f12_one(v);
   if (ok) miller_cc<FTower>(&v, xP, yP, &ctx);
   f12_st_global(mv, n, idx, v);
@@ -477,6 +552,7 @@ k_f_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
   if (flag[idx]) {
     f12_ld_global(f, mv, n, idx);
     f12_final_exp(acc, f);
+    f12_to_reference(acc);
   } else {
     f12_one(acc);
   }
@@ -513,6 +589,8 @@ __global__ void k_f_tower_op(int op, uint8_t* __restrict__ out, const uint8_t* _
   F12 x, y, r;
   f12_from_wire(x, a + idx * (12 * kWS));
   f12_from_wire(y, b + idx * (12 * kWS));
+  f12_to_internal(x);
+  f12_to_internal(y);
   switch (op) {
     case 0: f12_mul(&r, &x, &y); break;
     case 1: r = x; f12_sqr(&r); break;
@@ -520,6 +598,7 @@ __global__ void k_f_tower_op(int op, uint8_t* __restrict__ out, const uint8_t* _
     case 3: f12_final_exp(r, x); break;
     default: r = x; f12_mul_line(&r, &y.c[0].a, &y.c[3], &y.c[4]); break;
   }
+  f12_to_reference(r);
   f12_to_wire(out + idx * (12 * kWS), r);
 }
 

@@ -21,10 +21,11 @@ def _bytes(elems):
     return b"".join(b"".join(c.to_bytes(20, "big") for c in e) for e in elems)
 
 
-@pytest.fixture(scope="module")
-def f_env():
+@pytest.fixture(scope="module", params=["internal_basis", "reference_basis"])
+def f_env(request):
     from pbc_b200.pairing import Pairing
-    return Pairing(PARAMS["f"]), O.pairing_from_param(PARAMS["f"])
+    extra = "" if request.param == "internal_basis" else "b200_reference_basis 1\n"
+    return Pairing(PARAMS["f"] + extra), O.pairing_from_param(PARAMS["f"])
 
 
 @pytest.fixture(scope="module")

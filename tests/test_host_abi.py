@@ -102,18 +102,47 @@ def test_derived_constants_match_oracle(built):
 
 
 def test_bn_parameter_and_frobenius_tables(built):
-    """Type F init recovers the BN parameter u from q and r and tabulates xi^(i (q^k - 1)/6)."""
+    """Type F init recovers the BN parameter u from q and r and tabulates xi^(i (q^k - 1)/6) in
+    the basis the kernels use: the reference's (forced by the b200_reference_basis test switch) or
+    the internal one K[z]/(z^6 - xi')."""
     from pbc_b200.params import PARAMS
     from oracle import pbc_oracle as O
-    f, of = built.Pairing(PARAMS["f"]), O.pairing_from_param(PARAMS["f"])
+    of = O.pairing_from_param(PARAMS["f"])
     q, F2 = of.q, of.Fq2
+    f = built.Pairing(PARAMS["f"] + "b200_reference_basis 1\n")
     (u,) = f.derived_constant("bn_u", 8)
     assert 36 * u ** 4 + 36 * u ** 3 + 24 * u ** 2 + 6 * u + 1 == q
     for k in (1, 2, 3):
         g = F2.pow(of.negalpha, (q ** k - 1) // 6)
-        got = f.derived_constant("frob%d" % k, 20)
         want = []
         for i in range(1, 6):
             want.extend(F2.pow(g, i))
-        assert got == want
+        assert f.derived_constant("frob%d" % k, 20) == want
     assert tuple(f.derived_constant("frob2", 20)[:2]) == of.xpowq2
+    with pytest.raises(built.PairingError):
+        f.derived_constant("basis_tau", 20)
+
+
+def test_internal_basis_constants_match_prototype(built):
+    """sigma, xi', tau of the isomorphic tower (engine.cu find_f_basis) vs the executable
+    specification tools/proto_f_nice_basis.py; tau^6 xi' = phi2(xi)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from proto_f_nice_basis import find_basis
+    from pbc_b200.params import PARAMS
+    from oracle import pbc_oracle as O
+    of = O.pairing_from_param(PARAMS["f"])
+    q = of.q
+    B = find_basis(q, of.Fq2.nqr, of.negalpha)
+    f = built.Pairing(PARAMS["f"])
+    assert f.derived_constant("basis_sigma", 20) == [B["sigma"]]
+    assert tuple(f.derived_constant("basis_xi_small", 4)) == B["xi_small"]
+    assert tuple(f.derived_constant("basis_tau", 20)) == B["tau"]
+    K = O.QuadExt(of.Fq, q - 1)
+    assert K.mul(K.pow(B["tau"], 6), B["xi_small"]) == B["xi1"]
+    for k in (1, 2, 3):
+        g = K.pow(B["xi_small"], (q ** k - 1) // 6)
+        want = []
+        for i in range(1, 6):
+            want.extend(K.pow(g, i))
+        assert f.derived_constant("frob%d" % k, 20) == want
