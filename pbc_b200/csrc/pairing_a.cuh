@@ -29,6 +29,9 @@ __constant__ AConsts c_a;
 #ifndef PBC_A_FUSED
 #define PBC_A_FUSED 0
 #endif
+#ifndef PBC_A_W12
+#define PBC_A_W12 1     // Miller loop in weight-(1,2) coordinates (0: Jacobian)
+#endif
 
 constexpr int kNA = 16;        // 32-bit limbs of the 512-bit prime
 constexpr int kWA = 64;        // wire bytes per coordinate
@@ -108,6 +111,51 @@ __device__ __forceinline__ void a_double_step() {
   a_fmul<O>(aF0, aF1, aT4, aT3, aT0, aT1, aT2);
 }
 
+// The step in weight-(1,2) coordinates x = X/Z, y = Y/Z^2 (the doubling of Costello, Lange and
+// Naehrig for y^2 = x^3 + a x, re-derived for a = 1; tools/proto_a_w12.py checks it against the
+// reference fixtures):
+//   A = X^2, B = Y^2, C = Z^2;   X' = (A - C)^2,  Z' = 4 B,
+//   Y' = (2 (A + C)^2 - X') ((A - C + Y)^2 - B - X')
+//   line at phi(Q), up to a factor in F_q^*:  Re = X (A - C) + (3A + C) Z Qx,  Im = ((Y + Z)^2 - B - C) Qy
+// 10 multiplications + 7 squarings per step with the f update (Jacobian form above: 13 + 6), and no
+// Z^2 slot to maintain.
+template <class O>
+__device__ __forceinline__ void a_double_step_w12() {
+  // f = f^2
+  O::add(aT0, aF0, aF1);
+  O::sub(aT1, aF0, aF1);
+  O::mul(aF1, aF0, aF1);
+  O::dbl(aF1, aF1);
+  O::mul(aF0, aT0, aT1);
+  O::sqr(aT0, aX);                 // A
+  O::sqr(aT1, aY);                 // B
+  O::sqr(aT2, aZ);                 // C
+  O::sub(aT3, aT0, aT2);           // A - C
+  O::add(aT4, aT0, aT2);           // A + C
+  O::dbl(aT5, aT0);
+  O::add(aT5, aT5, aT4);           // 3A + C
+  O::mul(aT5, aT5, aZ);
+  O::mul(aT5, aT5, aQX);
+  O::mul(aT0, aX, aT3);
+  O::add(aT5, aT5, aT0);           // Re l
+  O::add(aT0, aY, aZ);
+  O::sqr(aT0, aT0);
+  O::sub(aT0, aT0, aT1);
+  O::sub(aT0, aT0, aT2);           // 2 Y Z
+  O::mul(aT0, aT0, aQY);           // Im l
+  O::dbl(aZ, aT1, 2);              // Z' = 4 B
+  O::sqr(aT4, aT4);                // (A + C)^2
+  O::sqr(aX, aT3);                 // X'
+  O::dbl(aT4, aT4);
+  O::sub(aT4, aT4, aX);            // E
+  O::add(aT2, aT3, aY);
+  O::sqr(aT2, aT2);
+  O::sub(aT2, aT2, aT1);
+  O::sub(aT2, aT2, aX);            // F = 2 Y (A - C)
+  O::mul(aY, aT4, aT2);            // Y'
+  a_fmul<O>(aF0, aF1, aT5, aT0, aT1, aT2, aT3);
+}
+
 // The same step with the additive operations folded into the multiply calls (Ops::fmul / fsqr):
 // 19 multiplier calls + 1 subtraction instead of 19 + 22 separate calls.  Values are identical.
 //   S1 = 2 F0 F1, S0 = (F0+F1)(F0-F1)                      f^2  (F0, F1 are free afterwards)
@@ -171,7 +219,9 @@ k_a_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4* 
       O::st_global(save, 3, n, idx, aF0);
       O::st_global(save, 4, n, idx, aT1);
     }
-#if PBC_A_FUSED
+#if PBC_A_W12
+    a_double_step_w12<O>();
+#elif PBC_A_FUSED
     a_double_step_fused<O>();
 #else
     a_double_step<O>();
@@ -183,6 +233,30 @@ k_a_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4* 
   O::ld_global(aT3, save, 3, n, idx);
   O::ld_global(aT4, save, 4, n, idx);
   a_fmul<O>(aF0, aF1, aT3, aT4, aT0, aT1, aT2);
+#if PBC_A_W12
+  // chord through V = (X, Y, Z) and V1 = (X1, Y1, Z1) in weight-(1,2) coordinates, scaled by
+  // Z^2 Z1^2 (compute_abc_line :114-130):
+  //   a = Y Z1^2 - Y1 Z^2,  b = Z Z1 (X1 Z - X Z1),  c = X Z Y1 - Y X1 Z1
+  O::ld_global(aT0, save, 2, n, idx);          // Z1
+  O::ld_global(aT1, save, 0, n, idx);          // X1
+  O::ld_global(aT5, save, 1, n, idx);          // Y1
+  O::mul(aT2, aT1, aZ);                         // X1 Z
+  O::mul(aT3, aX, aT0);                         // X Z1
+  O::sub(aT2, aT2, aT3);
+  O::mul(aT2, aT2, aZ);
+  O::mul(aT4, aT2, aT0);                        // b
+  O::mul(aT3, aX, aZ);
+  O::mul(aT3, aT3, aT5);                        // X Z Y1
+  O::mul(aT1, aT1, aT0);                        // X1 Z1
+  O::mul(aT1, aT1, aY);                         // Y X1 Z1
+  O::sub(aT3, aT3, aT1);                        // c
+  O::sqr(aT0, aT0);                             // Z1^2
+  O::mul(aT0, aT0, aY);                         // Y Z1^2
+  O::sqr(aT1, aZ);                              // Z^2
+  O::mul(aT1, aT1, aT5);                        // Y1 Z^2
+  O::sub(aT2, aT0, aT1);                        // a
+  O::copy(aZ, aT3);                             // c where the common tail expects it
+#else
   // chord through V=(X,Y,Z) and V1=(X1,Y1,Z1), scaled by Z^3 Z1^3 (compute_abc_line :114-130):
   //   a = Y Z1^3 - Y1 Z^3,  b = X1 Z1 Z^3 - X Z Z1^3,  c = X Z Y1 - Y X1 Z1
   O::ld_global(aT0, save, 2, n, idx);          // Z1
@@ -202,6 +276,7 @@ k_a_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4* 
   O::mul(aT2, aY, aT2);                         // Y Z1^3
   O::mul(aT1, aT0, aT1);                        // Y1 Z^3
   O::sub(aT2, aT2, aT1);                        // a
+#endif
   O::mul(aT2, aT2, aQX);
   O::sub(aT2, aZ, aT2);                         // Re l = c - a Qx
   O::mul(aT4, aT4, aQY);                        // Im l = b Qy
