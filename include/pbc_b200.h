@@ -81,6 +81,25 @@ int pbc_b200_pp_pairings_apply(pbc_b200_pairing_t *p, unsigned char *out, const 
 int pbc_b200_pp_pairings_apply_device(pbc_b200_pairing_t *p, void *d_out, const void *d_in1,
                                       const void *d_in2, size_t n, void *stream);
 
+/* ---- the operations either side of the pairing ---------------------
+ * Batched element_pow_zn (include/pbc_field.h:262-275 -> arith/field.c:113-126):
+ *   g1_pow_zn:  out[i] = k[i] * in[i]   in G1 (ecc/curve.c:455-482; type a: G1 = G2)
+ *   gt_pow_zn:  out[i] = in[i] ^ k[i]   in GT (ecc/pairing.c:199-231)
+ * Elements in wire format; scalars are Zr wire bytes (pbc_b200_pairing_length_in_bytes_Zr = 20,
+ * big-endian, reduced mod r as element_from_bytes does).  The point at infinity (k = 0 mod r, or an
+ * input that is not on the curve) is written as all-zero bytes: the reference leaves stale
+ * coordinates behind its infinity flag (ecc/curve.c:603-609), so there is nothing to match.
+ * The _device forms take device pointers and enqueue on `stream`. */
+int pbc_b200_pairing_length_in_bytes_Zr(const pbc_b200_pairing_t *p);
+int pbc_b200_g1_pow_zn(pbc_b200_pairing_t *p, unsigned char *out, const unsigned char *in,
+                       const unsigned char *k, size_t n);
+int pbc_b200_gt_pow_zn(pbc_b200_pairing_t *p, unsigned char *out, const unsigned char *in,
+                       const unsigned char *k, size_t n);
+int pbc_b200_g1_pow_zn_device(pbc_b200_pairing_t *p, void *d_out, const void *d_in, const void *d_k,
+                              size_t n, void *stream);
+int pbc_b200_gt_pow_zn_device(pbc_b200_pairing_t *p, void *d_out, const void *d_in, const void *d_k,
+                              size_t n, void *stream);
+
 /* Multi-GPU fan-out for the host-buffer entry points: use devices [0, count).  count = 0 means
  * every visible device.  Default is 1 (the current device). */
 int pbc_b200_set_devices(pbc_b200_pairing_t *p, int count);

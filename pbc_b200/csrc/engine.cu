@@ -24,6 +24,8 @@
 #include "pairing_a.cuh"
 #include "pairing_d.cuh"
 #include "pairing_f.cuh"
+#include "group_a.cuh"
+#include "group_cc.cuh"
 
 namespace pbcb200 {
 __global__ void k_fqmul_chain(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, int iters, int mode);
@@ -101,6 +103,8 @@ struct pbc_b200_pairing_s {
   CCConsts cc;
   FConsts f;
   DConsts d;
+  ZrConsts zr;
+  int zr_len = 20;
   int ndev = 1;
   bool profile = false;        // record CUDA events between the kernels of the device-API path
   bool force_reference_basis = false;   // test switches, from "b200_*" keys of the parameter text
@@ -189,6 +193,8 @@ static int init_type_a(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   if (h.bits() > 384) return fail("type a: cofactor too large");
   if (exp1 <= 0 || exp2 <= exp1) return fail("type a: bad exp1/exp2");
   p->type = 'a';
+  memset(&p->zr, 0, sizeof p->zr);
+  r.to_words(p->zr.r, 5);
   p->nlimbs = kNA;
   p->full = true;
   p->g1_len = p->g2_len = p->gt_len = 128;
@@ -291,6 +297,8 @@ static int init_type_f(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   BigUInt six(6);
   if (!((q % six) == BigUInt(1))) return fail("type f: q must be 1 mod 6");
   p->type = 'f';
+  memset(&p->zr, 0, sizeof p->zr);
+  r.to_words(p->zr.r, 5);
   p->nlimbs = kNS;
   p->full = false;
   p->g1_len = 2 * kWS; p->g2_len = 4 * kWS; p->gt_len = 12 * kWS;
@@ -409,6 +417,8 @@ static int init_type_d(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   if (q.bits() > 159 || q.bits() < 129) return fail("type d: this build supports 129..159-bit q (got %zu)", q.bits());
   if (r.bits() > 160 || r.bits() < 3) return fail("type d: bad group order");
   p->type = 'd';
+  memset(&p->zr, 0, sizeof p->zr);
+  r.to_words(p->zr.r, 5);
   p->nlimbs = kNS;
   p->full = false;
   p->g1_len = 2 * kWS; p->g2_len = 6 * kWS; p->gt_len = 6 * kWS;
@@ -482,6 +492,9 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
       CUDA_OK(allow_smem(k_a_prod<kBlockProd>, kSmemAProd));
       CUDA_OK(allow_smem(k_a_pp_init<32>, kSmemAPPInit));
       CUDA_OK(allow_smem(k_a_pp_apply<kBlockMiller>, kSmemAPPApply));
+      CUDA_OK(allow_smem(k_a_g1_mul<kBlockMiller>, (size_t)kGSlots * 64 * kBlockMiller));
+      CUDA_OK(allow_smem(k_a_g1_finish<kBlockFinal>, (size_t)4 * 64 * kBlockFinal));
+      CUDA_OK(allow_smem(k_a_gt_pow<kBlockMiller>, (size_t)7 * 64 * kBlockMiller));
     }
     c.ready = true;
   }
@@ -491,6 +504,7 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
     CUDA_OK(cudaDeviceSynchronize());
     CUDA_OK(cudaMemcpyToSymbol(c_fp, &p->fp, sizeof(FpConsts)));
     if (p->type == 'a') CUDA_OK(cudaMemcpyToSymbol(c_a, &p->a, sizeof(AConsts)));
+    CUDA_OK(cudaMemcpyToSymbol(c_zr, &p->zr, sizeof(ZrConsts)));
     if (p->type == 'f' || p->type == 'd') CUDA_OK(cudaMemcpyToSymbol(c_cc, &p->cc, sizeof(CCConsts)));
     if (p->type == 'f') CUDA_OK(cudaMemcpyToSymbol(c_f, &p->f, sizeof(FConsts)));
     if (p->type == 'd') CUDA_OK(cudaMemcpyToSymbol(c_d, &p->d, sizeof(DConsts)));
@@ -905,6 +919,97 @@ double pbc_b200_bench_imad(int blocks, int threads, int iters, int reps) {
 }
 
 }  // extern "C"
+
+
+// ------------------------------------------------------------------------------------------
+// group operations either side of the pairing: batched element_pow_zn on G1 and GT
+// ------------------------------------------------------------------------------------------
+static int enqueue_group(pbc_b200_pairing_s* p, int which /*0 = G1, 1 = GT*/, uint8_t* d_out, const uint8_t* d_in,
+                         const uint8_t* d_k, size_t n, void* ws, cudaStream_t st) {
+  if (n == 0) return 0;
+  if (p->type == 'a') {
+    if (which == 0) {
+      uint4* xyz = (uint4*)ws;                 // [2][4][n]  (X, Y)
+      uint4* zarr = xyz + 8 * n;               // [4][n]
+      uint4* prefix = zarr + 4 * n;            // [4][n]
+      unsigned g = (unsigned)((n + kBlockMiller - 1) / kBlockMiller);
+      k_a_g1_mul<kBlockMiller><<<g, kBlockMiller, (size_t)kGSlots * 64 * kBlockMiller, st>>>(d_in, d_k, xyz, zarr, n);
+      LAUNCHED();
+      size_t T = n < (size_t)148 * 256 ? n : (size_t)148 * 256;
+      unsigned gi = (unsigned)((T + kBlockInv - 1) / kBlockInv);
+      k_batch_invert<kNA, true, kBlockInv><<<gi, kBlockInv, kSmemInv16, st>>>(zarr, prefix, n, T);
+      LAUNCHED();
+      unsigned gf = (unsigned)((n + kBlockFinal - 1) / kBlockFinal);
+      k_a_g1_finish<kBlockFinal><<<gf, kBlockFinal, (size_t)4 * 64 * kBlockFinal, st>>>(xyz, zarr, d_out, n);
+      LAUNCHED();
+    } else {
+      unsigned g = (unsigned)((n + kBlockMiller - 1) / kBlockMiller);
+      k_a_gt_pow<kBlockMiller><<<g, kBlockMiller, (size_t)7 * 64 * kBlockMiller, st>>>(d_in, d_k, d_out, n);
+      LAUNCHED();
+    }
+  } else {
+    unsigned g = (unsigned)((n + kBlockCC - 1) / kBlockCC);
+    if (which == 0) k_cc_g1_mul<kBlockCC><<<g, kBlockCC, 0, st>>>(d_in, d_k, d_out, n);
+    else if (p->type == 'f') k_f_gt_pow<kBlockCC><<<g, kBlockCC, 0, st>>>(d_in, d_k, d_out, n);
+    else k_d_gt_pow<kBlockCC><<<g, kBlockCC, 0, st>>>(d_in, d_k, d_out, n);
+    LAUNCHED();
+  }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int run_group(pbc_b200_pairing_s* p, int which, unsigned char* out, const unsigned char* in,
+                     const unsigned char* k, size_t n, bool device, void* stream) {
+  if (!p || (n && (!out || !in || !k))) return fail("null argument");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(p->mu);
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  if (ctx_prepare(p, dev)) return 1;
+  DevCtx& c = p->ctx[dev];
+  size_t elen = which == 0 ? (size_t)p->g1_len : (size_t)p->gt_len;
+  size_t wsb = p->type == 'a' && which == 0 ? n * 64 * (2 + 1 + 1) : 16;
+  size_t stage = device ? 0 : n * (2 * elen + (size_t)p->zr_len);
+  if (c.cap_dev < wsb + stage) {
+    CUDA_OK(cudaDeviceSynchronize());
+    cudaFree(c.ws_dev);
+    c.ws_dev = nullptr; c.cap_dev = 0;
+    CUDA_OK(cudaMalloc(&c.ws_dev, wsb + stage));
+    c.cap_dev = wsb + stage;
+  }
+  if (device)
+    return enqueue_group(p, which, (uint8_t*)out, (const uint8_t*)in, (const uint8_t*)k, n, c.ws_dev, (cudaStream_t)stream);
+  uint8_t* d_in = (uint8_t*)c.ws_dev + wsb;
+  uint8_t* d_out = d_in + n * elen;
+  uint8_t* d_k = d_out + n * elen;
+  cudaStream_t st = c.stream[0];
+  CUDA_OK(cudaMemcpyAsync(d_in, in, n * elen, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(d_k, k, n * (size_t)p->zr_len, cudaMemcpyHostToDevice, st));
+  if (enqueue_group(p, which, d_out, d_in, d_k, n, c.ws_dev, st)) return 1;
+  CUDA_OK(cudaMemcpyAsync(out, d_out, n * elen, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" {
+int pbc_b200_pairing_length_in_bytes_Zr(const pbc_b200_pairing_t* p) { return p->zr_len; }
+int pbc_b200_g1_pow_zn(pbc_b200_pairing_t* p, unsigned char* out, const unsigned char* in, const unsigned char* k,
+                       size_t n) {
+  return run_group(p, 0, out, in, k, n, false, nullptr);
+}
+int pbc_b200_gt_pow_zn(pbc_b200_pairing_t* p, unsigned char* out, const unsigned char* in, const unsigned char* k,
+                       size_t n) {
+  return run_group(p, 1, out, in, k, n, false, nullptr);
+}
+int pbc_b200_g1_pow_zn_device(pbc_b200_pairing_t* p, void* d_out, const void* d_in, const void* d_k, size_t n,
+                              void* stream) {
+  return run_group(p, 0, (unsigned char*)d_out, (const unsigned char*)d_in, (const unsigned char*)d_k, n, true, stream);
+}
+int pbc_b200_gt_pow_zn_device(pbc_b200_pairing_t* p, void* d_out, const void* d_in, const void* d_k, size_t n,
+                              void* stream) {
+  return run_group(p, 1, (unsigned char*)d_out, (const unsigned char*)d_in, (const unsigned char*)d_k, n, true, stream);
+}
+}
 
 // ------------------------------------------------------------------------------------------
 // F_p differential-test hook

@@ -45,6 +45,7 @@ class Pairing:
         self.g2_len = lib.pbc_b200_pairing_length_in_bytes_G2(self._h)
         self.gt_len = lib.pbc_b200_pairing_length_in_bytes_GT(self._h)
         self.type = chr(lib.pbc_b200_pairing_type(self._h))
+        self.zr_len = lib.pbc_b200_pairing_length_in_bytes_Zr(self._h)
 
     def clear(self):
         """pairing_clear"""
@@ -112,6 +113,31 @@ class Pairing:
         if lib.pbc_b200_pp_pairings_apply(self._h, C.addressof(out), _addr(in1), _addr(in2), n):
             raise PairingError(last_error())
         return out.raw[:n * self.gt_len]
+
+    # -- element_pow_zn on G1 / GT (include/pbc_field.h:262-275) ------------------------------------
+    def g1_pow_zn(self, points: bytes, scalars: bytes, n=None) -> bytes:
+        if n is None:
+            n = len(points) // self.g1_len
+        out = C.create_string_buffer(max(1, n * self.g1_len))
+        if lib.pbc_b200_g1_pow_zn(self._h, C.addressof(out), _addr(points), _addr(scalars), n):
+            raise PairingError(last_error())
+        return out.raw[:n * self.g1_len]
+
+    def gt_pow_zn(self, elems: bytes, scalars: bytes, n=None) -> bytes:
+        if n is None:
+            n = len(elems) // self.gt_len
+        out = C.create_string_buffer(max(1, n * self.gt_len))
+        if lib.pbc_b200_gt_pow_zn(self._h, C.addressof(out), _addr(elems), _addr(scalars), n):
+            raise PairingError(last_error())
+        return out.raw[:n * self.gt_len]
+
+    def g1_pow_zn_device(self, d_out, d_in, d_k, n, stream=0):
+        if lib.pbc_b200_g1_pow_zn_device(self._h, d_out, d_in, d_k, n, stream):
+            raise PairingError(last_error())
+
+    def gt_pow_zn_device(self, d_out, d_in, d_k, n, stream=0):
+        if lib.pbc_b200_gt_pow_zn_device(self._h, d_out, d_in, d_k, n, stream):
+            raise PairingError(last_error())
 
     # -- test / bench hooks -----------------------------------------------------------------------
     def fp_op(self, op: int, a: bytes, b, n: int) -> bytes:
