@@ -42,10 +42,11 @@ SEED = 20260922
 # unit = one 32x32->64 multiply-accumulate (IMAD.WIDE.U32); a t-limb(64-bit) Montgomery mulmod is
 # 2(2t)^2 + 2t of them: 528 for t = 8 (type a), 78 for t = 3 (types f, d)  -- SURVEY.md 8(d).
 # ref_mulmods = reference-algorithm mulmods per output (SURVEY 8d probes); ref_main = the part the
-# first kernel (Miller loop) stands for.  exec_unit_ops_main = what OUR first kernel executes.
+# first kernel (Miller loop) stands for.  exec_unit_ops_main = what OUR first kernel executes
+# (type A, weight-(1,2) Miller loop: 1616 multiplications of 528 units + 1121 squarings of 408).
 WORKLOADS = {
     "a": dict(param="a", mode="single", k=1, n=1 << 20, unit=528, ref_mulmods=4394, ref_main=4394 - 719,
-              exec_unit_ops_main=2093 * 528 + 961 * 408, cpu_rate=1100.0, port_rate=110.0,
+              exec_unit_ops_main=1616 * 528 + 1121 * 408, cpu_rate=1100.0, port_rate=110.0,
               name="type A (param/a.param) element_pairing, batch 2^20 (P,Q) pairs per GPU, 512-bit F_q",
               dtype="u32 limbs (16 x 32-bit = 512-bit F_q, exact integer)", kernels=("k_a_miller", "k_batch_invert", "k_a_finalexp")),
     "f": dict(param="f", mode="single", k=1, n=1 << 20, unit=78, ref_mulmods=98183, ref_main=None,
@@ -57,7 +58,7 @@ WORKLOADS = {
               name="type D (param/d159.param, MNT k=6) element_pairing, batch 2^18 pairs per GPU, 159-bit F_q",
               dtype="u32 limbs (5 x 32-bit = 160-bit F_q, exact integer)", kernels=("k_d_miller", "-", "k_d_finalexp")),
     "prod16": dict(param="a", mode="prod", k=16, n=1 << 16, unit=528, ref_mulmods=41536, ref_main=41536 - 719,
-                   exec_unit_ops_main=16 * (2093 * 528 + 961 * 408), cpu_rate=130.0, port_rate=8.0,
+                   exec_unit_ops_main=16 * (1616 * 528 + 1121 * 408), cpu_rate=130.0, port_rate=8.0,
                    name="type A element_prod_pairing n=16, 2^16 outputs (2^20 Miller loops) over all GPUs",
                    dtype="u32 limbs (16 x 32-bit = 512-bit F_q, exact integer)",
                    kernels=("k_a_miller+k_a_prod", "k_batch_invert", "k_a_finalexp")),

@@ -190,3 +190,28 @@ void element_pairing_batch(element_t out[], element_t in1[], element_t in2[], in
   }
   pbc_free(b1);
 }
+
+/* out[i] = in[i]^k[i] (element_pow_zn, include/pbc_field.h:262-275) for arrays of G1 or GT elements
+ * of an attached pairing: one GPU batch instead of n windowed powers on the CPU.  k[i] in Zr. */
+void element_pow_zn_batch(element_t out[], element_t in[], element_t k[], int n) {
+  if (n <= 0) return;
+  pairing_ptr pairing = in[0]->field->pairing;
+  struct attach_s *a = find_attach(pairing);
+  int is_gt = in[0]->field == pairing->GT;
+  if (!is_gt && in[0]->field != pairing->G1) pbc_die("pbc_b200: element_pow_zn_batch takes G1 or GT elements");
+  size_t elen = is_gt ? a->gt_len : a->g1_len, zlen = pbc_b200_pairing_length_in_bytes_Zr(a->h);
+  unsigned char *bi = pbc_malloc((2 * elen + zlen) * (size_t)n);
+  unsigned char *bo = bi + (size_t)n * elen, *bk = bo + (size_t)n * elen;
+  int i;
+  memset(bi, 0, (2 * elen + zlen) * (size_t)n);
+  for (i = 0; i < n; i++) {
+    if (!element_is0(in[i])) element_to_bytes(bi + (size_t)i * elen, in[i]);
+    element_to_bytes(bk + (size_t)i * zlen, k[i]);
+  }
+  check((is_gt ? pbc_b200_gt_pow_zn : pbc_b200_g1_pow_zn)(a->h, bo, bi, bk, (size_t)n), "element_pow_zn_batch");
+  for (i = 0; i < n; i++) {
+    if (element_is0(in[i]) || element_is0(k[i])) { element_set0(out[i]); continue; }
+    element_from_bytes(out[i], bo + (size_t)i * elen);
+  }
+  pbc_free(bi);
+}

@@ -14,6 +14,7 @@
 #include <pbc.h>
 
 void element_pairing_batch(element_t out[], element_t in1[], element_t in2[], int n);
+void element_pow_zn_batch(element_t out[], element_t in[], element_t k[], int n);
 int pbc_b200_pairing_batch(pairing_t pairing, unsigned char *out, const unsigned char *in1,
                            const unsigned char *in2, size_t n);
 
@@ -95,7 +96,29 @@ int main(int argc, char **argv) {
     element_pairing(e2, p2, q2);
     if (!same(E[i], e2)) { printf("batch mismatch at %d\n", i); bad++; if (bad > 8) break; }
   }
-  printf("shim_test: %s (%d batch pairings, prod, pp, identity; G1 %d B, G2 %d B, GT %d B)\n",
+  /* 6. element_pow_zn over arrays, G1 and GT, GPU batch vs the reference's windowed power */
+  {
+    int m = n < 16 ? n : 16;
+    element_t *K = malloc(m * sizeof *K), *R = malloc(m * sizeof *R), ref, kc;
+    element_init_G1(ref, cpu); element_init_Zr(kc, cpu);
+    for (i = 0; i < m; i++) { element_init_Zr(K[i], gpu); element_random(K[i]); element_init_G1(R[i], gpu); }
+    element_pow_zn_batch(R, P + 6, K, m);
+    for (i = 0; i < m; i++) {
+      copy_elem(p2, P[6 + i]); copy_elem(kc, K[i]);
+      element_pow_zn(ref, p2, kc);
+      if (!same(R[i], ref)) { printf("G1 pow_zn batch mismatch at %d\n", i); bad++; }
+    }
+    element_pow_zn_batch(E + 6, E + 6, K, m);          /* in place on GT */
+    for (i = 0; i < m; i++) {
+      copy_elem(p2, P[6 + i]); copy_elem(q2, Q[6 + i]); copy_elem(kc, K[i]);
+      element_pairing(e2, p2, q2);
+      element_pow_zn(e2, e2, kc);
+      if (!same(E[6 + i], e2)) { printf("GT pow_zn batch mismatch at %d\n", i); bad++; }
+    }
+    for (i = 0; i < m; i++) { element_clear(K[i]); element_clear(R[i]); }
+    element_clear(ref); element_clear(kc);
+  }
+  printf("shim_test: %s (%d batch pairings, prod, pp, identity, pow_zn; G1 %d B, G2 %d B, GT %d B)\n",
          bad ? "FAILED" : "OK", n, pairing_length_in_bytes_G1(gpu), pairing_length_in_bytes_G2(gpu),
          pairing_length_in_bytes_GT(gpu));
   for (i = 0; i < n; i++) { element_clear(P[i]); element_clear(Q[i]); element_clear(E[i]); }
