@@ -15,7 +15,13 @@
 
 namespace pbcb200 {
 
-constexpr int kNS = 5;         // 32-bit limbs
+// PBC_NS: 32-bit limbs of the small field.  5 = minimal (product-scanning multiplier, 55 products,
+// ~140 instructions); 6 = one spare limb so the even/odd operand-scanning multiplier of fp.cuh applies
+// (78 products but ~105 instructions) -- an A/B experiment, see DESIGN.md.
+#ifndef PBC_NS
+#define PBC_NS 5
+#endif
+constexpr int kNS = PBC_NS;    // 32-bit limbs
 constexpr int kWS = 20;        // wire bytes per coordinate (arith/montfp.c:577)
 
 struct Fq { uint32_t v[kNS]; };
@@ -29,12 +35,12 @@ struct Fq { uint32_t v[kNS]; };
 #if PBC_FQ_CALL
 __device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) {
   Fq r;
-  mont_mul_ps<kNS, false>(r.v, a.v, b.v);
+  if (kNS % 2 == 0) mont_mul<kNS + (kNS & 1), false>(r.v, a.v, b.v); else mont_mul_ps<kNS, false>(r.v, a.v, b.v);
   return r;
 }
 __device__ __noinline__ Fq fq_sqr_call(Fq a) {
   Fq r;
-  mont_sqr_ps<kNS, false>(r.v, a.v);
+  if (kNS % 2 == 0) mont_mul<kNS + (kNS & 1), false>(r.v, a.v, a.v); else mont_sqr_ps<kNS, false>(r.v, a.v);
   return r;
 }
 __device__ __forceinline__ void fq_mul(Fq& r, const Fq& a, const Fq& b) { r = fq_mul_call(a, b); }
