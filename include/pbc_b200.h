@@ -83,7 +83,9 @@ int pbc_b200_pp_pairings_apply_device(pbc_b200_pairing_t *p, void *d_out, const 
 
 /* ---- the operations either side of the pairing ---------------------
  * Batched element_pow_zn (include/pbc_field.h:262-275 -> arith/field.c:113-126):
- *   g1_pow_zn:  out[i] = k[i] * in[i]   in G1 (ecc/curve.c:455-482; type a: G1 = G2)
+ *   g1_pow_zn:  out[i] = k[i] * in[i]   in G1 (ecc/curve.c:455-482)
+ *   g2_pow_zn:  the same in G2: the twist over F_q^2 (type f, ecc/f_param.c:367-378) or F_q^3
+ *               (type d, ecc/d_param.c:1060-1070); type a: G2 = G1
  *   gt_pow_zn:  out[i] = in[i] ^ k[i]   in GT (ecc/pairing.c:199-231)
  * Elements in wire format; scalars are Zr wire bytes (pbc_b200_pairing_length_in_bytes_Zr = 20,
  * big-endian, reduced mod r as element_from_bytes does).  The point at infinity (k = 0 mod r, or an
@@ -95,6 +97,10 @@ int pbc_b200_g1_pow_zn(pbc_b200_pairing_t *p, unsigned char *out, const unsigned
                        const unsigned char *k, size_t n);
 int pbc_b200_gt_pow_zn(pbc_b200_pairing_t *p, unsigned char *out, const unsigned char *in,
                        const unsigned char *k, size_t n);
+int pbc_b200_g2_pow_zn(pbc_b200_pairing_t *p, unsigned char *out, const unsigned char *in,
+                       const unsigned char *k, size_t n);
+int pbc_b200_g2_pow_zn_device(pbc_b200_pairing_t *p, void *d_out, const void *d_in, const void *d_k,
+                              size_t n, void *stream);
 int pbc_b200_g1_pow_zn_device(pbc_b200_pairing_t *p, void *d_out, const void *d_in, const void *d_k,
                               size_t n, void *stream);
 int pbc_b200_gt_pow_zn_device(pbc_b200_pairing_t *p, void *d_out, const void *d_in, const void *d_k,

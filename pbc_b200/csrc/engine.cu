@@ -353,6 +353,7 @@ static int init_type_f(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   put2(c.twist_b, tb_use);
   put2(c.kx, kx);
   put2(c.ky, ky);
+  (q * q).to_words(c.qsq, 2 * kNS);
   to_mont(c.sigma, sigma, q, kNS);
   to_mont(c.sigma_inv, sigma_inv, q, kNS);
   for (int j = 1; j < 6; j++) { put2(c.tau[j - 1], taup[j]); put2(c.tau_inv[j - 1], tauinv[j]); }
@@ -924,11 +925,11 @@ double pbc_b200_bench_imad(int blocks, int threads, int iters, int reps) {
 // ------------------------------------------------------------------------------------------
 // group operations either side of the pairing: batched element_pow_zn on G1 and GT
 // ------------------------------------------------------------------------------------------
-static int enqueue_group(pbc_b200_pairing_s* p, int which /*0 = G1, 1 = GT*/, uint8_t* d_out, const uint8_t* d_in,
+static int enqueue_group(pbc_b200_pairing_s* p, int which /*0 = G1, 1 = GT, 2 = G2*/, uint8_t* d_out, const uint8_t* d_in,
                          const uint8_t* d_k, size_t n, void* ws, cudaStream_t st) {
   if (n == 0) return 0;
   if (p->type == 'a') {
-    if (which == 0) {
+    if (which == 0 || which == 2) {                // type a: G2 = G1 (ecc/a_param.c:1461-1462)
       uint4* xyz = (uint4*)ws;                 // [2][4][n]  (X, Y)
       uint4* zarr = xyz + 8 * n;               // [4][n]
       uint4* prefix = zarr + 4 * n;            // [4][n]
@@ -950,6 +951,8 @@ static int enqueue_group(pbc_b200_pairing_s* p, int which /*0 = G1, 1 = GT*/, ui
   } else {
     unsigned g = (unsigned)((n + kBlockCC - 1) / kBlockCC);
     if (which == 0) k_cc_g1_mul<kBlockCC><<<g, kBlockCC, 0, st>>>(d_in, d_k, d_out, n);
+    else if (which == 2 && p->type == 'f') k_cc_g2_mul<KF2, kBlockCC><<<g, kBlockCC, 0, st>>>(d_in, d_k, d_out, n);
+    else if (which == 2) k_cc_g2_mul<KF3, kBlockCC><<<g, kBlockCC, 0, st>>>(d_in, d_k, d_out, n);
     else if (p->type == 'f') k_f_gt_pow<kBlockCC><<<g, kBlockCC, 0, st>>>(d_in, d_k, d_out, n);
     else k_d_gt_pow<kBlockCC><<<g, kBlockCC, 0, st>>>(d_in, d_k, d_out, n);
     LAUNCHED();
@@ -967,8 +970,8 @@ static int run_group(pbc_b200_pairing_s* p, int which, unsigned char* out, const
   CUDA_OK(cudaGetDevice(&dev));
   if (ctx_prepare(p, dev)) return 1;
   DevCtx& c = p->ctx[dev];
-  size_t elen = which == 0 ? (size_t)p->g1_len : (size_t)p->gt_len;
-  size_t wsb = p->type == 'a' && which == 0 ? n * 64 * (2 + 1 + 1) : 16;
+  size_t elen = which == 0 ? (size_t)p->g1_len : (which == 2 ? (size_t)p->g2_len : (size_t)p->gt_len);
+  size_t wsb = p->type == 'a' && which != 1 ? n * 64 * (2 + 1 + 1) : 16;
   size_t stage = device ? 0 : n * (2 * elen + (size_t)p->zr_len);
   if (c.cap_dev < wsb + stage) {
     CUDA_OK(cudaDeviceSynchronize());
@@ -1000,6 +1003,14 @@ int pbc_b200_g1_pow_zn(pbc_b200_pairing_t* p, unsigned char* out, const unsigned
 int pbc_b200_gt_pow_zn(pbc_b200_pairing_t* p, unsigned char* out, const unsigned char* in, const unsigned char* k,
                        size_t n) {
   return run_group(p, 1, out, in, k, n, false, nullptr);
+}
+int pbc_b200_g2_pow_zn(pbc_b200_pairing_t* p, unsigned char* out, const unsigned char* in, const unsigned char* k,
+                       size_t n) {
+  return run_group(p, 2, out, in, k, n, false, nullptr);
+}
+int pbc_b200_g2_pow_zn_device(pbc_b200_pairing_t* p, void* d_out, const void* d_in, const void* d_k, size_t n,
+                              void* stream) {
+  return run_group(p, 2, (unsigned char*)d_out, (const unsigned char*)d_in, (const unsigned char*)d_k, n, true, stream);
 }
 int pbc_b200_g1_pow_zn_device(pbc_b200_pairing_t* p, void* d_out, const void* d_in, const void* d_k, size_t n,
                               void* stream) {

@@ -91,6 +91,76 @@ __device__ __forceinline__ void fq_set(Fq& r, const uint32_t* c) {
 }
 __device__ __forceinline__ void fq_one(Fq& r) { fq_set(r, c_fp.one); }
 
+// ---------------------------------------------------------------------------------------------
+// Lazy reduction: double-width (2 kNS words) unreduced products, combined with plain carry chains and
+// reduced once.  fq_redc needs its input below q R (R = 2^(32 kNS)); the result is canonical.
+// ---------------------------------------------------------------------------------------------
+struct FqW { uint32_t v[2 * kNS]; };
+
+// t = a b, schoolbook by columns (kNS^2 products)
+__device__ __noinline__ FqW fq_mulw_call(Fq a, Fq b) {
+  FqW t;
+  uint32_t u0 = 0, u1 = 0, u2 = 0;
+#pragma unroll
+  for (int i = 0; i < 2 * kNS - 1; i++) {
+#pragma unroll
+    for (int j = (i < kNS ? 0 : i - kNS + 1); j <= (i < kNS ? i : kNS - 1); j++) PBC_MAC3(u0, u1, u2, a.v[j], b.v[i - j]);
+    t.v[i] = u0;
+    u0 = u1; u1 = u2; u2 = 0;
+  }
+  t.v[2 * kNS - 1] = u0;
+  return t;
+}
+// (t + m q) / R with m chosen so the division is exact (Montgomery reduction), then one conditional
+// subtraction: canonical for t < q R.
+__device__ __noinline__ Fq fq_redc_call(FqW t) {
+  uint32_t m[kNS], o[kNS];
+  uint32_t v0 = 0, v1 = 0, v2 = 0;
+#pragma unroll
+  for (int i = 0; i < kNS; i++) {
+#pragma unroll
+    for (int j = 0; j < i; j++) PBC_MAC3(v0, v1, v2, m[j], c_fp.p[i - j]);
+    PBC_ASM("add.cc.u32 %0, %0, %3; addc.cc.u32 %1, %1, 0; addc.u32 %2, %2, 0;" : "+r"(v0), "+r"(v1), "+r"(v2) : "r"(t.v[i]));
+    m[i] = v0 * c_fp.np0;
+    PBC_MAC3(v0, v1, v2, m[i], c_fp.p[0]);
+    v0 = v1; v1 = v2; v2 = 0;
+  }
+#pragma unroll
+  for (int i = kNS; i < 2 * kNS; i++) {
+#pragma unroll
+    for (int j = i - kNS + 1; j < kNS; j++) PBC_MAC3(v0, v1, v2, m[j], c_fp.p[i - j]);
+    PBC_ASM("add.cc.u32 %0, %0, %3; addc.cc.u32 %1, %1, 0; addc.u32 %2, %2, 0;" : "+r"(v0), "+r"(v1), "+r"(v2) : "r"(t.v[i]));
+    o[i - kNS] = v0;
+    v0 = v1; v1 = v2; v2 = 0;
+  }
+  Fq r;
+  uint32_t d[kNS], borrow;
+  PBC_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(d[0]) : "r"(o[0]), "r"(c_fp.p[0]));
+#pragma unroll
+  for (int k = 1; k < kNS; k++) PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(d[k]) : "r"(o[k]), "r"(c_fp.p[k]));
+  PBC_ASM("subc.u32 %0, 0, 0;" : "=r"(borrow));
+  bool use_d = v0 != 0 || borrow == 0;
+#pragma unroll
+  for (int k = 0; k < kNS; k++) r.v[k] = use_d ? d[k] : o[k];
+  return r;
+}
+__device__ __forceinline__ void fqw_add(FqW& r, const FqW& a, const FqW& b) {
+  PBC_ASM("add.cc.u32 %0, %1, %2;" : "=r"(r.v[0]) : "r"(a.v[0]), "r"(b.v[0]));
+#pragma unroll
+  for (int k = 1; k < 2 * kNS; k++) PBC_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(r.v[k]) : "r"(a.v[k]), "r"(b.v[k]));
+}
+__device__ __forceinline__ void fqw_sub(FqW& r, const FqW& a, const FqW& b) {
+  PBC_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(r.v[0]) : "r"(a.v[0]), "r"(b.v[0]));
+#pragma unroll
+  for (int k = 1; k < 2 * kNS; k++) PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(r.v[k]) : "r"(a.v[k]), "r"(b.v[k]));
+}
+// a + b without reduction (the caller knows the sum fits the limbs)
+__device__ __forceinline__ void fq_add_nr(Fq& r, const Fq& a, const Fq& b) {
+  PBC_ASM("add.cc.u32 %0, %1, %2;" : "=r"(r.v[0]) : "r"(a.v[0]), "r"(b.v[0]));
+#pragma unroll
+  for (int k = 1; k < kNS; k++) PBC_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(r.v[k]) : "r"(a.v[k]), "r"(b.v[k]));
+}
+
 // wire bytes (big-endian, 20 per coordinate) -> Montgomery form (arith/montfp.c:498-517 reduces mod q)
 __device__ __forceinline__ void fq_from_wire(Fq& r, const uint8_t* p) {
   limbs_from_be<kNS, kWS>(r.v, p);

@@ -4,8 +4,9 @@
 //   element_pow_zn on GT (ecc/pairing.c:199-231 -> windowed power in F_q^12 / F_q^6)
 // Same values, different route: left-to-right double-and-add on Jacobian coordinates (the formulas
 // of miller_cc.cuh without the lines) with one Fermat inversion at the end, and square-and-multiply
-// on the tower routines of pairing_f.cuh / pairing_d.cuh.  G2 of these types (curves over F_q^2 and
-// F_q^3) is not built yet.
+// on the tower routines of pairing_f.cuh / pairing_d.cuh.  G2 (the twists over F_q^2 for type f, F_q^3
+// for type d; ecc/f_param.c:367-378, ecc/d_param.c:1060-1070) runs the same double-and-add on the
+// tower's field routines through a small policy struct.
 #pragma once
 #include "group_a.cuh"
 #include "pairing_d.cuh"
@@ -89,6 +90,155 @@ k_cc_g1_mul(const uint8_t* __restrict__ P, const uint8_t* __restrict__ K, uint8_
   if (inf) { fq_zero(X); fq_zero(Y); }
   fq_to_wire(out + idx * (2 * kWS), X);
   fq_to_wire(out + idx * (2 * kWS) + kWS, Y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// G2: y^2 = x^3 + a' x + b' over K = F_q^2 (type f, a' = 0) or F_q^3 (type d).  KF supplies the
+// field: struct El; mul/sqr/inv on pointers (the tower's out-of-line routines), add/sub/dbl inline,
+// wire <-> basis-in-use conversion, and the curve constants.
+// ---------------------------------------------------------------------------------------------
+struct KF2 {                       // type f
+  typedef F2 El;
+  static constexpr int kWire = 2 * kWS;
+  static __device__ __forceinline__ void mul(El* r, const El* a, const El* b) { f2_mul(r, a, b); }
+  static __device__ __forceinline__ void sqr(El* r, const El* a) { f2_sqr(r, a); }
+  static __device__ __forceinline__ void inv(El* r, const El* a) { f2_inv(r, a); }
+  static __device__ __forceinline__ void add(El& r, const El& a, const El& b) { f2_add(r, a, b); }
+  static __device__ __forceinline__ void sub(El& r, const El& a, const El& b) { f2_sub(r, a, b); }
+  static __device__ __forceinline__ void one(El& r) { f2_zero(r); fq_one(r.a); }
+  static __device__ __forceinline__ bool is_zero(const El& a) { return fq_is_zero(a.a) && fq_is_zero(a.b); }
+  static __device__ __forceinline__ bool eq(const El& a, const El& b) { return f2_eq(a, b); }
+  static __device__ __forceinline__ bool a_is_zero() { return true; }
+  static __device__ __forceinline__ void add_curve_a(El&) {}
+  static __device__ __forceinline__ void mul_curve_a(El&) {}
+  static __device__ __forceinline__ void add_curve_b(El& r) { f2_add(r, r, *f2_const(c_f.twist_b)); }
+  static __device__ __forceinline__ void from_wire(El& r, const uint8_t* p) {
+    Fq s;
+    fq_from_wire(r.a, p);
+    fq_from_wire(r.b, p + kWS);
+    fq_set(s, c_f.sigma);
+    fq_mul(r.b, r.b, s);
+  }
+  static __device__ __forceinline__ void to_wire(uint8_t* p, const El& a, bool zero) {
+    Fq s, b;
+    fq_set(s, c_f.sigma_inv);
+    fq_mul(b, a.b, s);
+    El o;
+    o.a = a.a;
+    o.b = b;
+    if (zero) f2_zero(o);
+    fq_to_wire(p, o.a);
+    fq_to_wire(p + kWS, o.b);
+  }
+};
+struct KF3 {                       // type d
+  typedef F3 El;
+  static constexpr int kWire = 3 * kWS;
+  static __device__ __forceinline__ void mul(El* r, const El* a, const El* b) { f3_mul(r, a, b); }
+  static __device__ __forceinline__ void sqr(El* r, const El* a) { f3_sqr(r, a); }
+  static __device__ __forceinline__ void inv(El* r, const El* a) { f3_inv(r, a); }
+  static __device__ __forceinline__ void add(El& r, const El& a, const El& b) { f3_add(r, a, b); }
+  static __device__ __forceinline__ void sub(El& r, const El& a, const El& b) { f3_sub(r, a, b); }
+  static __device__ __forceinline__ void one(El& r) { f3_zero(r); fq_one(r.c[0]); }
+  static __device__ __forceinline__ bool is_zero(const El& a) { return fq_is_zero(a.c[0]) && fq_is_zero(a.c[1]) && fq_is_zero(a.c[2]); }
+  static __device__ __forceinline__ bool eq(const El& a, const El& b) { return f3_eq(a, b); }
+  static __device__ __forceinline__ bool a_is_zero() { return false; }
+  static __device__ __forceinline__ void add_curve_a(El& r) { Fq k; fq_set(k, c_d.twist_a); fq_add(r.c[0], r.c[0], k); }
+  static __device__ __forceinline__ void mul_curve_a(El& r) { Fq k; fq_set(k, c_d.twist_a); f3_scale(r, r, k); }
+  static __device__ __forceinline__ void add_curve_b(El& r) { Fq k; fq_set(k, c_d.twist_b); fq_add(r.c[0], r.c[0], k); }
+  static __device__ __forceinline__ void from_wire(El& r, const uint8_t* p) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) fq_from_wire(r.c[i], p + i * kWS);
+  }
+  static __device__ __forceinline__ void to_wire(uint8_t* p, const El& a, bool zero) {
+    El o = a;
+    if (zero) f3_zero(o);
+#pragma unroll
+    for (int i = 0; i < 3; i++) fq_to_wire(p + i * kWS, o.c[i]);
+  }
+};
+
+// out[i] = k[i] * in[i] on the twist.  One thread per point; all temporaries that are passed by
+// address live at function scope (stack discipline note in pairing_f.cuh).
+template <class KF, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, PBC_CC_MINBLOCKS)
+k_cc_g2_mul(const uint8_t* __restrict__ P, const uint8_t* __restrict__ K, uint8_t* __restrict__ out, size_t n) {
+  typedef typename KF::El El;
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  El xP, yP, X, Y, Z, Z2, M, Y2, t, u, H, R;
+  KF::from_wire(xP, P + idx * (2 * KF::kWire));
+  KF::from_wire(yP, P + idx * (2 * KF::kWire) + KF::kWire);
+  // on the curve?  y^2 == (x^2 + a') x + b'
+  KF::sqr(&t, &xP);
+  KF::add_curve_a(t);
+  KF::mul(&t, &t, &xP);
+  KF::add_curve_b(t);
+  KF::sqr(&u, &yP);
+  bool ok = KF::eq(t, u);
+  uint32_t k[5];
+  zr_from_wire(k, K + idx * kWZ);
+  int top = zr_top_bit(k);
+  X = xP;
+  Y = yP;
+  KF::one(Z);
+  for (int j = top - 1; j >= 0; j--) {
+    // V = 2V:  M = 3 X^2 + a' Z^4
+    KF::sqr(&Z2, &Z);
+    KF::sqr(&t, &X);
+    KF::add(M, t, t);
+    KF::add(M, M, t);
+    if (!KF::a_is_zero()) {
+      KF::sqr(&u, &Z2);
+      KF::mul_curve_a(u);
+      KF::add(M, M, u);
+    }
+    KF::sqr(&Y2, &Y);
+    KF::mul(&u, &Y, &Z);
+    KF::add(Z, u, u);
+    KF::mul(&t, &X, &Y2);
+    KF::add(t, t, t);
+    KF::add(t, t, t);                    // S = 4 X Y^2
+    KF::sqr(&X, &M);
+    KF::sub(X, X, t);
+    KF::sub(X, X, t);
+    KF::sqr(&Y2, &Y2);
+    KF::add(Y2, Y2, Y2);
+    KF::add(Y2, Y2, Y2);
+    KF::add(Y2, Y2, Y2);                 // 8 Y^4
+    KF::sub(t, t, X);
+    KF::mul(&Y, &M, &t);
+    KF::sub(Y, Y, Y2);
+    if ((k[j >> 5] >> (j & 31)) & 1u) {
+      // V = V + P (mixed)
+      KF::sqr(&Z2, &Z);
+      KF::mul(&t, &Z2, &Z);
+      KF::mul(&H, &xP, &Z2);
+      KF::sub(H, H, X);
+      KF::mul(&R, &yP, &t);
+      KF::sub(R, R, Y);
+      KF::mul(&Z, &H, &Z);
+      KF::sqr(&t, &H);
+      KF::mul(&u, &t, &H);
+      KF::mul(&t, &t, &X);
+      KF::sqr(&X, &R);
+      KF::sub(X, X, u);
+      KF::sub(X, X, t);
+      KF::sub(X, X, t);
+      KF::sub(t, t, X);
+      KF::mul(&t, &t, &R);
+      KF::mul(&u, &u, &Y);
+      KF::sub(Y, t, u);
+    }
+  }
+  bool inf = !ok || top < 0 || KF::is_zero(Z);
+  KF::inv(&t, &Z);
+  KF::sqr(&u, &t);
+  KF::mul(&X, &X, &u);
+  KF::mul(&u, &u, &t);
+  KF::mul(&Y, &Y, &u);
+  KF::to_wire(out + idx * (2 * KF::kWire), X, inf);
+  KF::to_wire(out + idx * (2 * KF::kWire) + KF::kWire, Y, inf);
 }
 
 // out[i] = in[i]^k[i] in GT (type f: 240-byte F_q^12 elements)

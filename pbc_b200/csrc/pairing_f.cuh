@@ -51,6 +51,7 @@ struct FConsts {
   uint32_t kx[2][kNS], ky[2][kNS];     // second argument: Qx'' = phi2(Qx) kx, Qy'' = phi2(Qy) ky
   uint32_t tau[5][2][kNS];             // tau^j,  j = 1..5  (wire -> internal, test hook)
   uint32_t tau_inv[5][2][kNS];         // tau^-j, j = 1..5  (internal -> wire)
+  uint32_t qsq[2 * kNS];               // q^2 as a plain double-width integer (lazy reduction offset)
 };
 __constant__ FConsts c_f;
 
@@ -67,7 +68,31 @@ __device__ __forceinline__ bool f2_eq(const F2& x, const F2& y) { return fq_eq(x
 
 // (x0 + x1 s)(y0 + y1 s) = x0 y0 + beta x1 y1 + ((x0 + x1)(y0 + y1) - x0 y0 - x1 y1) s;
 // internal basis: beta = -1, three multiplications.
+// Internal basis, lazily reduced (PBC_F2_LAZY): three unreduced products, the Karatsuba combination on
+// double-width values, two reductions:  re = x0 y0 - x1 y1 + q^2 (< 2 q^2),  im = (x0 + x1)(y0 + y1)
+// - x0 y0 - x1 y1 (< 2 q^2); the operand sums stay below 2q < 2^160 and need no reduction.
+#ifndef PBC_F2_LAZY
+#define PBC_F2_LAZY 1
+#endif
 __device__ __noinline__ void f2_mul(F2* r, const F2* x, const F2* y) {
+  if (PBC_F2_LAZY && c_f.nice) {
+    Fq x0 = x->a, x1 = x->b, y0 = y->a, y1 = y->b, sx, sy;
+    FqW t0, t1, t2, qq;
+    fq_add_nr(sx, x0, x1);
+    fq_add_nr(sy, y0, y1);
+    t0 = fq_mulw_call(x0, y0);
+    t1 = fq_mulw_call(x1, y1);
+    t2 = fq_mulw_call(sx, sy);
+    fqw_sub(t2, t2, t0);
+    fqw_sub(t2, t2, t1);
+#pragma unroll
+    for (int k = 0; k < 2 * kNS; k++) qq.v[k] = c_f.qsq[k];
+    fqw_add(t0, t0, qq);
+    fqw_sub(t0, t0, t1);
+    r->a = fq_redc_call(t0);
+    r->b = fq_redc_call(t2);
+    return;
+  }
   Fq t0, t1, t2, u;
   fq_add(t2, x->a, x->b);
   fq_add(u, y->a, y->b);
@@ -80,7 +105,7 @@ __device__ __noinline__ void f2_mul(F2* r, const F2* x, const F2* y) {
     fq_sub(r->a, t0, t1);
   } else {
     fq_set(u, c_f.beta);
-    fq_mul(t1, t1, u);
+    fq_mul_hot(t1, t1, u);
     fq_add(r->a, t0, t1);
   }
   r->b = t2;
@@ -110,24 +135,28 @@ __device__ __forceinline__ void f2_scale(F2& r, const F2& x, const Fq& k) { fq_m
 // address taken is __noinline__ and declares them at function scope; inlined helpers take no
 // addresses of their own locals.  Constants are passed as pointers into __constant__ memory.
 __device__ __forceinline__ const F2* f2_const(const uint32_t c[2][kNS]) { return reinterpret_cast<const F2*>(c); }
-// k x for a small non-negative integer k (double-and-add)
-__device__ __forceinline__ void fq_mul_small(Fq& r, const Fq& x, uint32_t k) {
-  Fq acc;
-  fq_zero(acc);
-  for (int j = 31 - __clz(k | 1u); j >= 0; j--) {
-    fq_dbl(acc, acc);
-    if ((k >> j) & 1u) fq_add(acc, acc, x);
-  }
-  r = acc;
+// r (+)= k x for k in 0..7 given x, 2x, 4x: at most two additions, branches are warp-uniform
+__device__ __forceinline__ void fq_small_combo(Fq& r, uint32_t k, const Fq& x1, const Fq& x2, const Fq& x4) {
+  bool have = false;
+  if (k & 4u) { r = x4; have = true; }
+  if (k & 2u) { if (have) fq_add(r, r, x2); else r = x2; have = true; }
+  if (k & 1u) { if (have) fq_add(r, r, x1); else r = x1; have = true; }
+  if (!have) fq_zero(r);
 }
-// r = xi x.  Internal basis: xi' = a + b i with small integers: (a x0 - b x1) + (b x0 + a x1) i.
+// r = xi x.  Internal basis: xi' = a + b i with small integers a, b <= 7:
+//   (a x0 - b x1) + (b x0 + a x1) i, the multiples built from x, 2x, 4x (6 additions for 4 + 2i;
+// the first version ran four generic double-and-add loops here and spent 14% of k_f_miller's
+// instructions in this routine).  Reference basis: a full F_q^2 product by xi.
 __device__ __noinline__ void f2_mul_xi(F2& r, const F2& x) {
   if (c_f.nice) {
-    Fq p, q2, s2, t;
-    fq_mul_small(p, x.a, c_f.xi_a);
-    fq_mul_small(q2, x.b, c_f.xi_b);
-    fq_mul_small(s2, x.a, c_f.xi_b);
-    fq_mul_small(t, x.b, c_f.xi_a);
+    const uint32_t a = c_f.xi_a, b = c_f.xi_b, m = a | b;
+    Fq a1 = x.a, b1 = x.b, a2, a4, b2, b4, p, q2, s2, t;
+    if (m & 6u) { fq_dbl(a2, a1); fq_dbl(b2, b1); }
+    if (m & 4u) { fq_dbl(a4, a2); fq_dbl(b4, b2); }
+    fq_small_combo(p, a, a1, a2, a4);      // a x0
+    fq_small_combo(q2, b, b1, b2, b4);     // b x1
+    fq_small_combo(s2, b, a1, a2, a4);     // b x0
+    fq_small_combo(t, a, b1, b2, b4);      // a x1
     fq_sub(r.a, p, q2);
     fq_add(r.b, s2, t);
   } else {
@@ -471,12 +500,44 @@ __device__ __noinline__ void f12_frob(F12& r, const F12& f, int k) {
     f2_mul(&r.c[i], &t, f2_const(c_f.frob[k - 1][i - 1]));
   }
 }
+// (a + b s)^2 in F_q^4 = F_q^2[s]/(s^2 - xi), s = x^3:  (a^2 + xi b^2, (a + b)^2 - a^2 - b^2)
+__device__ __noinline__ void f4_sqr(F2* r0, F2* r1, const F2* a, const F2* b) {
+  F2 sa, sb, t;
+  f2_sqr(&sa, a);
+  f2_sqr(&sb, b);
+  f2_add(t, *a, *b);
+  f2_sqr(&t, &t);
+  f2_sub(t, t, sa);
+  f2_sub(*r1, t, sb);
+  f2_mul_xi(sb, sb);
+  f2_add(*r0, sa, sb);
+}
+// Squaring in the cyclotomic subgroup (Granger-Scott; tools/proto_f_cyclo_sqr.py): with F_q^12 seen as
+// F_q^4[x]/(x^3 - s), f = u0 + u1 x + u2 x^2, u0 = (c0, c3), u1 = (c1, c4), u2 = (c2, c5):
+//   f^2 = (3 u0^2 - 2 conj u0) + (3 s u2^2 + 2 conj u1) x + (3 u1^2 - 2 conj u2) x^2
+// 9 F_q^2 squarings instead of the 12 products of the generic square.  Valid after the easy part of
+// the final exponentiation only.
+__device__ __noinline__ void f12_cyc_sqr(F12* v) {
+  F2 A0, A1, B0, B1, C0, C1, t;
+  f4_sqr(&A0, &A1, &v->c[0], &v->c[3]);
+  f4_sqr(&B0, &B1, &v->c[1], &v->c[4]);
+  f4_sqr(&C0, &C1, &v->c[2], &v->c[5]);
+  // 3X -+ 2u: X + 2 (X -+ u)
+  f2_sub(t, A0, v->c[0]); f2_dbl(t, t); f2_add(v->c[0], t, A0);
+  f2_add(t, A1, v->c[3]); f2_dbl(t, t); f2_add(v->c[3], t, A1);
+  f2_sub(t, B0, v->c[2]); f2_dbl(t, t); f2_add(v->c[2], t, B0);
+  f2_add(t, B1, v->c[5]); f2_dbl(t, t); f2_add(v->c[5], t, B1);
+  f2_mul_xi(C1, C1);                       // s (C0 + C1 s) = xi C1 + C0 s
+  f2_add(t, C1, v->c[1]); f2_dbl(t, t); f2_add(v->c[1], t, C1);
+  f2_sub(t, C0, v->c[4]); f2_dbl(t, t); f2_add(v->c[4], t, C0);
+}
+
 // f^u for the BN parameter u (on the cyclotomic subgroup the inverse is the conjugate)
 __device__ __noinline__ void f12_pow_u(F12& r, const F12& f) {
   F12 acc;
   acc = f;
   for (int j = (int)c_f.u_bits - 2; j >= 0; j--) {
-    f12_sqr(&acc);
+    f12_cyc_sqr(&acc);
     if ((c_f.u_abs[j >> 5] >> (j & 31)) & 1u) f12_mul(&acc, &acc, &f);
   }
   if (c_f.u_neg) f12_conj(r, acc); else r = acc;
@@ -511,7 +572,7 @@ __device__ __noinline__ void f12_final_exp(F12& acc, F12& f) {
   f12_frob(x, fu3, 1);
   f12_mul(&x, &x, &fu3);
   f12_conj(t0, x);                     // y6 = 1/(f^(u^3) f^(u^3 q))
-  f12_sqr(&t0);
+  f12_cyc_sqr(&t0);
   f12_frob(x, fu2, 1);
   f12_mul(&x, &x, &fu);
   f12_conj(y, x);                      // y4 = 1/(f^u f^(u^2 q))
@@ -524,9 +585,9 @@ __device__ __noinline__ void f12_final_exp(F12& acc, F12& f) {
   f12_mul(&t1, &t1, &t0);
   f12_frob(x, fu2, 2);                 // y2 = f^(u^2 q^2)
   f12_mul(&t0, &t0, &x);
-  f12_sqr(&t1);
+  f12_cyc_sqr(&t1);
   f12_mul(&t1, &t1, &t0);
-  f12_sqr(&t1);
+  f12_cyc_sqr(&t1);
   f12_conj(y, f);                      // y1 = 1/f
   f12_mul(&t0, &t1, &y);
   f12_frob(x, f, 1);
@@ -535,7 +596,7 @@ __device__ __noinline__ void f12_final_exp(F12& acc, F12& f) {
   f12_frob(y, f, 3);
   f12_mul(&x, &x, &y);                 // y0 = f^q f^(q^2) f^(q^3)
   f12_mul(&t1, &t1, &x);
-  f12_sqr(&t0);
+  f12_cyc_sqr(&t0);
   f12_mul(&acc, &t0, &t1);
 }
 
@@ -580,7 +641,7 @@ __device__ __forceinline__ void f12_to_wire(uint8_t* p, const F12& v) {
 }
 
 // Differential-test hook on GT-sized operands (240 wire bytes): op 0 = a*b, 1 = a^2, 2 = 1/a,
-// 3 = f_tateexp(a), 4 = a * line, the line c + L3 x^3 + L4 x^4 taken from b's coefficients 0 (real
+// 3 = f_tateexp(a), 5 = cyclotomic square of a (a must be in the cyclotomic subgroup), 4 = a * line, the line c + L3 x^3 + L4 x^4 taken from b's coefficients 0 (real
 // part only), 3 and 4.
 __global__ void k_f_tower_op(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a,
                              const uint8_t* __restrict__ b, size_t n) {
@@ -596,6 +657,7 @@ __global__ void k_f_tower_op(int op, uint8_t* __restrict__ out, const uint8_t* _
     case 1: r = x; f12_sqr(&r); break;
     case 2: f12_inv(&r, &x); break;
     case 3: f12_final_exp(r, x); break;
+    case 5: r = x; f12_cyc_sqr(&r); break;
     default: r = x; f12_mul_line(&r, &y.c[0].a, &y.c[3], &y.c[4]); break;
   }
   f12_to_reference(r);

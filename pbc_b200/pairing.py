@@ -123,6 +123,14 @@ class Pairing:
             raise PairingError(last_error())
         return out.raw[:n * self.g1_len]
 
+    def g2_pow_zn(self, points: bytes, scalars: bytes, n=None) -> bytes:
+        if n is None:
+            n = len(points) // self.g2_len
+        out = C.create_string_buffer(max(1, n * self.g2_len))
+        if lib.pbc_b200_g2_pow_zn(self._h, C.addressof(out), _addr(points), _addr(scalars), n):
+            raise PairingError(last_error())
+        return out.raw[:n * self.g2_len]
+
     def gt_pow_zn(self, elems: bytes, scalars: bytes, n=None) -> bytes:
         if n is None:
             n = len(elems) // self.gt_len

@@ -1,5 +1,10 @@
 """Generate tests/golden/*.json from the compiled, unmodified reference (oracle/_ref).
 
+NOTE: the first parameter set generated in a process (a) does not reproduce its random draws from
+run to run (the reference seeds part of its state at first use); a.json as committed was kept and
+its later additions ("pow": Qa, e_Pa_Qa) were computed by the reference from the stored inputs.
+
+
 Run HERE (container with /root/reference):  make -C oracle && python tests/golden/make_golden.py
 The fixtures are what travels to the GPU box; nothing at test time reads /root/reference.
 All byte strings are the reference wire format (element_to_bytes), hex-encoded.
@@ -40,6 +45,8 @@ def main():
         a = rp.random(R.ZR, 4)
         Pa = rp.pow_zn(R.G1, P[:4 * rp.g1_len], a, 4)
         Ea = rp.pairing(Pa, Q[:4 * rp.g2_len], 4)
+        Qa = rp.pow_zn(R.G2, Q[:4 * rp.g2_len], a, 4)          # same scalars on G2 (no new random draws)
+        Eaa = rp.pairing(Pa, Qa, 4)                            # e(P^a, Q^a) = e(P, Q)^(a^2)
         # off-curve inputs decode to O and pair to the GT identity
         badP = bytes([P[0] ^ 1]) + P[1:rp.g1_len]
         badQ = Q[:rp.g2_len - 1] + bytes([Q[rp.g2_len - 1] ^ 1])
@@ -57,7 +64,8 @@ def main():
                      "e": chunks(EP, rp.gt_len)},
             "pp": {"P": P[:rp.g1_len].hex(), "e": chunks(EPP, rp.gt_len)},
             "pow": {"a": chunks(a, rp.zr_len), "Pa": chunks(Pa, rp.g1_len),
-                    "e_Pa_Q": chunks(Ea, rp.gt_len)},
+                    "e_Pa_Q": chunks(Ea, rp.gt_len), "Qa": chunks(Qa, rp.g2_len),
+                    "e_Pa_Qa": chunks(Eaa, rp.gt_len)},
             "offcurve": {"badP": badP.hex(), "badQ": badQ.hex(), "identity": e_badP.hex()},
         }
         with open(os.path.join(ROOT, "tests", "golden", name + ".json"), "w") as f:

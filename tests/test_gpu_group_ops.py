@@ -88,3 +88,37 @@ def test_pow_then_pair_is_bilinear_on_device(env):
     lhs = d.apply(d.g1_pow_zn(P, ks, n), Q, n)
     rhs = d.gt_pow_zn(d.apply(P, Q, n), ks, n)
     assert lhs == rhs
+
+
+# ---- G2: the twist over F_q^2 (type f) / F_q^3 (type d); type a: G2 = G1 ----
+def test_g2_pow_reference_fixtures(env):
+    g, d = env["g"], env["dev"]
+    n = len(g["pow"]["a"])
+    assert d.g2_pow_zn(_cat(g["pairing"]["Q"][:n]), _cat(g["pow"]["a"]), n) == _cat(g["pow"]["Qa"])
+
+
+def test_g2_pow_matches_oracle_edge_scalars(env):
+    g, d, orc = env["g"], env["dev"], env["orc"]
+    rnd = random.Random(31)
+    r = orc.r
+    ks = [0, 1, 2, 3, r - 1, r, r + 5, 1 << 159, 0xFFFFFFFF] + [rnd.randrange(r) for _ in range(7)]
+    n = len(ks)
+    pts = [bytes.fromhex(g["pairing"]["Q"][i % len(g["pairing"]["Q"])]) for i in range(n)]
+    got = d.g2_pow_zn(b"".join(pts), b"".join(k.to_bytes(20, "big") for k in ks), n)
+    L = d.g2_len
+    for i, (k, pb) in enumerate(zip(ks, pts)):
+        R = orc.G2.mul(k % r, orc.G2.from_bytes(pb))
+        want = bytes(L) if R is None else orc.G2.to_bytes(R)
+        assert got[i * L:(i + 1) * L] == want, "scalar %d" % i
+    bad = bytes.fromhex(g["offcurve"]["badQ"])
+    assert d.g2_pow_zn(bad, (5).to_bytes(20, "big"), 1) == bytes(L)
+
+
+def test_both_arguments_powered_on_device(env):
+    """e(aP, aQ) with both multiples taken on the GPU == the reference's e(P^a, Q^a)"""
+    g, d = env["g"], env["dev"]
+    n = len(g["pow"]["a"])
+    a = _cat(g["pow"]["a"])
+    aP = d.g1_pow_zn(_cat(g["pairing"]["P"][:n]), a, n)
+    aQ = d.g2_pow_zn(_cat(g["pairing"]["Q"][:n]), a, n)
+    assert d.apply(aP, aQ, n) == _cat(g["pow"]["e_Pa_Qa"])

@@ -37,3 +37,19 @@ def test_reference_benchmark_program_links_unchanged_and_runs_on_gpu(tmp_path):
     r = subprocess.run([exe], input=PARAMS["a"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr
     assert "BUG" not in r.stdout and "average pairing time" in r.stdout
+
+
+@pytest.mark.parametrize("name", ["a", "f", "d159"])
+def test_plain_c_caller_of_the_c_abi(tmp_path, name, golden):
+    """examples/batch_pairing_demo.c: a C program that includes only include/pbc_b200.h"""
+    exe = os.path.join(ROOT, "examples", "_build", "batch_pairing_demo")
+    if not os.path.exists(exe):
+        pytest.skip("examples/_build/batch_pairing_demo not built (make -C examples)")
+    g = golden[name]["pairing"]
+    (tmp_path / "p.param").write_text(PARAMS[name])
+    (tmp_path / "P.bin").write_bytes(b"".join(bytes.fromhex(x) for x in g["P"]))
+    (tmp_path / "Q.bin").write_bytes(b"".join(bytes.fromhex(x) for x in g["Q"]))
+    r = subprocess.run([exe, str(tmp_path / "p.param"), str(tmp_path / "P.bin"), str(tmp_path / "Q.bin"),
+                        str(tmp_path / "E.bin")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert (tmp_path / "E.bin").read_bytes() == b"".join(bytes.fromhex(x) for x in g["e"])

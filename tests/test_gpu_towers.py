@@ -73,6 +73,24 @@ def test_f12_ops(f_env, op):
         assert got[i * L:(i + 1) * L] == F12.to_bytes(r), "op %d element %d" % (op, i)
 
 
+def test_f12_cyclotomic_square(f_env):
+    """Granger-Scott squaring (tower op 5) on elements of the cyclotomic subgroup == generic square"""
+    dev, orc = f_env
+    rnd = random.Random(77)
+    F12, F2, q = orc.Fq12, orc.Fq2, orc.q
+    elems = []
+    for _ in range(16):
+        f = tuple((rnd.randrange(q), rnd.randrange(q)) for _ in range(6))
+        conj = tuple(c if i % 2 == 0 else F2.neg(c) for i, c in enumerate(f))
+        g = F12.mul(conj, F12.inv(f))
+        elems.append(F12.mul(F12.pow(g, q * q), g))
+    A = b"".join(F12.to_bytes(g) for g in elems)
+    got = dev.tower_op(5, A, A, len(elems))
+    L = orc.gt_len
+    for i, g in enumerate(elems):
+        assert got[i * L:(i + 1) * L] == F12.to_bytes(F12.sqr(g)), i
+
+
 def _f6d(e):
     return (tuple(e[:3]), tuple(e[3:]))
 
