@@ -106,6 +106,16 @@ int pbc_b200_g1_pow_zn_device(pbc_b200_pairing_t *p, void *d_out, const void *d_
 int pbc_b200_gt_pow_zn_device(pbc_b200_pairing_t *p, void *d_out, const void *d_in, const void *d_k,
                               size_t n, void *stream);
 
+/* Batched element_from_hash on G1 (include/pbc_field.h:202-212 -> curve_from_hash,
+ * ecc/curve.c:455-482 with pbc_mpz_from_hash, arith/field.c:643-668): out[i] = the G1 element the
+ * reference derives from the `len` bytes at data + i*len -- x from the hash, x <- x^2 + 1 until
+ * x^3 + ax + b is a square, the odd square root, times the cofactor of G1.  Needs q = 3 mod 4 or
+ * q = 5 mod 8 (a.param, f.param, d159.param all qualify). */
+int pbc_b200_g1_from_hash(pbc_b200_pairing_t *p, unsigned char *out, const unsigned char *data,
+                          size_t len, size_t n);
+int pbc_b200_g1_from_hash_device(pbc_b200_pairing_t *p, void *d_out, const void *d_data, size_t len,
+                                 size_t n, void *stream);
+
 /* Multi-GPU fan-out for the host-buffer entry points: use devices [0, count).  count = 0 means
  * every visible device.  Default is 1 (the current device). */
 int pbc_b200_set_devices(pbc_b200_pairing_t *p, int count);

@@ -46,6 +46,7 @@ def _lib():
         L.pbcref_mul.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p,
                                  C.c_size_t]
         L.pbcref_from_str.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p]
+        L.pbcref_from_hash.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
         L.pbcref_is_identity.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
         _cached = L
     return _cached
@@ -103,6 +104,11 @@ class RefPairing:
     def pow_zn(self, group, x: bytes, k: bytes, n: int) -> bytes:
         out = C.create_string_buffer(n * self._len(group))
         self.L.pbcref_pow_zn(self.h, group, x, k, out, n)
+        return out.raw
+
+    def from_hash(self, group, data: bytes, length: int, n: int) -> bytes:
+        out = C.create_string_buffer(n * self._len(group))
+        self.L.pbcref_from_hash(self.h, group, data, length, out, n)
         return out.raw
 
     def mul(self, group, a: bytes, b: bytes, n: int) -> bytes:

@@ -176,6 +176,20 @@ void pbcref_pow_zn(void *hv, int group, const unsigned char *in, const unsigned 
   element_clear(e); element_clear(z);
 }
 
+/* out[i] = element_from_hash(data + i*len, len) in the group (include/pbc_field.h:202-212;
+ * G1/G2: ecc/curve.c:455-482 curve_from_hash). */
+void pbcref_from_hash(void *hv, int group, const unsigned char *data, int len, unsigned char *out, size_t n) {
+  pbcref_t *h = hv;
+  element_t e;
+  init_group(e, h, group);
+  int elen = group_len(h, group);
+  for (size_t i = 0; i < n; i++) {
+    element_from_hash(e, (void *)(data + i * (size_t)len), len);
+    element_to_bytes(out + i * elen, e);
+  }
+  element_clear(e);
+}
+
 /* out[i] = a[i] * b[i] in the group (additive groups: a+b). */
 void pbcref_mul(void *hv, int group, const unsigned char *a, const unsigned char *b,
                 unsigned char *out, size_t n) {

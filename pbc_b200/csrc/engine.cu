@@ -104,6 +104,8 @@ struct pbc_b200_pairing_s {
   FConsts f;
   DConsts d;
   ZrConsts zr;
+  HashConsts hash;
+  bool hash_ok = false;        // element_from_hash available (q = 3 mod 4 or 5 mod 8)
   int zr_len = 20;
   int ndev = 1;
   bool profile = false;        // record CUDA events between the kernels of the device-API path
@@ -181,6 +183,8 @@ static bool get_int(const std::map<std::string, std::string>& tab, const char* k
   return true;
 }
 
+static void fill_hash(pbc_b200_pairing_s* p, const BigUInt& q, const BigUInt& cofac);
+
 static int init_type_a(pbc_b200_pairing_s* p, const std::map<std::string, std::string>& tab) {
   BigUInt q, r, h;
   int exp2, exp1, sign1, sign0;
@@ -203,9 +207,28 @@ static int init_type_a(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   h.to_words(p->a.h, 12);
   p->a.hbits = (uint32_t)h.bits();
   p->a.exp2 = exp2; p->a.exp1 = exp1; p->a.sign1 = sign1;
+  fill_hash(p, q, h);                      // G1 cofactor = h (ecc/a_param.c:1451)
   BigUInt R = BigUInt(1).shl(512);
   ((R * BigUInt(2)) % q).to_words(p->a.two, kNA);
   return 0;
+}
+
+// element_from_hash constants (ecc/curve.c:455-482, arith/field.c:643-668)
+static void fill_hash(pbc_b200_pairing_s* p, const BigUInt& q, const BigUInt& cofac) {
+  HashConsts& h = p->hash;
+  memset(&h, 0, sizeof h);
+  q.to_words(h.q, 16);
+  h.count = (uint32_t)((q.bits() + 7) / 8);
+  BigUInt one(1), e;
+  if (q.word(0) % 4 == 3) { h.sqrt_mode = 1; e = (q + one) / BigUInt(4); }
+  else if (q.word(0) % 8 == 5) { h.sqrt_mode = 2; e = (q - BigUInt(5)) / BigUInt(8); }
+  else { h.sqrt_mode = 0; }
+  e.to_words(h.exp, 16);
+  h.expbits = (uint32_t)e.bits();
+  BigUInt c = cofac.is_zero() ? one : cofac;
+  c.to_words(h.cofac, 12);
+  h.cofbits = (uint32_t)c.bits();
+  p->hash_ok = h.sqrt_mode != 0 && c.bits() <= 384;
 }
 
 // x -> x * 2^(32 n) mod q, as n little-endian words
@@ -304,6 +327,7 @@ static int init_type_f(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   p->g1_len = 2 * kWS; p->g2_len = 4 * kWS; p->gt_len = 12 * kWS;
   fill_fp_consts(&p->fp, q, kNS);
   fill_cc(&p->cc, BigUInt(), b, r, q);
+  fill_hash(p, q, BigUInt(1));             // no cofactor on G1 (ecc/f_param.c:372)
   HostF2Field Kref{q, beta % q};
   HostF2 alpha{a0 % q, a1 % q};
   HostF2 xi = Kref.neg(alpha);
@@ -425,6 +449,12 @@ static int init_type_d(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   p->g1_len = 2 * kWS; p->g2_len = 6 * kWS; p->gt_len = 6 * kWS;
   fill_fp_consts(&p->fp, q, kNS);
   fill_cc(&p->cc, a, b, r, q);
+  {
+    BigUInt hco(1);
+    auto ith = tab.find("h");
+    if (ith != tab.end()) BigUInt::from_dec(ith->second, &hco);
+    fill_hash(p, q, hco);                  // G1 cofactor = h (ecc/d_param.c:1016)
+  }
   DConsts& c = p->d;
   memset(&c, 0, sizeof c);
   BigUInt v = nqr % q, vinv = BigUInt::invmod(v, q), one(1);
@@ -496,6 +526,7 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
       CUDA_OK(allow_smem(k_a_g1_mul<kBlockMiller>, (size_t)kGSlots * 64 * kBlockMiller));
       CUDA_OK(allow_smem(k_a_g1_finish<kBlockFinal>, (size_t)4 * 64 * kBlockFinal));
       CUDA_OK(allow_smem(k_a_gt_pow<kBlockMiller>, (size_t)7 * 64 * kBlockMiller));
+      CUDA_OK(allow_smem(k_a_g1_from_hash<kBlockMiller>, (size_t)kGSlots * 64 * kBlockMiller));
     }
     c.ready = true;
   }
@@ -506,6 +537,7 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
     CUDA_OK(cudaMemcpyToSymbol(c_fp, &p->fp, sizeof(FpConsts)));
     if (p->type == 'a') CUDA_OK(cudaMemcpyToSymbol(c_a, &p->a, sizeof(AConsts)));
     CUDA_OK(cudaMemcpyToSymbol(c_zr, &p->zr, sizeof(ZrConsts)));
+    CUDA_OK(cudaMemcpyToSymbol(c_hash, &p->hash, sizeof(HashConsts)));
     if (p->type == 'f' || p->type == 'd') CUDA_OK(cudaMemcpyToSymbol(c_cc, &p->cc, sizeof(CCConsts)));
     if (p->type == 'f') CUDA_OK(cudaMemcpyToSymbol(c_f, &p->f, sizeof(FConsts)));
     if (p->type == 'd') CUDA_OK(cudaMemcpyToSymbol(c_d, &p->d, sizeof(DConsts)));
@@ -1019,6 +1051,70 @@ int pbc_b200_g1_pow_zn_device(pbc_b200_pairing_t* p, void* d_out, const void* d_
 int pbc_b200_gt_pow_zn_device(pbc_b200_pairing_t* p, void* d_out, const void* d_in, const void* d_k, size_t n,
                               void* stream) {
   return run_group(p, 1, (unsigned char*)d_out, (const unsigned char*)d_in, (const unsigned char*)d_k, n, true, stream);
+}
+}
+
+
+// element_from_hash on G1 (include/pbc_field.h:202-212 -> ecc/curve.c:455-482), batched
+static int run_from_hash(pbc_b200_pairing_s* p, unsigned char* out, const unsigned char* data, size_t len, size_t n,
+                         bool device, void* stream) {
+  if (!p || (n && (!out || !data))) return fail("null argument");
+  if (!p->hash_ok) return fail("element_from_hash: needs q = 3 mod 4 or q = 5 mod 8 and a cofactor below 2^384");
+  if (len == 0 || len > (1u << 20)) return fail("element_from_hash: hash length must be 1..2^20 bytes");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(p->mu);
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  if (ctx_prepare(p, dev)) return 1;
+  DevCtx& c = p->ctx[dev];
+  size_t elen = (size_t)p->g1_len;
+  size_t wsb = p->type == 'a' ? n * 64 * (2 + 1 + 1) : 16;
+  size_t stage = device ? 0 : n * (elen + len);
+  if (c.cap_dev < wsb + stage) {
+    CUDA_OK(cudaDeviceSynchronize());
+    cudaFree(c.ws_dev);
+    c.ws_dev = nullptr; c.cap_dev = 0;
+    CUDA_OK(cudaMalloc(&c.ws_dev, wsb + stage));
+    c.cap_dev = wsb + stage;
+  }
+  cudaStream_t st = device ? (cudaStream_t)stream : c.stream[0];
+  uint8_t* d_out = device ? (uint8_t*)out : (uint8_t*)c.ws_dev + wsb;
+  const uint8_t* d_data = device ? (const uint8_t*)data : d_out + n * elen;
+  if (!device) CUDA_OK(cudaMemcpyAsync((void*)d_data, data, n * len, cudaMemcpyHostToDevice, st));
+  if (p->type == 'a') {
+    uint4* xyz = (uint4*)c.ws_dev;
+    uint4* zarr = xyz + 8 * n;
+    uint4* prefix = zarr + 4 * n;
+    unsigned g = (unsigned)((n + kBlockMiller - 1) / kBlockMiller);
+    k_a_g1_from_hash<kBlockMiller><<<g, kBlockMiller, (size_t)kGSlots * 64 * kBlockMiller, st>>>(d_data, (int)len, xyz, zarr, n);
+    LAUNCHED();
+    size_t T = n < (size_t)148 * 256 ? n : (size_t)148 * 256;
+    unsigned gi = (unsigned)((T + kBlockInv - 1) / kBlockInv);
+    k_batch_invert<kNA, true, kBlockInv><<<gi, kBlockInv, kSmemInv16, st>>>(zarr, prefix, n, T);
+    LAUNCHED();
+    unsigned gf = (unsigned)((n + kBlockFinal - 1) / kBlockFinal);
+    k_a_g1_finish<kBlockFinal><<<gf, kBlockFinal, (size_t)4 * 64 * kBlockFinal, st>>>(xyz, zarr, d_out, n);
+    LAUNCHED();
+  } else {
+    unsigned g = (unsigned)((n + kBlockCC - 1) / kBlockCC);
+    k_cc_g1_from_hash<kBlockCC><<<g, kBlockCC, 0, st>>>(d_data, (int)len, d_out, n);
+    LAUNCHED();
+  }
+  CUDA_OK(cudaGetLastError());
+  if (!device) {
+    CUDA_OK(cudaMemcpyAsync(out, d_out, n * elen, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+extern "C" {
+int pbc_b200_g1_from_hash(pbc_b200_pairing_t* p, unsigned char* out, const unsigned char* data, size_t len, size_t n) {
+  return run_from_hash(p, out, data, len, n, false, nullptr);
+}
+int pbc_b200_g1_from_hash_device(pbc_b200_pairing_t* p, void* d_out, const void* d_data, size_t len, size_t n,
+                                 void* stream) {
+  return run_from_hash(p, (unsigned char*)d_out, (const unsigned char*)d_data, len, n, true, stream);
 }
 }
 

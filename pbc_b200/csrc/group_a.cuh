@@ -20,6 +20,56 @@ struct ZrConsts {
 };
 __constant__ ZrConsts c_zr;
 
+// element_from_hash on G1 (ecc/curve.c:455-482): square-root exponent and cofactor, plain integers
+struct HashConsts {
+  uint32_t q[16];        // the field order (limit of pbc_mpz_from_hash, arith/field.c:643-668)
+  uint32_t exp[16];      // sqrt_mode 1: (q + 1) / 4 (q = 3 mod 4);  2: (q - 5) / 8 (q = 5 mod 8, Atkin)
+  uint32_t cofac[12];    // cofactor of G1 (h for types a and d, 1 for type f)
+  uint32_t expbits, cofbits, sqrt_mode, count;   // count = bytes of q
+};
+__constant__ HashConsts c_hash;
+
+// pbc_mpz_from_hash: fill `count` bytes with the data repeated, a counter byte after each copy
+// (arith/field.c:649-661), read big-endian into NW little-endian words, halve while > q (:665-667).
+template <int NW>
+__device__ __forceinline__ void hash_to_words(uint32_t* x, const uint8_t* data, int len) {
+  uint8_t buf[4 * NW];
+  const int count = (int)c_hash.count;
+  int i = 0;
+  uint8_t counter = 0;
+  for (;;) {
+    int n;
+    bool done;
+    if (len >= count - i) { n = count - i; done = true; } else { n = len; done = false; }
+    for (int k = 0; k < n; k++) buf[i + k] = data[k];
+    i += n;
+    if (done) break;
+    buf[i] = counter++;
+    i++;
+    if (i == count) break;
+  }
+#pragma unroll
+  for (int w = 0; w < NW; w++) {
+    uint32_t v = 0;
+    if (4 * w < count) {
+      const uint8_t* b = buf + count - 4 - 4 * w;
+      v = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+    }
+    x[w] = v;
+  }
+  for (int it = 0; it < 8; it++) {
+    bool gt = false, decided = false;
+#pragma unroll
+    for (int w = NW - 1; w >= 0; w--) {
+      if (!decided && x[w] != c_hash.q[w]) { gt = x[w] > c_hash.q[w]; decided = true; }
+    }
+    if (!gt) break;
+#pragma unroll
+    for (int w = 0; w < NW - 1; w++) x[w] = __funnelshift_r(x[w], x[w + 1], 1);
+    x[NW - 1] >>= 1;
+  }
+}
+
 constexpr int kWZ = 20;  // Zr wire bytes
 
 // 20 big-endian bytes -> five little-endian words, reduced mod r (r > 2^157: at most 7 subtractions)
@@ -151,6 +201,55 @@ k_a_g1_finish(const uint4* __restrict__ xyz, const uint4* __restrict__ zinv, uin
     }
     limbs_to_be<kNA, kWA>(o + c * kWA, x);
   }
+}
+
+// element_from_hash on G1, type a (q = 3 mod 4): try-and-increment on x, y = the odd root of
+// x^3 + x via t^((q+1)/4), then the cofactor multiple (h = (q + 1)/r, 353 bits for a.param).
+// Output as k_a_g1_mul leaves it (Jacobian X, Y and Z for the batched inversion).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_a_g1_from_hash(const uint8_t* __restrict__ data, int len, uint4* __restrict__ xyz,
+                 uint4* __restrict__ zarr, size_t n) {
+  using O = Ops<kNA, true, BLOCK>;
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  bool live = idx < n;
+  size_t src = live ? idx : 0;
+  uint32_t x[kNA], one[kNA] = {1};
+  hash_to_words<kNA>(x, data + src * (size_t)len, len);
+  mont_mul<kNA, true>(x, x, c_fp.r2);            // also reduces z == q to 0
+  O::st(gPX, x);
+  O::set_const(gT4, c_fp.one);
+  for (int tries = 0; tries < 64; tries++) {
+    O::sqr(gT0, gPX);
+    O::add(gT0, gT0, gT4);
+    O::mul(gT0, gT0, gPX);                       // t = x^3 + x
+    O::copy(gPY, gT0);
+    for (int j = (int)c_hash.expbits - 2; j >= 0; j--) {
+      O::sqr(gPY, gPY);
+      if ((c_hash.exp[j >> 5] >> (j & 31)) & 1u) O::mul(gPY, gPY, gT0);
+    }
+    O::sqr(gT1, gPY);
+    if (O::eq(gT1, gT0)) break;                  // t is a square (0 included), gPY = a root
+    O::sqr(gPX, gPX);
+    O::add(gPX, gPX, gT4);                       // x <- x^2 + 1
+  }
+  // keep the odd root (fp_sgn_odd, arith/montfp.c:460-472)
+  O::ld(x, gPY);
+  mont_mul<kNA, true>(x, x, one);
+  if (!(x[0] & 1u) && !fp_is_zero<kNA>(x)) O::neg(gPY, gPY);
+  // cofactor multiple
+  O::copy(gX, gPX);
+  O::copy(gY, gPY);
+  O::set_const(gZ, c_fp.one);
+  O::set_const(gZ2, c_fp.one);
+  for (int j = (int)c_hash.cofbits - 2; j >= 0; j--) {
+    g_double<O>();
+    if ((c_hash.cofac[j >> 5] >> (j & 31)) & 1u) g_add_affine<O>();
+  }
+  if (!live) return;
+  O::st_global(xyz, 0, n, idx, gX);
+  O::st_global(xyz, 1, n, idx, gY);
+  O::st_global(zarr, 0, n, idx, gZ);
 }
 
 // out[i] = in[i]^k[i] in F_q^2 (GT wire format: re || im)

@@ -92,6 +92,120 @@ k_cc_g1_mul(const uint8_t* __restrict__ P, const uint8_t* __restrict__ K, uint8_
   fq_to_wire(out + idx * (2 * kWS) + kWS, Y);
 }
 
+// element_from_hash on G1 for the five-limb fields (ecc/curve.c:455-482): try-and-increment, the odd
+// square root (q = 3 mod 4: t^((q+1)/4); q = 5 mod 8: Atkin's b = (2t)^((q-5)/8), i = 2 t b^2,
+// root = t b (i - 1)), then the cofactor multiple (d159: h = 3; type f: none).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, PBC_CC_MINBLOCKS)
+k_cc_g1_from_hash(const uint8_t* __restrict__ data, int len, uint8_t* __restrict__ out, size_t n) {
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  Fq x, y, t, b, u, w, A, B, one, X, Y, Z, Z2, M, Y2, H, R;
+  uint32_t xw[kNS];
+  hash_to_words<kNS>(xw, data + idx * (size_t)len, len);
+  fq_set(x, xw);
+  fq_set(t, c_fp.r2);
+  fq_mul(x, x, t);
+  fq_set(A, c_cc.A);
+  fq_set(B, c_cc.B);
+  fq_one(one);
+  for (int tries = 0; tries < 64; tries++) {
+    fq_sqr(t, x);
+    fq_add(t, t, A);
+    fq_mul(t, t, x);
+    fq_add(t, t, B);                       // t = x^3 + A x + B
+    if (c_hash.sqrt_mode == 1) u = t; else fq_dbl(u, t);
+    b = u;
+    for (int j = (int)c_hash.expbits - 2; j >= 0; j--) {
+      fq_sqr(b, b);
+      if ((c_hash.exp[j >> 5] >> (j & 31)) & 1u) fq_mul(b, b, u);
+    }
+    if (c_hash.expbits == 0) b = one;
+    if (c_hash.sqrt_mode == 1) {
+      y = b;
+    } else {
+      fq_sqr(w, b);
+      fq_mul(w, w, u);                     // i = 2 t b^2
+      fq_sub(w, w, one);
+      fq_mul(y, t, b);
+      fq_mul(y, y, w);                     // t b (i - 1)
+    }
+    fq_sqr(w, y);
+    if (fq_eq(w, t)) break;
+    fq_sqr(x, x);
+    fq_add(x, x, one);
+  }
+  {
+    uint32_t c[kNS], o1[kNS] = {1};
+    mont_mul_ps<kNS, false>(c, y.v, o1);
+    if (!(c[0] & 1u) && !fp_is_zero<kNS>(c)) fq_neg(y, y);
+  }
+  if (c_hash.cofbits <= 1) {               // cofactor 1: the point itself
+    fq_to_wire(out + idx * (2 * kWS), x);
+    fq_to_wire(out + idx * (2 * kWS) + kWS, y);
+    return;
+  }
+  X = x;
+  Y = y;
+  fq_one(Z);
+  for (int j = (int)c_hash.cofbits - 2; j >= 0; j--) {
+    fq_sqr(Z2, Z);
+    fq_sqr(t, X);
+    fq_dbl(M, t);
+    fq_add(M, M, t);
+    if (!c_cc.a_is_zero) {
+      fq_sqr(u, Z2);
+      fq_mul(u, u, A);
+      fq_add(M, M, u);
+    }
+    fq_sqr(Y2, Y);
+    fq_mul(u, Y, Z);
+    fq_dbl(Z, u);
+    fq_mul(t, X, Y2);
+    fq_dbl(t, t);
+    fq_dbl(t, t);
+    fq_sqr(X, M);
+    fq_sub(X, X, t);
+    fq_sub(X, X, t);
+    fq_sqr(Y2, Y2);
+    fq_dbl(Y2, Y2);
+    fq_dbl(Y2, Y2);
+    fq_dbl(Y2, Y2);
+    fq_sub(t, t, X);
+    fq_mul(Y, M, t);
+    fq_sub(Y, Y, Y2);
+    if ((c_hash.cofac[j >> 5] >> (j & 31)) & 1u) {
+      fq_sqr(Z2, Z);
+      fq_mul(t, Z2, Z);
+      fq_mul(H, x, Z2);
+      fq_sub(H, H, X);
+      fq_mul(R, y, t);
+      fq_sub(R, R, Y);
+      fq_mul(Z, H, Z);
+      fq_sqr(t, H);
+      fq_mul(u, t, H);
+      fq_mul(t, t, X);
+      fq_sqr(X, R);
+      fq_sub(X, X, u);
+      fq_sub(X, X, t);
+      fq_sub(X, X, t);
+      fq_sub(t, t, X);
+      fq_mul(t, t, R);
+      fq_mul(u, u, Y);
+      fq_sub(Y, t, u);
+    }
+  }
+  bool inf = fq_is_zero(Z);
+  fq_inv(&t, &Z);
+  fq_sqr(u, t);
+  fq_mul(X, X, u);
+  fq_mul(u, u, t);
+  fq_mul(Y, Y, u);
+  if (inf) { fq_zero(X); fq_zero(Y); }
+  fq_to_wire(out + idx * (2 * kWS), X);
+  fq_to_wire(out + idx * (2 * kWS) + kWS, Y);
+}
+
 // ---------------------------------------------------------------------------------------------
 // G2: y^2 = x^3 + a' x + b' over K = F_q^2 (type f, a' = 0) or F_q^3 (type d).  KF supplies the
 // field: struct El; mul/sqr/inv on pointers (the tower's out-of-line routines), add/sub/dbl inline,

@@ -123,6 +123,19 @@ class Pairing:
             raise PairingError(last_error())
         return out.raw[:n * self.g1_len]
 
+    def g1_from_hash(self, data: bytes, length: int, n=None) -> bytes:
+        """element_from_hash on G1 for n hashes of `length` bytes each, back to back"""
+        if n is None:
+            n = len(data) // length
+        out = C.create_string_buffer(max(1, n * self.g1_len))
+        if lib.pbc_b200_g1_from_hash(self._h, C.addressof(out), _addr(data), length, n):
+            raise PairingError(last_error())
+        return out.raw[:n * self.g1_len]
+
+    def g1_from_hash_device(self, d_out, d_data, length, n, stream=0):
+        if lib.pbc_b200_g1_from_hash_device(self._h, d_out, d_data, length, n, stream):
+            raise PairingError(last_error())
+
     def g2_pow_zn(self, points: bytes, scalars: bytes, n=None) -> bytes:
         if n is None:
             n = len(points) // self.g2_len

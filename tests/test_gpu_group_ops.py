@@ -122,3 +122,42 @@ def test_both_arguments_powered_on_device(env):
     aP = d.g1_pow_zn(_cat(g["pairing"]["P"][:n]), a, n)
     aQ = d.g2_pow_zn(_cat(g["pairing"]["Q"][:n]), a, n)
     assert d.apply(aP, aQ, n) == _cat(g["pow"]["e_Pa_Qa"])
+
+
+# ---- element_from_hash on G1 (ecc/curve.c:455-482) ----
+@pytest.mark.parametrize("length", [3, 20, 32, 70])
+def test_g1_from_hash_reference_fixtures(env, length):
+    blk = env["g"]["hash"][str(length)]
+    got = env["dev"].g1_from_hash(_cat(blk["data"]), length, len(blk["data"]))
+    assert got == _cat(blk["G1"])
+
+
+def test_g1_from_hash_matches_oracle_on_many_inputs(env):
+    import hashlib
+    d, orc = env["dev"], env["orc"]
+    n = 40
+    hs = [hashlib.sha256(b"msg-%d" % i).digest() for i in range(n)]
+    got = d.g1_from_hash(b"".join(hs), 32, n)
+    L = d.g1_len
+    for i, h in enumerate(hs):
+        assert got[i * L:(i + 1) * L] == orc.G1.to_bytes(O.g1_from_hash(orc, h)), i
+
+
+def test_bls_style_verification_entirely_on_device(env):
+    """sigma = sk * H(m), pk = sk * g2: e(sigma, g2) == e(H(m), pk) -- hash-to-curve, both scalar
+    multiplications and both pairings on the GPU; a forged signature must fail."""
+    import hashlib
+    g, d, orc = env["g"], env["dev"], env["orc"]
+    n = 6
+    rnd = random.Random(41)
+    sk = rnd.randrange(1, orc.r).to_bytes(20, "big")
+    g2 = bytes.fromhex(g["pairing"]["Q"][0])
+    pk = d.g2_pow_zn(g2, sk, 1)
+    msgs = b"".join(hashlib.sha256(b"bls-%d" % i).digest() for i in range(n))
+    H = d.g1_from_hash(msgs, 32, n)
+    sig = d.g1_pow_zn(H, sk * n, n)
+    lhs = d.apply(sig, g2 * n, n)
+    rhs = d.apply(H, pk * n, n)
+    assert lhs == rhs
+    forged = d.g1_pow_zn(H, (int.from_bytes(sk, "big") ^ 1).to_bytes(20, "big") * n, n)
+    assert d.apply(forged, g2 * n, n) != rhs

@@ -92,3 +92,16 @@ def test_param_parser_rejects_garbage():
         O.pairing_from_param("q 17\nr 3\n")
     with pytest.raises(ValueError):
         O.pairing_from_param("type zz\nq 17\n")
+
+
+def test_from_hash_restatement_matches_reference_fixtures(golden):
+    """curve_from_hash (ecc/curve.c:455-482) + pbc_mpz_from_hash (arith/field.c:643-668): the
+    oracle's restatement vs G1 elements the compiled reference derived from the same bytes."""
+    from oracle import pbc_oracle as O
+    from pbc_b200.params import PARAMS
+    for name in ("a", "f", "d159"):
+        orc = O.pairing_from_param(PARAMS[name])
+        for ln, blk in golden[name]["hash"].items():
+            for d, want in zip(blk["data"], blk["G1"]):
+                assert len(d) == 2 * int(ln)
+                assert orc.G1.to_bytes(O.g1_from_hash(orc, bytes.fromhex(d))).hex() == want

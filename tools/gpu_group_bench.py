@@ -70,6 +70,20 @@ def main():
                 line["cpu_cores"] = cores
                 line["parity_vs_reference"] = bytes(out[:m * pr.g1_len].cpu().numpy().tobytes()) == ref_out
             print(json.dumps(line))
+        # element_from_hash on G1: n SHA-256-sized inputs
+        import numpy as np
+        dH = torch.from_numpy(np.random.default_rng(7).integers(0, 256, n * 32, dtype=np.uint8)).cuda()
+        for _ in range(2):
+            pr.g1_from_hash_device(dO1.data_ptr(), dH.data_ptr(), 32, n, st.cuda_stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(3):
+            pr.g1_from_hash_device(dO1.data_ptr(), dH.data_ptr(), 32, n, st.cuda_stream)
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        print(json.dumps({"type": wn, "op": "element_from_hash G1 (32-byte inputs)", "n": n, "ms": ms, "per_s": n / ms * 1e3}))
 
 
 if __name__ == "__main__":
