@@ -116,6 +116,14 @@ int pbc_b200_g1_from_hash(pbc_b200_pairing_t *p, unsigned char *out, const unsig
 int pbc_b200_g1_from_hash_device(pbc_b200_pairing_t *p, void *d_out, const void *d_data, size_t len,
                                  size_t n, void *stream);
 
+/* Batched element_from_bytes_compressed on G1 (ecc/curve.c:762-813): each input is the x
+ * coordinate in wire format followed by one byte, 1 when y is odd (fp_sgn_odd); output is the full
+ * wire element x || y.  An x with no point on the curve gives zero bytes.  (Compression itself is
+ * x plus the parity of y and needs no GPU; pbc_b200/pairing.py has it.) */
+int pbc_b200_pairing_length_in_bytes_compressed_G1(const pbc_b200_pairing_t *p);
+int pbc_b200_g1_from_bytes_compressed(pbc_b200_pairing_t *p, unsigned char *out, const unsigned char *in,
+                                      size_t n);
+
 /* Multi-GPU fan-out for the host-buffer entry points: use devices [0, count).  count = 0 means
  * every visible device.  Default is 1 (the current device). */
 int pbc_b200_set_devices(pbc_b200_pairing_t *p, int count);

@@ -46,6 +46,9 @@ def _lib():
         L.pbcref_mul.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p,
                                  C.c_size_t]
         L.pbcref_from_str.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p]
+        L.pbcref_compressed_len.argtypes = [C.c_void_p, C.c_int]
+        L.pbcref_compress.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_size_t]
+        L.pbcref_decompress.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_size_t]
         L.pbcref_from_hash.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
         L.pbcref_is_identity.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
         _cached = L
@@ -109,6 +112,17 @@ class RefPairing:
     def from_hash(self, group, data: bytes, length: int, n: int) -> bytes:
         out = C.create_string_buffer(n * self._len(group))
         self.L.pbcref_from_hash(self.h, group, data, length, out, n)
+        return out.raw
+
+    def compress(self, group, x: bytes, n: int) -> bytes:
+        clen = self.L.pbcref_compressed_len(self.h, group)
+        out = C.create_string_buffer(n * clen)
+        self.L.pbcref_compress(self.h, group, x, out, n)
+        return out.raw
+
+    def decompress(self, group, x: bytes, n: int) -> bytes:
+        out = C.create_string_buffer(n * self._len(group))
+        self.L.pbcref_decompress(self.h, group, x, out, n)
         return out.raw
 
     def mul(self, group, a: bytes, b: bytes, n: int) -> bytes:

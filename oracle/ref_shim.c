@@ -190,6 +190,39 @@ void pbcref_from_hash(void *hv, int group, const unsigned char *data, int len, u
   element_clear(e);
 }
 
+/* element_to_bytes_compressed / element_from_bytes_compressed (ecc/curve.c:762-813) on G1 or G2:
+ * compress: wire -> x || sign byte;  decompress: x || sign byte -> wire. */
+int pbcref_compressed_len(void *hv, int group) {
+  pbcref_t *h = hv;
+  element_t e;
+  init_group(e, h, group);
+  int n = element_length_in_bytes_compressed(e);
+  element_clear(e);
+  return n;
+}
+void pbcref_compress(void *hv, int group, const unsigned char *in, unsigned char *out, size_t n) {
+  pbcref_t *h = hv;
+  element_t e;
+  init_group(e, h, group);
+  int len = group_len(h, group), clen = element_length_in_bytes_compressed(e);
+  for (size_t i = 0; i < n; i++) {
+    element_from_bytes(e, (unsigned char *)in + i * len);
+    element_to_bytes_compressed(out + i * clen, e);
+  }
+  element_clear(e);
+}
+void pbcref_decompress(void *hv, int group, const unsigned char *in, unsigned char *out, size_t n) {
+  pbcref_t *h = hv;
+  element_t e;
+  init_group(e, h, group);
+  int len = group_len(h, group), clen = element_length_in_bytes_compressed(e);
+  for (size_t i = 0; i < n; i++) {
+    element_from_bytes_compressed(e, (unsigned char *)in + i * clen);
+    element_to_bytes(out + i * len, e);
+  }
+  element_clear(e);
+}
+
 /* out[i] = a[i] * b[i] in the group (additive groups: a+b). */
 void pbcref_mul(void *hv, int group, const unsigned char *a, const unsigned char *b,
                 unsigned char *out, size_t n) {

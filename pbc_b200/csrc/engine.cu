@@ -527,6 +527,7 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
       CUDA_OK(allow_smem(k_a_g1_finish<kBlockFinal>, (size_t)4 * 64 * kBlockFinal));
       CUDA_OK(allow_smem(k_a_gt_pow<kBlockMiller>, (size_t)7 * 64 * kBlockMiller));
       CUDA_OK(allow_smem(k_a_g1_from_hash<kBlockMiller>, (size_t)kGSlots * 64 * kBlockMiller));
+      CUDA_OK(allow_smem(k_a_g1_decompress<kBlockMiller>, (size_t)5 * 64 * kBlockMiller));
     }
     c.ready = true;
   }
@@ -1116,6 +1117,45 @@ int pbc_b200_g1_from_hash_device(pbc_b200_pairing_t* p, void* d_out, const void*
                                  void* stream) {
   return run_from_hash(p, (unsigned char*)d_out, (const unsigned char*)d_data, len, n, true, stream);
 }
+}
+
+
+// element_from_bytes_compressed on G1 (ecc/curve.c:799-813), batched; host buffers
+extern "C" int pbc_b200_pairing_length_in_bytes_compressed_G1(const pbc_b200_pairing_t* p) { return p->g1_len / 2 + 1; }
+extern "C" int pbc_b200_g1_from_bytes_compressed(pbc_b200_pairing_t* p, unsigned char* out, const unsigned char* in,
+                                                 size_t n) {
+  if (!p || (n && (!out || !in))) return fail("null argument");
+  if (!p->hash_ok) return fail("element_from_bytes_compressed: needs q = 3 mod 4 or q = 5 mod 8");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(p->mu);
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  if (ctx_prepare(p, dev)) return 1;
+  DevCtx& c = p->ctx[dev];
+  size_t clen = (size_t)p->g1_len / 2 + 1, elen = (size_t)p->g1_len, need = n * (clen + elen) + 16;
+  if (c.cap_dev < need) {
+    CUDA_OK(cudaDeviceSynchronize());
+    cudaFree(c.ws_dev);
+    c.ws_dev = nullptr; c.cap_dev = 0;
+    CUDA_OK(cudaMalloc(&c.ws_dev, need));
+    c.cap_dev = need;
+  }
+  cudaStream_t st = c.stream[0];
+  uint8_t* d_out = (uint8_t*)c.ws_dev;               // element output first: keeps it 4-byte aligned
+  uint8_t* d_in = d_out + n * elen;
+  CUDA_OK(cudaMemcpyAsync(d_in, in, n * clen, cudaMemcpyHostToDevice, st));
+  if (p->type == 'a') {
+    unsigned g = (unsigned)((n + kBlockMiller - 1) / kBlockMiller);
+    k_a_g1_decompress<kBlockMiller><<<g, kBlockMiller, (size_t)5 * 64 * kBlockMiller, st>>>(d_in, d_out, n);
+  } else {
+    unsigned g = (unsigned)((n + kBlockCC - 1) / kBlockCC);
+    k_cc_g1_decompress<kBlockCC><<<g, kBlockCC, 0, st>>>(d_in, d_out, n);
+  }
+  LAUNCHED();
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(out, d_out, n * elen, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -252,6 +252,54 @@ k_a_g1_from_hash(const uint8_t* __restrict__ data, int len, uint4* __restrict__ 
   O::st_global(zarr, 0, n, idx, gZ);
 }
 
+// element_from_bytes_compressed on G1, type a (ecc/curve.c:799-813): x (64 bytes) || sign byte ->
+// x || y with y = the root of x^3 + x whose parity the flag asks for (1 = odd, fp_sgn_odd).  An x
+// whose right-hand side is not a square has no point: written as zero bytes (the reference's
+// Tonelli loop returns garbage there).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_a_g1_decompress(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t n) {
+  using O = Ops<kNA, true, BLOCK>;
+  enum { sX, sY, sT, sU, sONE };
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  bool live = idx < n;
+  size_t src = live ? idx : 0;
+  const uint8_t* p = in + src * (kWA + 1);
+  uint32_t x[kNA], one[kNA] = {1};
+  limbs_from_be_bytes<kNA, kWA>(x, p);     // items are 65 bytes apart: byte loads
+  mont_mul<kNA, true>(x, x, c_fp.r2);
+  O::st(sX, x);
+  O::set_const(sONE, c_fp.one);
+  O::sqr(sT, sX);
+  O::add(sT, sT, sONE);
+  O::mul(sT, sT, sX);
+  O::copy(sY, sT);
+  for (int j = (int)c_hash.expbits - 2; j >= 0; j--) {
+    O::sqr(sY, sY);
+    if ((c_hash.exp[j >> 5] >> (j & 31)) & 1u) O::mul(sY, sY, sT);
+  }
+  O::sqr(sU, sY);
+  bool ok = O::eq(sU, sT);
+  if (!live) return;
+  uint32_t y[kNA];
+  O::ld(y, sY);
+  mont_mul<kNA, true>(y, y, one);
+  bool odd = (y[0] & 1u) != 0, want_odd = p[kWA] != 0;
+  if (odd != want_odd && !fp_is_zero<kNA>(y)) {
+    O::neg(sY, sY);
+    O::ld(y, sY);
+    mont_mul<kNA, true>(y, y, one);
+  }
+  O::ld(x, sX);
+  mont_mul<kNA, true>(x, x, one);
+  if (!ok) {
+#pragma unroll
+    for (int k = 0; k < kNA; k++) { x[k] = 0; y[k] = 0; }
+  }
+  limbs_to_be<kNA, kWA>(out + idx * (2 * kWA), x);
+  limbs_to_be<kNA, kWA>(out + idx * (2 * kWA) + kWA, y);
+}
+
 // out[i] = in[i]^k[i] in F_q^2 (GT wire format: re || im)
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)

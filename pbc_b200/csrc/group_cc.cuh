@@ -206,6 +206,52 @@ k_cc_g1_from_hash(const uint8_t* __restrict__ data, int len, uint8_t* __restrict
   fq_to_wire(out + idx * (2 * kWS) + kWS, Y);
 }
 
+// element_from_bytes_compressed on G1 for the five-limb fields (ecc/curve.c:799-813): x (20 bytes) ||
+// sign byte -> x || y.  No square root -> zero bytes.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, PBC_CC_MINBLOCKS)
+k_cc_g1_decompress(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t n) {
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  const uint8_t* p = in + idx * (kWS + 1);
+  Fq x, y, t, b, u, w, one, k;
+  limbs_from_be_bytes<kNS, kWS>(x.v, p);
+  fq_set(k, c_fp.r2);
+  fq_mul(x, x, k);
+  fq_one(one);
+  fq_sqr(t, x);
+  fq_set(k, c_cc.A);
+  fq_add(t, t, k);
+  fq_mul(t, t, x);
+  fq_set(k, c_cc.B);
+  fq_add(t, t, k);
+  if (c_hash.sqrt_mode == 1) u = t; else fq_dbl(u, t);
+  b = u;
+  for (int j = (int)c_hash.expbits - 2; j >= 0; j--) {
+    fq_sqr(b, b);
+    if ((c_hash.exp[j >> 5] >> (j & 31)) & 1u) fq_mul(b, b, u);
+  }
+  if (c_hash.expbits == 0) b = one;
+  if (c_hash.sqrt_mode == 1) {
+    y = b;
+  } else {
+    fq_sqr(w, b);
+    fq_mul(w, w, u);
+    fq_sub(w, w, one);
+    fq_mul(y, t, b);
+    fq_mul(y, y, w);
+  }
+  fq_sqr(w, y);
+  bool ok = fq_eq(w, t);
+  uint32_t c[kNS], o1[kNS] = {1};
+  mont_mul_ps<kNS, false>(c, y.v, o1);
+  bool odd = (c[0] & 1u) != 0, want_odd = p[kWS] != 0;
+  if (odd != want_odd && !fp_is_zero<kNS>(c)) fq_neg(y, y);
+  if (!ok) { fq_zero(x); fq_zero(y); }
+  fq_to_wire(out + idx * (2 * kWS), x);
+  fq_to_wire(out + idx * (2 * kWS) + kWS, y);
+}
+
 // ---------------------------------------------------------------------------------------------
 // G2: y^2 = x^3 + a' x + b' over K = F_q^2 (type f, a' = 0) or F_q^3 (type d).  KF supplies the
 // field: struct El; mul/sqr/inv on pointers (the tower's out-of-line routines), add/sub/dbl inline,

@@ -242,6 +242,19 @@ __device__ __forceinline__ void limbs_from_be(uint32_t* x, const uint8_t* p) {
     }
   }
 }
+// the same from a byte pointer of any alignment
+template <int N, int WB>
+__device__ __forceinline__ void limbs_from_be_bytes(uint32_t* x, const uint8_t* p) {
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    if (k < WB / 4) {
+      const uint8_t* b = p + WB - 4 - 4 * k;
+      x[k] = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+    } else {
+      x[k] = 0;
+    }
+  }
+}
 template <int N, int WB>
 __device__ __forceinline__ void limbs_to_be(uint8_t* p, const uint32_t* x) {
 #pragma unroll

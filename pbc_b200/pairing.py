@@ -136,6 +136,23 @@ class Pairing:
         if lib.pbc_b200_g1_from_hash_device(self._h, d_out, d_data, length, n, stream):
             raise PairingError(last_error())
 
+    def g1_compress(self, points: bytes, n=None) -> bytes:
+        """element_to_bytes_compressed (ecc/curve.c:762-775): x || (1 if y is odd else 0); host only"""
+        L = self.g1_len
+        if n is None:
+            n = len(points) // L
+        return b"".join(points[i * L:i * L + L // 2] + bytes([points[(i + 1) * L - 1] & 1]) for i in range(n))
+
+    def g1_decompress(self, data: bytes, n=None) -> bytes:
+        """element_from_bytes_compressed on the GPU"""
+        clen = self.g1_len // 2 + 1
+        if n is None:
+            n = len(data) // clen
+        out = C.create_string_buffer(max(1, n * self.g1_len))
+        if lib.pbc_b200_g1_from_bytes_compressed(self._h, C.addressof(out), _addr(data), n):
+            raise PairingError(last_error())
+        return out.raw[:n * self.g1_len]
+
     def g2_pow_zn(self, points: bytes, scalars: bytes, n=None) -> bytes:
         if n is None:
             n = len(points) // self.g2_len

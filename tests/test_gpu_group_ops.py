@@ -161,3 +161,26 @@ def test_bls_style_verification_entirely_on_device(env):
     assert lhs == rhs
     forged = d.g1_pow_zn(H, (int.from_bytes(sk, "big") ^ 1).to_bytes(20, "big") * n, n)
     assert d.apply(forged, g2 * n, n) != rhs
+
+
+# ---- element_to/from_bytes_compressed on G1 (ecc/curve.c:762-813) ----
+def test_g1_compressed_roundtrip_reference_fixtures(env):
+    g, d = env["g"], env["dev"]
+    n = len(g["compressed"]["G1"])
+    P = _cat(g["pairing"]["P"][:n])
+    comp = _cat(g["compressed"]["G1"])
+    assert d.g1_compress(P, n) == comp                      # host-side compression == the reference's
+    assert d.g1_decompress(comp, n) == P
+    clen = g["compressed"]["len"]
+    flipped = b"".join(comp[i * clen:(i + 1) * clen - 1] + bytes([comp[(i + 1) * clen - 1] ^ 1]) for i in range(n))
+    assert d.g1_decompress(flipped, n) == _cat(g["compressed"]["G1_flipped_sign"])
+
+
+def test_g1_decompress_x_without_point_gives_zero_bytes(env):
+    d, orc = env["dev"], env["orc"]
+    q, E = orc.q, orc.G1
+    x = 2
+    while pow(((x * x + E.a) * x + E.b) % q, (q - 1) // 2, q) != q - 1:
+        x += 1
+    L = d.g1_len
+    assert d.g1_decompress(x.to_bytes(L // 2, "big") + b"\x01", 1) == bytes(L)
