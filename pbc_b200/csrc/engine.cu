@@ -465,10 +465,39 @@ static int init_type_d(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   to_mont(c.twist_a, BigUInt::mulmod(a % q, v2, q), q, kNS);
   to_mont(c.twist_b, BigUInt::mulmod(b % q, BigUInt::mulmod(v2, v, q), q), q, kNS);
   to_mont(c.two, BigUInt(2), q, kNS);
-  HostF3Field K{q, {c0 % q, c1 % q, c2 % q}};
+  HostF3Field Kref{q, {c0 % q, c1 % q, c2 % q}};
   HostF3 x;
   x.c[1] = one;
-  HostF3 x3 = K.mul(K.mul(x, x), x), x4 = K.mul(x3, x);
+  HostF3 x3 = Kref.mul(Kref.mul(x, x), x), x4 = Kref.mul(x3, x);
+  HostF3 xq_ref = Kref.pow(x, q), xq2_ref = Kref.mul(xq_ref, xq_ref);
+  // internal cubic w^3 + p w + 1 (tools/proto_d_basis.py): x = lam w - s
+  HostF3Field K = Kref;
+  if (!p->force_reference_basis && (q % BigUInt(3)) == BigUInt(2)) {
+    BigUInt i3 = BigUInt::invmod(BigUInt(3), q), i27 = BigUInt::invmod(BigUInt(27), q);
+    BigUInt C0 = c0 % q, C1 = c1 % q, C2 = c2 % q;
+    BigUInt s0 = BigUInt::mulmod(C2, i3, q);
+    BigUInt C2sq = BigUInt::mulmod(C2, C2, q);
+    BigUInt P = BigUInt::submod(C1, BigUInt::mulmod(C2sq, i3, q), q);
+    BigUInt R0 = BigUInt::addmod(BigUInt::submod(C0, BigUInt::mulmod(BigUInt::mulmod(C1, C2, q), i3, q), q),
+                                 BigUInt::mulmod(BigUInt::mulmod(BigUInt(2), BigUInt::mulmod(C2sq, C2, q), q), i27, q), q);
+    BigUInt lam = BigUInt::powmod(R0, (q * BigUInt(2) - one) / BigUInt(3), q);
+    BigUInt lam2 = BigUInt::mulmod(lam, lam, q);
+    if (!R0.is_zero() && BigUInt::mulmod(lam2, lam, q) == R0) {
+      BigUInt lami = BigUInt::invmod(lam, q);
+      BigUInt pc = BigUInt::mulmod(P, BigUInt::mulmod(lami, lami, q), q);
+      c.nice = 1;
+      to_mont(c.pcoef, pc, q, kNS);
+      to_mont(c.bs, s0, q, kNS);
+      to_mont(c.bs2, BigUInt::mulmod(s0, s0, q), q, kNS);
+      to_mont(c.b2s, BigUInt::addmod(s0, s0, q), q, kNS);
+      to_mont(c.blam, lam, q, kNS);
+      to_mont(c.blam2, lam2, q, kNS);
+      to_mont(c.blami, lami, q, kNS);
+      to_mont(c.blami2, BigUInt::mulmod(lami, lami, q), q, kNS);
+      K = HostF3Field{q, {one, pc, BigUInt()}};
+      p->derived["basis_cubic"] = {s0, lam, pc};
+    }
+  }
   HostF3 xq = K.pow(x, q), xq2 = K.mul(xq, xq);
   for (int i = 0; i < 3; i++) {
     to_mont(c.xpwr3[i], x3.c[i], q, kNS);
@@ -484,8 +513,9 @@ static int init_type_d(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   p->derived["phikonr"] = {ph};
   p->derived["xpwr3"] = {x3.c[0], x3.c[1], x3.c[2]};
   p->derived["xpwr4"] = {x4.c[0], x4.c[1], x4.c[2]};
-  p->derived["xpowq"] = {xq.c[0], xq.c[1], xq.c[2]};
-  p->derived["xpowq2"] = {xq2.c[0], xq2.c[1], xq2.c[2]};
+  p->derived["xpowq"] = {xq_ref.c[0], xq_ref.c[1], xq_ref.c[2]};      // reference-basis values (tests)
+  p->derived["xpowq2"] = {xq2_ref.c[0], xq2_ref.c[1], xq2_ref.c[2]};
+  p->derived["xpowq_in_use"] = {xq.c[0], xq.c[1], xq.c[2]};
   p->derived["nqrinv"] = {vinv};
   p->derived["nqrinv2"] = {BigUInt::mulmod(vinv, vinv, q)};
   c.phibits = (uint32_t)ph.bits();

@@ -309,9 +309,11 @@ struct KF3 {                       // type d
   static __device__ __forceinline__ void from_wire(El& r, const uint8_t* p) {
 #pragma unroll
     for (int i = 0; i < 3; i++) fq_from_wire(r.c[i], p + i * kWS);
+    f3_to_internal(r);
   }
   static __device__ __forceinline__ void to_wire(uint8_t* p, const El& a, bool zero) {
     El o = a;
+    f3_to_reference(o);
     if (zero) f3_zero(o);
 #pragma unroll
     for (int i = 0; i < 3; i++) fq_to_wire(p + i * kWS, o.c[i]);
@@ -434,6 +436,8 @@ k_d_gt_pow(const uint8_t* __restrict__ G, const uint8_t* __restrict__ K, uint8_t
   F6D base, acc;
   uint32_t k[5];
   f6d_from_wire(base, G + idx * (6 * kWS));
+  f3_to_internal(base.a);
+  f3_to_internal(base.b);
   zr_from_wire(k, K + idx * kWZ);
   int top = zr_top_bit(k);
   acc = base;
@@ -442,6 +446,8 @@ k_d_gt_pow(const uint8_t* __restrict__ G, const uint8_t* __restrict__ K, uint8_t
     if ((k[j >> 5] >> (j & 31)) & 1u) f6d_mul(&acc, &acc, &base);
   }
   if (top < 0) f6d_one(acc);
+  f3_to_reference(acc.a);
+  f3_to_reference(acc.b);
   f6d_to_wire(out + idx * (6 * kWS), acc);
 }
 

@@ -29,7 +29,15 @@ struct DConsts {
   uint32_t two[kNS];               // Montgomery 2
   uint32_t phikonr[8];             // (q^2 - q + 1)/r, plain integer (ecc/d_param.c:1035-1041)
   uint32_t phibits;
-  uint32_t pad[3];
+  // Internal cubic basis (q = 2 mod 3; tools/proto_d_basis.py):  F_q^3 = F_q[w]/(w^3 + p w + 1) with
+  // x = lam w - s, s = c2/3, lam^3 = c0 - c1 c2/3 + 2 c2^3/27, p = (c1 - c2^2/3)/lam^2.  A product
+  // then folds its two high coefficients with 2 multiplications (by p) instead of 6.  nice == 0: the
+  // reference polynomial (xpwr3/xpwr4 rows).  xpowq / xpowq2 hold the values of the basis in use.
+  uint32_t nice;
+  uint32_t pad[2];
+  uint32_t pcoef[kNS];             // p
+  uint32_t bs[kNS], bs2[kNS], b2s[kNS];          // s, s^2, 2 s
+  uint32_t blam[kNS], blam2[kNS], blami[kNS], blami2[kNS];   // lam, lam^2, 1/lam, 1/lam^2
 };
 __constant__ DConsts c_d;
 
@@ -64,10 +72,21 @@ __device__ __forceinline__ void f3_scale(F3& r, const F3& x, const Fq& k) {
   for (int i = 0; i < 3; i++) fq_mul(r.c[i], x.c[i], k);
 }
 
-// degree-4 product d0..d4 folded with the x^3, x^4 rows (polymod_mul_degree3, arith/poly.c:870-930)
+// degree-4 product d0..d4 folded with the x^3, x^4 rows (polymod_mul_degree3, arith/poly.c:870-930);
+// internal basis: w^3 = -p w - 1, w^4 = -p w^2 - w:  r0 = d0 - d3, r1 = d1 - p d3 - d4, r2 = d2 - p d4
 __device__ __forceinline__ void f3_reduce(F3* r, const Fq& d0, const Fq& d1, const Fq& d2, const Fq& d3,
                                           const Fq& d4) {
   Fq t, k;
+  if (c_d.nice) {
+    fq_set(k, c_d.pcoef);
+    fq_sub(r->c[0], d0, d3);
+    fq_mul_hot(t, d3, k);
+    fq_sub(r->c[1], d1, t);
+    fq_sub(r->c[1], r->c[1], d4);
+    fq_mul_hot(t, d4, k);
+    fq_sub(r->c[2], d2, t);
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     const Fq& lo = i == 0 ? d0 : (i == 1 ? d1 : d2);
@@ -78,6 +97,42 @@ __device__ __forceinline__ void f3_reduce(F3* r, const Fq& d0, const Fq& d1, con
     fq_mul_hot(t, d4, k);
     fq_add(r->c[i], r->c[i], t);
   }
+}
+// reference basis -> basis in use:  b0 = a0 - a1 s + a2 s^2,  b1 = lam (a1 - 2 s a2),  b2 = lam^2 a2
+__device__ __noinline__ void f3_to_internal(F3& v) {
+  Fq k, t, u;
+  if (!c_d.nice) return;
+  fq_set(k, c_d.bs);
+  fq_mul(t, v.c[1], k);
+  fq_sub(v.c[0], v.c[0], t);
+  fq_set(k, c_d.bs2);
+  fq_mul(t, v.c[2], k);
+  fq_add(v.c[0], v.c[0], t);
+  fq_set(k, c_d.b2s);
+  fq_mul(t, v.c[2], k);
+  fq_sub(u, v.c[1], t);
+  fq_set(k, c_d.blam);
+  fq_mul(v.c[1], u, k);
+  fq_set(k, c_d.blam2);
+  fq_mul(v.c[2], v.c[2], k);
+}
+// basis in use -> reference basis:  a2 = b2 / lam^2,  a1 = b1 / lam + 2 s a2,  a0 = b0 + a1 s - a2 s^2
+__device__ __noinline__ void f3_to_reference(F3& v) {
+  Fq k, t;
+  if (!c_d.nice) return;
+  fq_set(k, c_d.blami2);
+  fq_mul(v.c[2], v.c[2], k);
+  fq_set(k, c_d.blami);
+  fq_mul(v.c[1], v.c[1], k);
+  fq_set(k, c_d.b2s);
+  fq_mul(t, v.c[2], k);
+  fq_add(v.c[1], v.c[1], t);
+  fq_set(k, c_d.bs);
+  fq_mul(t, v.c[1], k);
+  fq_add(v.c[0], v.c[0], t);
+  fq_set(k, c_d.bs2);
+  fq_mul(t, v.c[2], k);
+  fq_sub(v.c[0], v.c[0], t);
 }
 __device__ __noinline__ void f3_mul(F3* r, const F3* x, const F3* y) {
   Fq d0, d1, d2, d3, d4, m1, s, t;
@@ -246,7 +301,10 @@ k_d_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_
     fq_from_wire(ctx.Qx.c[i], q + i * kWS);
     fq_from_wire(ctx.Qy.c[i], q + (3 + i) * kWS);
   }
-  // Y^2 == X^3 + (a v^2) X + b v^3 over F_q^3 (ecc/curve.c:57-76)
+  f3_to_internal(ctx.Qx);
+  f3_to_internal(ctx.Qy);
+  // Y^2 == X^3 + (a v^2) X + b v^3 over F_q^3 (ecc/curve.c:57-76; the coefficients lie in F_q, so
+  // the identity holds in either basis)
   f3_sqr(&t, &ctx.Qx);
   fq_set(k, c_d.twist_a);
   fq_add(t.c[0], t.c[0], k);
@@ -347,6 +405,8 @@ k_d_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
   if (flag[idx]) {
     f6d_ld_global(f, mv, n, idx);
     f6d_final_exp(out0, out1, f);
+    f3_to_reference(out0);
+    f3_to_reference(out1);
   } else {
     f3_zero(out0);
     f3_zero(out1);
@@ -384,6 +444,7 @@ __global__ void k_d_tower_op(int op, uint8_t* __restrict__ out, const uint8_t* _
   F6D x, y, r;
   f6d_from_wire(x, a + idx * (6 * kWS));
   f6d_from_wire(y, b + idx * (6 * kWS));
+  f3_to_internal(x.a); f3_to_internal(x.b); f3_to_internal(y.a); f3_to_internal(y.b);
   switch (op) {
     case 0: f6d_mul(&r, &x, &y); break;
     case 1: r = x; f6d_sqr(&r); break;
@@ -392,6 +453,7 @@ __global__ void k_d_tower_op(int op, uint8_t* __restrict__ out, const uint8_t* _
     case 5: f3_mul(&r.a, &x.a, &y.a); f3_zero(r.b); break;
     default: f3_inv(&r.a, &x.a); f3_zero(r.b); break;
   }
+  f3_to_reference(r.a); f3_to_reference(r.b);
   f6d_to_wire(out + idx * (6 * kWS), r);
 }
 

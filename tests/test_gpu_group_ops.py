@@ -10,7 +10,8 @@ from pbc_b200.params import PARAMS
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = {"a": ("a", ""), "f": ("f", ""), "f_refbasis": ("f", "b200_reference_basis 1\n"), "d159": ("d159", "")}
+VARIANTS = {"a": ("a", ""), "f": ("f", ""), "f_refbasis": ("f", "b200_reference_basis 1\n"), "d159": ("d159", ""),
+            "d159_refbasis": ("d159", "b200_reference_basis 1\n")}
 
 
 @pytest.fixture(scope="module", params=sorted(VARIANTS))

@@ -28,10 +28,11 @@ def f_env(request):
     return Pairing(PARAMS["f"] + extra), O.pairing_from_param(PARAMS["f"])
 
 
-@pytest.fixture(scope="module")
-def d_env():
+@pytest.fixture(scope="module", params=["internal_basis", "reference_basis"])
+def d_env(request):
     from pbc_b200.pairing import Pairing
-    return Pairing(PARAMS["d159"]), O.pairing_from_param(PARAMS["d159"])
+    extra = "" if request.param == "internal_basis" else "b200_reference_basis 1\n"
+    return Pairing(PARAMS["d159"] + extra), O.pairing_from_param(PARAMS["d159"])
 
 
 def _f12(e):

@@ -146,3 +146,24 @@ def test_internal_basis_constants_match_prototype(built):
         for i in range(1, 6):
             want.extend(K.pow(g, i))
         assert f.derived_constant("frob%d" % k, 20) == want
+
+
+def test_internal_cubic_basis_constants_match_prototype(built):
+    """s, lam, p of the Type D internal cubic w^3 + p w + 1 (engine.cu init_type_d) vs the executable
+    specification tools/proto_d_basis.py; the Frobenius constant x^q is re-derived in that basis."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from proto_d_basis import find_basis
+    from pbc_b200.params import PARAMS
+    from oracle import pbc_oracle as O
+    od = O.pairing_from_param(PARAMS["d159"])
+    q = od.q
+    B = find_basis(q, *od.Fq3.low)
+    d = built.Pairing(PARAMS["d159"])
+    assert d.derived_constant("basis_cubic", 20) == [B["s"], B["lam"], B["p"]]
+    F3n = O.PolyModExt(od.Fq, [1, B["p"], 0])
+    assert tuple(d.derived_constant("xpowq_in_use", 20)) == F3n.pow((0, 1, 0), q)
+    ref = built.Pairing(PARAMS["d159"] + "b200_reference_basis 1\n")
+    assert tuple(ref.derived_constant("xpowq_in_use", 20)) == od.xpowq
+    with pytest.raises(built.PairingError):
+        ref.derived_constant("basis_cubic", 20)
