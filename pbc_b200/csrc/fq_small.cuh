@@ -66,9 +66,9 @@ __device__ __forceinline__ void fq_sqr(Fq& r, const Fq& a) { mont_sqr_ps<kNS, fa
 #ifndef PBC_FQ_ADD_CALL
 #define PBC_FQ_ADD_CALL 0
 #endif
-#if PBC_FQ_ADD_CALL
 __device__ __noinline__ Fq fq_add_call(Fq a, Fq b) { Fq r; fp_add<kNS, false>(r.v, a.v, b.v); return r; }
 __device__ __noinline__ Fq fq_sub_call(Fq a, Fq b) { Fq r; fp_sub<kNS>(r.v, a.v, b.v); return r; }
+#if PBC_FQ_ADD_CALL
 __device__ __forceinline__ void fq_add(Fq& r, const Fq& a, const Fq& b) { r = fq_add_call(a, b); }
 __device__ __forceinline__ void fq_sub(Fq& r, const Fq& a, const Fq& b) { r = fq_sub_call(a, b); }
 __device__ __forceinline__ void fq_dbl(Fq& r, const Fq& a) { r = fq_add_call(a, a); }
@@ -142,6 +142,21 @@ __device__ __noinline__ Fq fq_redc_call(FqW t) {
   bool use_d = v0 != 0 || borrow == 0;
 #pragma unroll
   for (int k = 0; k < kNS; k++) r.v[k] = use_d ? d[k] : o[k];
+  return r;
+}
+// the same for t < 2 q R (sums of several double-width terms): the quotient is below 3q, two
+// conditional subtractions
+__device__ __noinline__ Fq fq_redc2_call(FqW t) {
+  Fq r = fq_redc_call(t);
+  // fq_redc_call subtracted q once if the value was >= q (or overflowed a limb); one more may be due.
+  // It cannot tell 2q <= x < 3q from q <= x < 2q by itself, so repeat the comparison here.
+  uint32_t d[kNS], borrow;
+  PBC_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(d[0]) : "r"(r.v[0]), "r"(c_fp.p[0]));
+#pragma unroll
+  for (int k = 1; k < kNS; k++) PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(d[k]) : "r"(r.v[k]), "r"(c_fp.p[k]));
+  PBC_ASM("subc.u32 %0, 0, 0;" : "=r"(borrow));
+#pragma unroll
+  for (int k = 0; k < kNS; k++) r.v[k] = borrow == 0 ? d[k] : r.v[k];
   return r;
 }
 __device__ __forceinline__ void fqw_add(FqW& r, const FqW& a, const FqW& b) {

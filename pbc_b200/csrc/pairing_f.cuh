@@ -59,8 +59,21 @@ __constant__ FConsts c_f;
 // F_q^2  (arith/fieldquadratic.c:197-309 fq_*)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void f2_set(F2& r, const uint32_t c[2][kNS]) { fq_set(r.a, c[0]); fq_set(r.b, c[1]); }
+// PBC_F2_ADD_CALL = 1: one out-of-line copy of the F_q^2 addition and subtraction (the tower routines
+// contain dozens of them; inlined they make up most of f6_mul / f12_sqr and the kernels are
+// instruction-fetch bound at full occupancy: ncu stall_no_instruction 2.7 per issue)
+#ifndef PBC_F2_ADD_CALL
+#define PBC_F2_ADD_CALL 1
+#endif
+#if PBC_F2_ADD_CALL
+__device__ __noinline__ void f2_add_call(F2* r, const F2* x, const F2* y) { fq_add(r->a, x->a, y->a); fq_add(r->b, x->b, y->b); }
+__device__ __noinline__ void f2_sub_call(F2* r, const F2* x, const F2* y) { fq_sub(r->a, x->a, y->a); fq_sub(r->b, x->b, y->b); }
+__device__ __forceinline__ void f2_add(F2& r, const F2& x, const F2& y) { f2_add_call(&r, &x, &y); }
+__device__ __forceinline__ void f2_sub(F2& r, const F2& x, const F2& y) { f2_sub_call(&r, &x, &y); }
+#else
 __device__ __forceinline__ void f2_add(F2& r, const F2& x, const F2& y) { fq_add(r.a, x.a, y.a); fq_add(r.b, x.b, y.b); }
 __device__ __forceinline__ void f2_sub(F2& r, const F2& x, const F2& y) { fq_sub(r.a, x.a, y.a); fq_sub(r.b, x.b, y.b); }
+#endif
 __device__ __forceinline__ void f2_dbl(F2& r, const F2& x) { fq_dbl(r.a, x.a); fq_dbl(r.b, x.b); }
 __device__ __forceinline__ void f2_neg(F2& r, const F2& x) { fq_neg(r.a, x.a); fq_neg(r.b, x.b); }
 __device__ __forceinline__ void f2_zero(F2& r) { fq_zero(r.a); fq_zero(r.b); }
@@ -327,20 +340,56 @@ __device__ __noinline__ void f12_inv(F12* r, const F12* p) {
 
 // v *= c + L3 x^3 + L4 x^4, c in F_q (the Miller line, ecc/f_param.c:109-149)
 //   out_k = c v_k + L3 v_{k-3} + L4 v_{k-4}, indices mod 6, a wrap multiplies by xi
+// double-width x y for F_q^2 operands in the internal basis (i^2 = -1), added into (re, im):
+//   re += x0 y0 - x1 y1 + q^2,  im += (x0 + x1)(y0 + y1) - x0 y0 - x1 y1       (each term < 2 q^2)
+__device__ __forceinline__ void f2_mulw_acc(FqW& re, FqW& im, const F2& x, const F2& y, const FqW& qq, bool first) {
+  Fq sx, sy;
+  FqW t0, t1, t2;
+  fq_add_nr(sx, x.a, x.b);
+  fq_add_nr(sy, y.a, y.b);
+  t0 = fq_mulw_call(x.a, y.a);
+  t1 = fq_mulw_call(x.b, y.b);
+  t2 = fq_mulw_call(sx, sy);
+  fqw_sub(t2, t2, t0);
+  fqw_sub(t2, t2, t1);
+  fqw_add(t0, t0, qq);
+  fqw_sub(t0, t0, t1);
+  if (first) { re = t0; im = t2; } else { fqw_add(re, re, t0); fqw_add(im, im, t2); }
+}
 __device__ __noinline__ void f12_mul_line(F12* v, const Fq* c, const F2* L3, const F2* L4) {
   // m3[0] = xi L3 (used when the product wraps past x^5), m3[1] = L3; same for L4.  (Indexing an
   // array instead of selecting between two pointers: nvcc 12.9 merged the stack slots of two live
   // temporaries when the operand pointer came from a select -- see tests/test_gpu_towers.py op 4.)
-  F2 m3[2], m4[2];
+  F2 m3[2], m4[2], t, u, w;
   F12 o;
+  FqW re, im, qq, sc;
   m3[1] = *L3;
   m4[1] = *L4;
   f2_mul_xi(m3[0], m3[1]);
   f2_mul_xi(m4[0], m4[1]);
+  if (PBC_F2_LAZY && c_f.nice) {
+    // every output coefficient is the sum of three products: accumulate them unreduced and reduce
+    // once (5 q^2 < 2 q R: fq_redc2) -- 12 reductions per line instead of 36
+#pragma unroll
+    for (int k = 0; k < 2 * kNS; k++) qq.v[k] = c_f.qsq[k];
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {
+      int i3 = k >= 3 ? k - 3 : k + 3, i4 = k >= 4 ? k - 4 : k + 2;
+      f2_mulw_acc(re, im, m3[k >= 3 ? 1 : 0], v->c[i3], qq, true);
+      f2_mulw_acc(re, im, m4[k >= 4 ? 1 : 0], v->c[i4], qq, false);
+      sc = fq_mulw_call(*c, v->c[k].a);
+      fqw_add(re, re, sc);
+      sc = fq_mulw_call(*c, v->c[k].b);
+      fqw_add(im, im, sc);
+      o.c[k].a = fq_redc2_call(re);
+      o.c[k].b = fq_redc2_call(im);
+    }
+    *v = o;
+    return;
+  }
 #pragma unroll 1
   for (int k = 0; k < 6; k++) {
     int i3 = k >= 3 ? k - 3 : k + 3, i4 = k >= 4 ? k - 4 : k + 2;
-    F2 t, u, w;
     f2_mul(&t, &m3[k >= 3 ? 1 : 0], &v->c[i3]);
     f2_mul(&u, &m4[k >= 4 ? 1 : 0], &v->c[i4]);
     f2_scale(w, v->c[k], *c);
