@@ -126,6 +126,7 @@ static constexpr int kBlockMiller = 128;
 static constexpr int kBlockFinal = 128;
 static constexpr int kBlockInv = 128;
 static constexpr int kBlockCC = 128;           // types f, d: threads per block
+static constexpr int kBlockCCMiller = PBC_CC_MILLER_BLOCK;   // ... of the Miller kernels (lock-step barrier)
 
 // The three reference operations that reach the GPU (include/pbc_pairing.h:141-171, :54-89).
 enum Mode { kSingle = 0, kProd = 1, kPP = 2 };
@@ -655,10 +656,10 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
     uint32_t* mv = (uint32_t*)ws;                // [W][m]
     uint32_t* flag = mv + W * m;                 // [m]
     size_t stride1 = job.mode == kPP ? 0 : (size_t)p->g1_len;
-    unsigned gm = (unsigned)((m + kBlockCC - 1) / kBlockCC);
+    unsigned gm = (unsigned)((m + kBlockCCMiller - 1) / kBlockCCMiller);
     STAGE(0);
-    if (isf) k_f_miller<kBlockCC><<<gm, kBlockCC, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1);
-    else k_d_miller<kBlockCC><<<gm, kBlockCC, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1);
+    if (isf) k_f_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1);
+    else k_d_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1);
     LAUNCHED();
     STAGE(1);
     if (job.mode == kProd) {
@@ -672,7 +673,8 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
     }
     STAGE(2);
     unsigned gf = (unsigned)((n + kBlockCC - 1) / kBlockCC);
-    if (isf) k_f_finalexp<kBlockCC><<<gf, kBlockCC, 0, st>>>(mv, flag, d_out, n);
+    unsigned gfm = (unsigned)((n + kBlockCCMiller - 1) / kBlockCCMiller);
+    if (isf) k_f_finalexp<kBlockCCMiller><<<gfm, kBlockCCMiller, 0, st>>>(mv, flag, d_out, n);
     else k_d_finalexp<kBlockCC><<<gf, kBlockCC, 0, st>>>(mv, flag, d_out, n);
     LAUNCHED();
     STAGE(3);

@@ -21,6 +21,16 @@
 #define PBC_CC_MINBLOCKS 4
 #endif
 
+// PBC_CC_LOCKSTEP = 1: a block-wide barrier at the top of every Miller iteration keeps the warps of a
+// block in the same code region (the loop over the bits of r is uniform across pairings), so they
+// share instruction-cache lines; needs every thread of the block inside the loop.
+#ifndef PBC_CC_LOCKSTEP
+#define PBC_CC_LOCKSTEP 1
+#endif
+#ifndef PBC_CC_MILLER_BLOCK
+#define PBC_CC_MILLER_BLOCK 256
+#endif
+
 namespace pbcb200 {
 
 struct CCConsts {
@@ -66,6 +76,7 @@ __device__ __forceinline__ void miller_cc(typename T::Acc* v, const Fq& xP, cons
   fq_one(Z);
   int m = (int)c_cc.rbits - 2;
   for (;;) {
+    if (PBC_CC_LOCKSTEP) __syncthreads();
     // ---- tangent at V ----
     fq_sqr(Z2, Z);
     fq_sqr(t, X);
@@ -118,6 +129,7 @@ __device__ __forceinline__ void miller_cc(typename T::Acc* v, const Fq& xP, cons
       fq_mul(t, t, X);
       fq_mul(u, xP, Y);
       mc_sub(c, t, u);                     // c = yP Z X - xP Y
+      if (PBC_CC_LOCKSTEP >= 2) __syncthreads();
       T::mul_line(v, &a, &b, &c, ctx);
       fq_sqr(t, H);                        // H^2
       fq_mul(u, t, H);                     // H^3
@@ -133,6 +145,7 @@ __device__ __forceinline__ void miller_cc(typename T::Acc* v, const Fq& xP, cons
       Z = b;
     }
     m--;
+    if (PBC_CC_LOCKSTEP >= 2) __syncthreads();
     T::sqr(v);
   }
 }

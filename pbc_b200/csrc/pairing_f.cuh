@@ -456,11 +456,12 @@ __device__ __noinline__ void f12_to_internal(F12& v) {
 // P: n1 x 40 bytes (stride1 = 0 shares one P: pairing_pp_*), Q: n x 80 bytes.
 // mv: [60][n] words, flag[n]: 1 = both inputs finite points on their curves.
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, PBC_CC_MINBLOCKS)
+__global__ void __launch_bounds__(BLOCK, (PBC_CC_MINBLOCKS * 128) / BLOCK)
 k_f_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_t* __restrict__ mv,
            uint32_t* __restrict__ flag, size_t n, size_t stride1) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (idx >= n) return;
+  const bool live = idx < n;      // every thread runs the loop (block-wide barrier inside)
+  if (!live) idx = 0;
   Fq xP, yP, yP2;
   const uint8_t* p = P + idx * stride1;
   fq_from_wire(xP, p);
@@ -489,7 +490,9 @@ k_f_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_
   f2_mul(&ctx.Qx, &ctx.Qx, f2_const(c_f.kx));
   f2_mul(&ctx.Qy, &ctx.Qy, f2_const(c_f.ky));
   f12_one(v);
-  if (ok) miller_cc<FTower>(&v, xP, yP, &ctx);
+  miller_cc<FTower>(&v, xP, yP, &ctx);   // off-curve inputs run too (total arithmetic) and are flagged
+  if (!live) return;
+  if (!ok) f12_one(v);
   f12_st_global(mv, n, idx, v);
   flag[idx] = ok ? 1u : 0u;
 }
@@ -586,6 +589,7 @@ __device__ __noinline__ void f12_pow_u(F12& r, const F12& f) {
   F12 acc;
   acc = f;
   for (int j = (int)c_f.u_bits - 2; j >= 0; j--) {
+    if (PBC_CC_LOCKSTEP) __syncthreads();        // uniform loop: keep the block's warps in step
     f12_cyc_sqr(&acc);
     if ((c_f.u_abs[j >> 5] >> (j & 31)) & 1u) f12_mul(&acc, &acc, &f);
   }
@@ -653,19 +657,20 @@ __device__ __noinline__ void f12_final_exp(F12& acc, F12& f) {
 // inversion, then the 472-bit power (q^4 - q^2 + 1)/r.  out: n x 240 bytes, coefficient order
 // x^0..x^5, each (re, im) (arith/poly.c:718-727, arith/fieldquadratic.c:323-329).
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, PBC_CC_MINBLOCKS)
+__global__ void __launch_bounds__(BLOCK, (PBC_CC_MINBLOCKS * 128) / BLOCK)
 k_f_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
              uint8_t* __restrict__ out, size_t n) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (idx >= n) return;
   F12 f, acc;
-  if (flag[idx]) {
-    f12_ld_global(f, mv, n, idx);
-    f12_final_exp(acc, f);
-    f12_to_reference(acc);
-  } else {
-    f12_one(acc);
-  }
+  const bool ok = flag[idx] != 0;
+  // every thread runs the exponentiation (block-wide barriers inside f12_pow_u); flagged-off
+  // entries exponentiate 1 and are overwritten with the identity afterwards
+  f12_ld_global(f, mv, n, idx);
+  if (!ok) f12_one(f);
+  f12_final_exp(acc, f);
+  f12_to_reference(acc);
+  if (!ok) f12_one(acc);
   uint8_t* o = out + idx * (12 * kWS);
 #pragma unroll 1
   for (int i = 0; i < 6; i++) {
