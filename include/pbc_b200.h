@@ -17,6 +17,12 @@
  *   - every output is bit-identical to the reference CPU path.
  * There is no CPU fallback: without a CUDA device every compute entry point fails.
  *
+ * Threading: like the reference (which is not thread-safe) a handle is used by one thread
+ * at a time; calls on DIFFERENT handles may come from different threads -- the blocking host-buffer
+ * entry points serialise per device (the curve constants of one handle at a time are resident in
+ * __constant__ memory).  With the asynchronous _device entry points keep one handle active per
+ * device until its stream has drained.
+ *
  * Return convention: 0 on success, non-zero on failure (pairing_init_set_buf returns 1 on
  * failure, ecc/pairing.c:88-98); pbc_b200_last_error() gives the message the reference would
  * have sent to pbc_error().

@@ -120,6 +120,12 @@ struct pbc_b200_pairing_s {
 static std::atomic<uint64_t> g_next_id{1};
 static std::mutex g_const_mu;
 static std::map<int, uint64_t> g_const_owner;   // device -> handle id whose constants are resident
+// The curve constants live in __constant__ memory, one set per device at a time.  Blocking (host
+// buffer) calls hold the device's lock from the constant check to their final synchronise, so calls
+// on different handles from different threads serialise per device instead of racing on the
+// constants.  The asynchronous _device entry points cannot hold it across the caller's stream: use
+// one handle per device at a time there (documented in include/pbc_b200.h).
+static std::mutex g_dev_mu[64];
 
 static constexpr size_t kChunk = 1u << 18;      // pairings per pipeline chunk (host API)
 static constexpr int kBlockMiller = 128;
@@ -690,6 +696,7 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
 // ------------------------------------------------------------------------------------------
 static int run_slice(pbc_b200_pairing_s* p, int dev, const Job& job, unsigned char* out,
                      const unsigned char* in1, const unsigned char* in2, size_t n) {
+  std::lock_guard<std::mutex> dev_lock(g_dev_mu[dev & 63]);
   if (ctx_prepare(p, dev)) return 1;
   DevCtx& c = p->ctx[dev];
   size_t per_out = job.mode == kProd ? job.k : 1;
@@ -1033,6 +1040,8 @@ static int run_group(pbc_b200_pairing_s* p, int which, unsigned char* out, const
   std::lock_guard<std::mutex> lk(p->mu);
   int dev = 0;
   CUDA_OK(cudaGetDevice(&dev));
+  std::unique_lock<std::mutex> dev_lock(g_dev_mu[dev & 63], std::defer_lock);
+  if (!device) dev_lock.lock();
   if (ctx_prepare(p, dev)) return 1;
   DevCtx& c = p->ctx[dev];
   size_t elen = which == 0 ? (size_t)p->g1_len : (which == 2 ? (size_t)p->g2_len : (size_t)p->gt_len);
@@ -1098,6 +1107,8 @@ static int run_from_hash(pbc_b200_pairing_s* p, unsigned char* out, const unsign
   std::lock_guard<std::mutex> lk(p->mu);
   int dev = 0;
   CUDA_OK(cudaGetDevice(&dev));
+  std::unique_lock<std::mutex> dev_lock(g_dev_mu[dev & 63], std::defer_lock);
+  if (!device) dev_lock.lock();
   if (ctx_prepare(p, dev)) return 1;
   DevCtx& c = p->ctx[dev];
   size_t elen = (size_t)p->g1_len;
@@ -1162,6 +1173,7 @@ extern "C" int pbc_b200_g1_from_bytes_compressed(pbc_b200_pairing_t* p, unsigned
   std::lock_guard<std::mutex> lk(p->mu);
   int dev = 0;
   CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> dev_lock(g_dev_mu[dev & 63]);
   if (ctx_prepare(p, dev)) return 1;
   DevCtx& c = p->ctx[dev];
   size_t clen = (size_t)p->g1_len / 2 + 1, elen = (size_t)p->g1_len, need = n * (clen + elen) + 16;
