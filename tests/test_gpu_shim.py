@@ -53,3 +53,12 @@ def test_plain_c_caller_of_the_c_abi(tmp_path, name, golden):
                         str(tmp_path / "E.bin")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert (tmp_path / "E.bin").read_bytes() == b"".join(bytes.fromhex(x) for x in g["e"])
+
+
+@pytest.mark.parametrize("name", ["a", "f", "d159"])
+def test_bls_batch_verify_example(name):
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "bls_batch_verify.py"), name, "96"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert '"rejected": [48]' in r.stdout
