@@ -277,69 +277,62 @@ __device__ __noinline__ void f6_inv(F6* r, const F6* a) {
 // ---------------------------------------------------------------------------------------------
 // F_q^12 = F_q^6[x]/(x^2 - y): even coefficients = real half, odd = imaginary half
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void f12_split(F6& re, F6& im, const F12& v) {
-#pragma unroll
-  for (int i = 0; i < 3; i++) { re.c[i] = v.c[2 * i]; im.c[i] = v.c[2 * i + 1]; }
-}
-__device__ __forceinline__ void f12_join(F12& v, const F6& re, const F6& im) {
-#pragma unroll
-  for (int i = 0; i < 3; i++) { v.c[2 * i] = re.c[i]; v.c[2 * i + 1] = im.c[i]; }
-}
+// Storage order: the three even coefficients (the "real" F_q^6 half) first, then the three odd ones, so
+// both halves are F6 objects in place and no routine copies them around:
+//   coefficient j of x^j lives at c[f12_pos(j)],  f12_pos = 0 3 1 4 2 5.
+__device__ __forceinline__ constexpr int f12_pos(int j) { return (j >> 1) + 3 * (j & 1); }
+#define F12C(v, j) ((v).c[f12_pos(j)])
+__device__ __forceinline__ F6* f12_lo(F12* v) { return reinterpret_cast<F6*>(&v->c[0]); }
+__device__ __forceinline__ F6* f12_hi(F12* v) { return reinterpret_cast<F6*>(&v->c[3]); }
+__device__ __forceinline__ const F6* f12_lo(const F12* v) { return reinterpret_cast<const F6*>(&v->c[0]); }
+__device__ __forceinline__ const F6* f12_hi(const F12* v) { return reinterpret_cast<const F6*>(&v->c[3]); }
 __device__ __forceinline__ void f12_one(F12& v) {
 #pragma unroll
   for (int i = 0; i < 6; i++) f2_zero(v.c[i]);
   fq_one(v.c[0].a);
 }
 
-// (A + B x)(C + D x) = AC + y BD + ((A + B)(C + D) - AC - BD) x
+// (A + B x)(C + D x) = AC + y BD + ((A + B)(C + D) - AC - BD) x;  r may alias p or q
 __device__ __noinline__ void f12_mul(F12* r, const F12* p, const F12* q) {
-  F6 A, B, C, D, t0, t1, t2;
-  f12_split(A, B, *p);
-  f12_split(C, D, *q);
-  f6_mul(&t0, &A, &C);
-  f6_mul(&t1, &B, &D);
-  f6_add(A, A, B);
-  f6_add(C, C, D);
-  f6_mul(&t2, &A, &C);
+  F6 t0, t1, t2, s1, s2;
+  f6_mul(&t0, f12_lo(p), f12_lo(q));
+  f6_mul(&t1, f12_hi(p), f12_hi(q));
+  f6_add(s1, *f12_lo(p), *f12_hi(p));
+  f6_add(s2, *f12_lo(q), *f12_hi(q));
+  f6_mul(&t2, &s1, &s2);
   f6_sub(t2, t2, t0);
   f6_sub(t2, t2, t1);
   f6_mul_y(t1, t1);
-  f6_add(t0, t0, t1);
-  f12_join(*r, t0, t2);
+  f6_add(*f12_lo(r), t0, t1);
+  *f12_hi(r) = t2;
 }
-// (A + B x)^2 = (A + B)(A + y B) - AB - y AB + 2 AB x
+// (A + B x)^2 = (A + B)(A + y B) - AB - y AB + 2 AB x, in place
 __device__ __noinline__ void f12_sqr(F12* v) {
-  F6 A, B, t0, t1, t2;
-  f12_split(A, B, *v);
-  f6_mul(&t0, &A, &B);
-  f6_mul_y(t1, B);
-  f6_add(t1, t1, A);
-  f6_add(A, A, B);
-  f6_mul(&t2, &A, &t1);
+  F6 t0, t1, t2;
+  f6_mul(&t0, f12_lo(v), f12_hi(v));
+  f6_mul_y(t1, *f12_hi(v));
+  f6_add(t1, t1, *f12_lo(v));
+  f6_add(t2, *f12_lo(v), *f12_hi(v));
+  f6_mul(&t2, &t2, &t1);
   f6_sub(t2, t2, t0);
   f6_mul_y(t1, t0);
-  f6_sub(t2, t2, t1);
-  f6_add(t0, t0, t0);
-  f12_join(*v, t2, t0);
+  f6_sub(*f12_lo(v), t2, t1);
+  f6_add(*f12_hi(v), t0, t0);
 }
-// 1/(A + B x) = (A - B x)/(A^2 - y B^2)
+// 1/(A + B x) = (A - B x)/(A^2 - y B^2);  r may alias p
 __device__ __noinline__ void f12_inv(F12* r, const F12* p) {
-  F6 A, B, t0, t1;
-  f12_split(A, B, *p);
-  f6_mul(&t0, &A, &A);
-  f6_mul(&t1, &B, &B);
+  F6 t0, t1;
+  f6_mul(&t0, f12_lo(p), f12_lo(p));
+  f6_mul(&t1, f12_hi(p), f12_hi(p));
   f6_mul_y(t1, t1);
   f6_sub(t0, t0, t1);
   f6_inv(&t0, &t0);
-  f6_mul(&A, &A, &t0);
-  f6_mul(&B, &B, &t0);
+  f6_mul(&t1, f12_hi(p), &t0);
+  f6_mul(f12_lo(r), f12_lo(p), &t0);
 #pragma unroll
-  for (int i = 0; i < 3; i++) f2_neg(B.c[i], B.c[i]);
-  f12_join(*r, A, B);
+  for (int i = 0; i < 3; i++) f2_neg(f12_hi(r)->c[i], t1.c[i]);
 }
 
-// v *= c + L3 x^3 + L4 x^4, c in F_q (the Miller line, ecc/f_param.c:109-149)
-//   out_k = c v_k + L3 v_{k-3} + L4 v_{k-4}, indices mod 6, a wrap multiplies by xi
 // double-width x y for F_q^2 operands in the internal basis (i^2 = -1), added into (re, im):
 //   re += x0 y0 - x1 y1 + q^2,  im += (x0 + x1)(y0 + y1) - x0 y0 - x1 y1       (each term < 2 q^2)
 __device__ __forceinline__ void f2_mulw_acc(FqW& re, FqW& im, const F2& x, const F2& y, const FqW& qq, bool first) {
@@ -375,14 +368,14 @@ __device__ __noinline__ void f12_mul_line(F12* v, const Fq* c, const F2* L3, con
 #pragma unroll 1
     for (int k = 0; k < 6; k++) {
       int i3 = k >= 3 ? k - 3 : k + 3, i4 = k >= 4 ? k - 4 : k + 2;
-      f2_mulw_acc(re, im, m3[k >= 3 ? 1 : 0], v->c[i3], qq, true);
-      f2_mulw_acc(re, im, m4[k >= 4 ? 1 : 0], v->c[i4], qq, false);
-      sc = fq_mulw_call(*c, v->c[k].a);
+      f2_mulw_acc(re, im, m3[k >= 3 ? 1 : 0], F12C(*v, i3), qq, true);
+      f2_mulw_acc(re, im, m4[k >= 4 ? 1 : 0], F12C(*v, i4), qq, false);
+      sc = fq_mulw_call(*c, F12C(*v, k).a);
       fqw_add(re, re, sc);
-      sc = fq_mulw_call(*c, v->c[k].b);
+      sc = fq_mulw_call(*c, F12C(*v, k).b);
       fqw_add(im, im, sc);
-      o.c[k].a = fq_redc2_call(re);
-      o.c[k].b = fq_redc2_call(im);
+      F12C(o, k).a = fq_redc2_call(re);
+      F12C(o, k).b = fq_redc2_call(im);
     }
     *v = o;
     return;
@@ -390,11 +383,11 @@ __device__ __noinline__ void f12_mul_line(F12* v, const Fq* c, const F2* L3, con
 #pragma unroll 1
   for (int k = 0; k < 6; k++) {
     int i3 = k >= 3 ? k - 3 : k + 3, i4 = k >= 4 ? k - 4 : k + 2;
-    f2_mul(&t, &m3[k >= 3 ? 1 : 0], &v->c[i3]);
-    f2_mul(&u, &m4[k >= 4 ? 1 : 0], &v->c[i4]);
-    f2_scale(w, v->c[k], *c);
+    f2_mul(&t, &m3[k >= 3 ? 1 : 0], &F12C(*v, i3));
+    f2_mul(&u, &m4[k >= 4 ? 1 : 0], &F12C(*v, i4));
+    f2_scale(w, F12C(*v, k), *c);
     f2_add(t, t, u);
-    f2_add(o.c[k], t, w);
+    f2_add(F12C(o, k), t, w);
   }
   *v = o;
 }
@@ -437,7 +430,7 @@ __device__ __noinline__ void f12_to_reference(F12& v) {
   Fq k;
   if (!c_f.nice) return;
 #pragma unroll 1
-  for (int j = 1; j < 6; j++) f2_mul(&v.c[j], &v.c[j], f2_const(c_f.tau_inv[j - 1]));
+  for (int j = 1; j < 6; j++) f2_mul(&F12C(v, j), &F12C(v, j), f2_const(c_f.tau_inv[j - 1]));
   fq_set(k, c_f.sigma_inv);
 #pragma unroll 1
   for (int j = 0; j < 6; j++) fq_mul(v.c[j].b, v.c[j].b, k);
@@ -450,7 +443,7 @@ __device__ __noinline__ void f12_to_internal(F12& v) {
 #pragma unroll 1
   for (int j = 0; j < 6; j++) fq_mul(v.c[j].b, v.c[j].b, k);
 #pragma unroll 1
-  for (int j = 1; j < 6; j++) f2_mul(&v.c[j], &v.c[j], f2_const(c_f.tau[j - 1]));
+  for (int j = 1; j < 6; j++) f2_mul(&F12C(v, j), &F12C(v, j), f2_const(c_f.tau[j - 1]));
 }
 
 // P: n1 x 40 bytes (stride1 = 0 shares one P: pairing_pp_*), Q: n x 80 bytes.
@@ -520,24 +513,12 @@ k_f_prod(const uint32_t* __restrict__ mv_in, const uint32_t* __restrict__ flag_i
   flag_out[idx] = ok ? 1u : 0u;
 }
 
-// coefficient i scaled by e^i (ecc/f_param.c:257-268 qpower)
-__device__ __noinline__ void f12_qpower(F12& r, const F12& f, const uint32_t e[2][kNS]) {
-  F2 ep;
-  const F2* e1 = f2_const(e);
-  ep = *e1;
-  r.c[0] = f.c[0];
-#pragma unroll 1
-  for (int i = 1; i < 6; i++) {
-    f2_mul(&r.c[i], &f.c[i], &ep);
-    if (i < 5) f2_mul(&ep, &ep, e1);
-  }
-}
-
 // f^(q^6): x -> -x
 __device__ __forceinline__ void f12_conj(F12& r, const F12& f) {
 #pragma unroll
-  for (int i = 0; i < 6; i++) {
-    if (i & 1) f2_neg(r.c[i], f.c[i]); else r.c[i] = f.c[i];
+  for (int i = 0; i < 3; i++) {            // storage: even coefficients 0..2, odd ones 3..5
+    r.c[i] = f.c[i];
+    f2_neg(r.c[3 + i], f.c[3 + i]);
   }
 }
 // f^(q^k), k = 1, 2, 3: coefficient i is conjugated in F_q^2 for odd k and scaled by frob[k-1][i-1]
@@ -547,9 +528,9 @@ __device__ __noinline__ void f12_frob(F12& r, const F12& f, int k) {
   if (k & 1) fq_neg(r.c[0].b, f.c[0].b);
 #pragma unroll 1
   for (int i = 1; i < 6; i++) {
-    t = f.c[i];
+    t = F12C(f, i);
     if (k & 1) fq_neg(t.b, t.b);
-    f2_mul(&r.c[i], &t, f2_const(c_f.frob[k - 1][i - 1]));
+    f2_mul(&F12C(r, i), &t, f2_const(c_f.frob[k - 1][i - 1]));
   }
 }
 // (a + b s)^2 in F_q^4 = F_q^2[s]/(s^2 - xi), s = x^3:  (a^2 + xi b^2, (a + b)^2 - a^2 - b^2)
@@ -571,17 +552,17 @@ __device__ __noinline__ void f4_sqr(F2* r0, F2* r1, const F2* a, const F2* b) {
 // the final exponentiation only.
 __device__ __noinline__ void f12_cyc_sqr(F12* v) {
   F2 A0, A1, B0, B1, C0, C1, t;
-  f4_sqr(&A0, &A1, &v->c[0], &v->c[3]);
-  f4_sqr(&B0, &B1, &v->c[1], &v->c[4]);
-  f4_sqr(&C0, &C1, &v->c[2], &v->c[5]);
+  f4_sqr(&A0, &A1, &F12C(*v, 0), &F12C(*v, 3));
+  f4_sqr(&B0, &B1, &F12C(*v, 1), &F12C(*v, 4));
+  f4_sqr(&C0, &C1, &F12C(*v, 2), &F12C(*v, 5));
   // 3X -+ 2u: X + 2 (X -+ u)
-  f2_sub(t, A0, v->c[0]); f2_dbl(t, t); f2_add(v->c[0], t, A0);
-  f2_add(t, A1, v->c[3]); f2_dbl(t, t); f2_add(v->c[3], t, A1);
-  f2_sub(t, B0, v->c[2]); f2_dbl(t, t); f2_add(v->c[2], t, B0);
-  f2_add(t, B1, v->c[5]); f2_dbl(t, t); f2_add(v->c[5], t, B1);
+  f2_sub(t, A0, F12C(*v, 0)); f2_dbl(t, t); f2_add(F12C(*v, 0), t, A0);
+  f2_add(t, A1, F12C(*v, 3)); f2_dbl(t, t); f2_add(F12C(*v, 3), t, A1);
+  f2_sub(t, B0, F12C(*v, 2)); f2_dbl(t, t); f2_add(F12C(*v, 2), t, B0);
+  f2_add(t, B1, F12C(*v, 5)); f2_dbl(t, t); f2_add(F12C(*v, 5), t, B1);
   f2_mul_xi(C1, C1);                       // s (C0 + C1 s) = xi C1 + C0 s
-  f2_add(t, C1, v->c[1]); f2_dbl(t, t); f2_add(v->c[1], t, C1);
-  f2_sub(t, C0, v->c[4]); f2_dbl(t, t); f2_add(v->c[4], t, C0);
+  f2_add(t, C1, F12C(*v, 1)); f2_dbl(t, t); f2_add(F12C(*v, 1), t, C1);
+  f2_sub(t, C0, F12C(*v, 4)); f2_dbl(t, t); f2_add(F12C(*v, 4), t, C0);
 }
 
 // f^u for the BN parameter u (on the cyclotomic subgroup the inverse is the conjugate)
@@ -674,23 +655,23 @@ k_f_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
   uint8_t* o = out + idx * (12 * kWS);
 #pragma unroll 1
   for (int i = 0; i < 6; i++) {
-    fq_to_wire(o + (2 * i) * kWS, acc.c[i].a);
-    fq_to_wire(o + (2 * i + 1) * kWS, acc.c[i].b);
+    fq_to_wire(o + (2 * i) * kWS, F12C(acc, i).a);
+    fq_to_wire(o + (2 * i + 1) * kWS, F12C(acc, i).b);
   }
 }
 
 __device__ __forceinline__ void f12_from_wire(F12& v, const uint8_t* p) {
 #pragma unroll 1
   for (int i = 0; i < 6; i++) {
-    fq_from_wire(v.c[i].a, p + (2 * i) * kWS);
-    fq_from_wire(v.c[i].b, p + (2 * i + 1) * kWS);
+    fq_from_wire(F12C(v, i).a, p + (2 * i) * kWS);
+    fq_from_wire(F12C(v, i).b, p + (2 * i + 1) * kWS);
   }
 }
 __device__ __forceinline__ void f12_to_wire(uint8_t* p, const F12& v) {
 #pragma unroll 1
   for (int i = 0; i < 6; i++) {
-    fq_to_wire(p + (2 * i) * kWS, v.c[i].a);
-    fq_to_wire(p + (2 * i + 1) * kWS, v.c[i].b);
+    fq_to_wire(p + (2 * i) * kWS, F12C(v, i).a);
+    fq_to_wire(p + (2 * i + 1) * kWS, F12C(v, i).b);
   }
 }
 
@@ -712,7 +693,7 @@ __global__ void k_f_tower_op(int op, uint8_t* __restrict__ out, const uint8_t* _
     case 2: f12_inv(&r, &x); break;
     case 3: f12_final_exp(r, x); break;
     case 5: r = x; f12_cyc_sqr(&r); break;
-    default: r = x; f12_mul_line(&r, &y.c[0].a, &y.c[3], &y.c[4]); break;
+    default: r = x; f12_mul_line(&r, &F12C(y, 0).a, &F12C(y, 3), &F12C(y, 4)); break;
   }
   f12_to_reference(r);
   f12_to_wire(out + idx * (12 * kWS), r);
