@@ -308,7 +308,7 @@ def main():
 
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
+        os.environ.pop("NCCL_DEBUG", None)     # any level >= VERSION prints "NCCL version ..." on stdout; keep it to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     pr = Pairing(PARAMS[w["param"]])
