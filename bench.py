@@ -62,6 +62,11 @@ WORKLOADS = {
                    name="type A element_prod_pairing n=16, 2^16 outputs (2^20 Miller loops) over all GPUs",
                    dtype="u32 limbs (16 x 32-bit = 512-bit F_q, exact integer)",
                    kernels=("k_a_miller+k_a_prod", "k_batch_invert", "k_a_finalexp")),
+    "pp": dict(param="a", mode="pp", k=1, n=1 << 20, unit=528, ref_mulmods=1838 + 719, ref_main=1838,
+               exec_unit_ops_main=(160 * 7 + 5) * 528 + 4 * 408, cpu_rate=400.0, port_rate=110.0,
+               name="type A pairing_pp_init + pairing_pp_apply: one fixed first argument, 2^20 second arguments per GPU",
+               dtype="u32 limbs (16 x 32-bit = 512-bit F_q, exact integer)",
+               kernels=("k_a_pp_init+k_a_pp_apply", "k_batch_invert", "k_a_finalexp")),
 }
 WIRE = {"a": (128, 128, 128), "f": (40, 80, 240), "d159": (40, 120, 120)}
 
@@ -93,7 +98,10 @@ def _ref_worker(args):
     from oracle import ref as R
     rp = R.RefPairing(PARAMS[name])
     t0 = time.perf_counter()
-    out = rp.pairing(Pb, Qb, n) if mode == "single" else rp.prod_pairing(Pb, Qb, k, n)
+    if mode == "pp":
+        out = rp.pp_pairing(Pb, Qb, n)
+    else:
+        out = rp.pairing(Pb, Qb, n) if mode == "single" else rp.prod_pairing(Pb, Qb, k, n)
     return out, time.perf_counter() - t0
 
 
@@ -102,7 +110,9 @@ def _port_worker(args):
     from oracle import pbc_oracle as O
     pr = O.pairing_from_param(PARAMS[name])
     t0 = time.perf_counter()
-    if mode == "single":
+    if mode == "pp":
+        out = O.pairing_batch(pr, Pb[:pr.g1_len] * n, Qb, n)
+    elif mode == "single":
         out = O.pairing_batch(pr, Pb, Qb, n)
     else:
         a, b = pr.g1_len, pr.g2_len
@@ -135,8 +145,8 @@ def cpu_pairings(w, P, Q, n, cores, pool=None):
     for c in range(cores):
         lo, hi = c * per, min(n, (c + 1) * per)
         if lo < hi:
-            jobs.append((w["param"], w["mode"], k, bytes(P[lo * k * g1:hi * k * g1]),
-                         bytes(Q[lo * k * g2:hi * k * g2]), hi - lo))
+            pslice = bytes(P[:g1]) if w["mode"] == "pp" else bytes(P[lo * k * g1:hi * k * g1])
+            jobs.append((w["param"], w["mode"], k, pslice, bytes(Q[lo * k * g2:hi * k * g2]), hi - lo))
     own = pool is None
     if own:
         pool = mp.get_context("fork").Pool(len(jobs))
@@ -241,12 +251,12 @@ def reference_arm(args):
     pool.close()
     pool.join()
     val = per_step * args.steps / wall
-    unit = "pairings/s" if w["mode"] == "single" else "outputs/s"
+    unit = "pairings/s" if w["mode"] in ("single", "pp") else "outputs/s"
     line = {
         "impl": "reference", "metric": "pairings/sec", "value": val, "unit": unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
-        "scaling": "weak" if w["mode"] == "single" else "strong",
+        "scaling": "weak" if w["mode"] in ("single", "pp") else "strong",
         "vs_baseline": None, "dtype": w["dtype"] if kind == "port" else "u64 limbs (GMP mpn)",
         "data": "synthetic",
         "config": {"workload": w["name"], "batch_per_step": per_step, "param": w["param"] + ".param",
@@ -279,7 +289,7 @@ def main():
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     w = WORKLOADS[args.workload]
-    k, single = w["k"], w["mode"] == "single"
+    k, single = w["k"], w["mode"] in ("single", "pp")
     # single pairings: every rank owns its own full batch (weak scaling); the product config is a
     # fixed 2^16 outputs split by output across the ranks (strong scaling)
     n = args.n or (w["n"] if single else max(1, w["n"] // world))
@@ -320,13 +330,17 @@ def main():
     st = torch.cuda.current_stream()
 
     def step():
-        if single:
+        if w["mode"] == "pp":
+            pr.pp_apply_device(dO.data_ptr(), dP.data_ptr(), dQ.data_ptr(), n, st.cuda_stream)
+        elif single:
             pr.apply_device(dO.data_ptr(), dP.data_ptr(), dQ.data_ptr(), n, st.cuda_stream)
         else:
             pr.prod_apply_device(dO.data_ptr(), dP.data_ptr(), dQ.data_ptr(), k, n, st.cuda_stream)
 
     def host_step():
-        if single:
+        if w["mode"] == "pp":
+            pr.pp_apply_into(Op, Pp, Qp, n)
+        elif single:
             pr.apply_into(Op, Pp, Qp, n)
         else:
             pr.prod_apply_into(Op, Pp, Qp, k, n)
@@ -403,8 +417,8 @@ def main():
             # type A: the Miller kernel, reference-equivalent and executed work both known
             kern, kms = w["kernels"][0], stage[0]
             ach_ref = n * w["ref_main"] * unit / (kms * 1e-3)
-            ach_exec = n * w["exec_unit_ops_main"] / (kms * 1e-3)
-            work = ("reference-equivalent %d mulmods x %d unit ops per output in this kernel; executed %d unit ops"
+            ach_exec = n * w["exec_unit_ops_main"] / (kms * 1e-3) if w["exec_unit_ops_main"] else None
+            work = ("reference-equivalent %d mulmods x %d unit ops per output in this kernel; executed %s unit ops"
                     % (w["ref_main"], unit, w["exec_unit_ops_main"]))
         else:
             # types f, d: SURVEY 8(d) gives the reference's mulmod count for the whole pairing only,

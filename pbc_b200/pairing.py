@@ -114,6 +114,14 @@ class Pairing:
             raise PairingError(last_error())
         return out.raw[:n * self.gt_len]
 
+    def pp_apply_into(self, out, in1, in2, n: int):
+        if lib.pbc_b200_pp_pairings_apply(self._h, _addr(out), _addr(in1), _addr(in2), n):
+            raise PairingError(last_error())
+
+    def pp_apply_device(self, d_out, d_in1, d_in2, n, stream=0):
+        if lib.pbc_b200_pp_pairings_apply_device(self._h, d_out, d_in1, d_in2, n, stream):
+            raise PairingError(last_error())
+
     # -- element_pow_zn on G1 / GT (include/pbc_field.h:262-275) ------------------------------------
     def g1_pow_zn(self, points: bytes, scalars: bytes, n=None) -> bytes:
         if n is None:
