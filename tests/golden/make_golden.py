@@ -19,8 +19,8 @@ from oracle import ref as R  # noqa: E402
 from pbc_b200.params import PARAMS  # noqa: E402
 
 SEED = 20260922
-N_SINGLE = {"a": 24, "f": 12, "d159": 16}
-PROD = {"a": (4, 3), "f": (3, 2), "d159": (4, 3)}  # (k, n_out)
+N_SINGLE = {"a": 24, "f": 12, "d159": 16, "g149": 12}
+PROD = {"a": (4, 3), "f": (3, 2), "d159": (4, 3), "g149": (3, 2)}  # (k, n_out)
 
 
 def chunks(b, n):
@@ -28,7 +28,10 @@ def chunks(b, n):
 
 
 def main():
+    only = sys.argv[1:]          # e.g. `make_golden.py g149` regenerates that file alone
     for name, text in PARAMS.items():
+        if only and name not in only:
+            continue
         rp = R.RefPairing(text)
         R.RefPairing.seed(SEED)
         n = N_SINGLE[name]

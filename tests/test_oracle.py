@@ -49,7 +49,7 @@ def test_kat_prod_and_pp_agree(pa):
     assert e2 == pa.Fq2.mul(KAT_E_GH, KAT_RES)
 
 
-@pytest.mark.parametrize("name,limit", [("a", 24), ("d159", 8), ("f", 3)])
+@pytest.mark.parametrize("name,limit", [("a", 24), ("d159", 8), ("f", 3), ("g149", 4)])
 def test_oracle_matches_reference_fixtures(golden, name, limit):
     g = golden[name]
     pr = O.pairing_from_param(PARAMS[name])
@@ -99,7 +99,7 @@ def test_from_hash_restatement_matches_reference_fixtures(golden):
     oracle's restatement vs G1 elements the compiled reference derived from the same bytes."""
     from oracle import pbc_oracle as O
     from pbc_b200.params import PARAMS
-    for name in ("a", "f", "d159"):
+    for name in ("a", "f", "d159", "g149"):
         orc = O.pairing_from_param(PARAMS[name])
         for ln, blk in golden[name]["hash"].items():
             for d, want in zip(blk["data"], blk["G1"]):
