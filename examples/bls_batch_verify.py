@@ -6,7 +6,7 @@ up): every step is one of the batched entry points of include/pbc_b200.h.
     sign     sigma_i = sk * H(m_i)                          pbc_b200_g1_from_hash, pbc_b200_g1_pow_zn
     verify   e(sigma_i, g2) * e(-H(m_i), pk) == 1           pbc_b200_g1_from_hash, pbc_b200_prod_pairings_apply (k = 2)
 
-usage: python examples/bls_batch_verify.py [a|f|d159] [n]
+usage: python examples/bls_batch_verify.py [a|f|d159|g149] [n]
 """
 import hashlib
 import json
@@ -40,7 +40,7 @@ def main():
     g = json.load(open(os.path.join(ROOT, "tests", "golden", name + ".json")))
     g2 = bytes.fromhex(g["pairing"]["Q"][0])                    # a fixed generator of G2
     rnd = random.Random(2026)
-    sk = rnd.randrange(1, prm["r"]).to_bytes(20, "big")
+    sk = rnd.randrange(1, prm["r"]).to_bytes(pr.zr_len, "big")
     pk = pr.g2_pow_zn(g2, sk, 1)
     msgs = b"".join(hashlib.sha256(b"message %d" % i).digest() for i in range(n))
 
@@ -62,7 +62,7 @@ def main():
     in2 = (g2 + pk) * n
     res = pr.prod_apply(in1, in2, 2, n)
     t_verify = time.perf_counter() - t0
-    one = pr.gt_pow_zn(res[:pr.gt_len], bytes(20), 1)           # x^0: the GT identity in wire form
+    one = pr.gt_pow_zn(res[:pr.gt_len], bytes(pr.zr_len), 1)           # x^0: the GT identity in wire form
     ok = [res[i * pr.gt_len:(i + 1) * pr.gt_len] == one for i in range(n)]
     assert ok.count(False) == 1 and not ok[bad], "exactly the forged signature must fail"
     print(json.dumps({"example": "bls_batch_verify", "type": name, "n": n,

@@ -24,6 +24,7 @@
 #include "pairing_a.cuh"
 #include "pairing_d.cuh"
 #include "pairing_f.cuh"
+#include "pairing_g.cuh"
 #include "group_a.cuh"
 #include "group_cc.cuh"
 
@@ -103,6 +104,7 @@ struct pbc_b200_pairing_s {
   CCConsts cc;
   FConsts f;
   DConsts d;
+  GConsts g;
   ZrConsts zr;
   HashConsts hash;
   bool hash_ok = false;        // element_from_hash available (q = 3 mod 4 or 5 mod 8)
@@ -150,7 +152,7 @@ static size_t ws_bytes(const pbc_b200_pairing_s* p, const Job& job, size_t n_out
     return n_out * (2 + 1 + 1) * fq + (size_t)(3 * (p->a.exp2 + 1) * kNA + 4) * 4;
   }
   // types f, d: Miller values [W][n] words + one flag word each; products add the reduced arrays
-  size_t W = p->type == 'f' ? kF12Words : kF6DWords;
+  size_t W = p->type == 'f' ? kF12Words : (p->type == 'g' ? kF10Words : kF6DWords);
   size_t n_in = job.mode == kProd ? n_out * job.k : n_out;
   size_t bytes = n_in * (W + 1) * 4;
   if (job.mode == kProd) bytes += n_out * (W + 1) * 4;
@@ -206,6 +208,7 @@ static int init_type_a(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   p->type = 'a';
   memset(&p->zr, 0, sizeof p->zr);
   r.to_words(p->zr.r, 5);
+  p->zr.zlen = (uint32_t)((r.bits() + 7) / 8);
   p->nlimbs = kNA;
   p->full = true;
   p->g1_len = p->g2_len = p->gt_len = 128;
@@ -329,6 +332,7 @@ static int init_type_f(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   p->type = 'f';
   memset(&p->zr, 0, sizeof p->zr);
   r.to_words(p->zr.r, 5);
+  p->zr.zlen = (uint32_t)((r.bits() + 7) / 8);
   p->nlimbs = kNS;
   p->full = false;
   p->g1_len = 2 * kWS; p->g2_len = 4 * kWS; p->gt_len = 12 * kWS;
@@ -451,6 +455,7 @@ static int init_type_d(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   p->type = 'd';
   memset(&p->zr, 0, sizeof p->zr);
   r.to_words(p->zr.r, 5);
+  p->zr.zlen = (uint32_t)((r.bits() + 7) / 8);
   p->nlimbs = kNS;
   p->full = false;
   p->g1_len = 2 * kWS; p->g2_len = 6 * kWS; p->gt_len = 6 * kWS;
@@ -529,6 +534,72 @@ static int init_type_d(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   return 0;
 }
 
+// g_init_pairing (ecc/g_param.c:1248-1353), k = 10
+static int init_type_g(pbc_b200_pairing_s* p, const std::map<std::string, std::string>& tab) {
+  BigUInt q, r, a, b, nqr, co[5];
+  int k = 0;
+  if (!get_big(tab, "q", &q) || !get_big(tab, "r", &r) || !get_big(tab, "a", &a) || !get_big(tab, "b", &b) ||
+      !get_int(tab, "k", &k) || !get_big(tab, "nqr", &nqr)) return 1;
+  for (int i = 0; i < 5; i++)
+    if (!get_big(tab, ("coeff" + std::to_string(i)).c_str(), &co[i])) return 1;
+  if (k != 10) return fail("type g: embedding degree must be 10 (got k = %d)", k);
+  if ((q.bits() + 7) / 8 != (size_t)kWG)
+    return fail("type g: this build supports 145..152-bit q (19-byte coordinates; got %zu bits)", q.bits());
+  if (r.bits() > 160 || r.bits() < 3) return fail("type g: bad group order");
+  p->type = 'g';
+  memset(&p->zr, 0, sizeof p->zr);
+  r.to_words(p->zr.r, 5);
+  p->zr.zlen = (uint32_t)((r.bits() + 7) / 8);
+  p->zr_len = (int)p->zr.zlen;
+  p->nlimbs = kNS;
+  p->full = false;
+  p->g1_len = 2 * kWG; p->g2_len = 10 * kWG; p->gt_len = 10 * kWG;
+  fill_fp_consts(&p->fp, q, kNS);
+  fill_cc(&p->cc, a, b, r, q);
+  {
+    BigUInt hco(1);
+    auto ith = tab.find("h");
+    if (ith != tab.end()) BigUInt::from_dec(ith->second, &hco);
+    fill_hash(p, q, hco);                  // G1 cofactor = h (ecc/g_param.c:1267)
+  }
+  GConsts& c = p->g;
+  memset(&c, 0, sizeof c);
+  BigUInt v = nqr % q, vinv = BigUInt::invmod(v, q), one(1);
+  BigUInt v2 = BigUInt::mulmod(v, v, q);
+  to_mont(c.nqr, v, q, kNS);
+  to_mont(c.nqrinv, vinv, q, kNS);
+  to_mont(c.nqrinv2, BigUInt::mulmod(vinv, vinv, q), q, kNS);
+  to_mont(c.twist_a, BigUInt::mulmod(a % q, v2, q), q, kNS);
+  to_mont(c.twist_b, BigUInt::mulmod(b % q, BigUInt::mulmod(v2, v, q), q), q, kNS);
+  to_mont(c.two, BigUInt(2), q, kNS);
+  HostPolyField K{q, {co[0] % q, co[1] % q, co[2] % q, co[3] % q, co[4] % q}};
+  HostPolyField::El x(5), xp;
+  x[1] = one;
+  xp = K.mul(K.mul(x, x), K.mul(K.mul(x, x), x));            // x^5
+  std::vector<BigUInt> rec;
+  for (int s = 0; s < 4; s++) {
+    for (int i = 0; i < 5; i++) { to_mont(c.xpwr[s][i], xp[i], q, kNS); rec.push_back(xp[i]); }
+    xp = K.mul(xp, x);
+  }
+  p->derived["xpwr"] = rec;
+  HostPolyField::El xq = K.pow(x, q), acc = xq;
+  rec.clear();
+  for (int s = 0; s < 4; s++) {
+    for (int i = 0; i < 5; i++) { to_mont(c.xpowq[s][i], acc[i], q, kNS); rec.push_back(acc[i]); }
+    acc = K.mul(acc, xq);
+  }
+  p->derived["xpowq"] = rec;
+  BigUInt q2 = q * q, q3 = q2 * q, q4 = q2 * q2;
+  BigUInt num = ((q4 + q2 + one) - q3) - q, ph, rem;
+  BigUInt::divmod(num, r, &ph, &rem);
+  if (!rem.is_zero()) return fail("type g: r does not divide q^4 - q^3 + q^2 - q + 1");
+  if (ph.bits() > 512) return fail("type g: final exponent too large");
+  ph.to_words(c.phikonr, 16);
+  c.phibits = (uint32_t)ph.bits();
+  p->derived["phikonr"] = {ph};
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // device contexts
 // ------------------------------------------------------------------------------------------
@@ -576,9 +647,10 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
     if (p->type == 'a') CUDA_OK(cudaMemcpyToSymbol(c_a, &p->a, sizeof(AConsts)));
     CUDA_OK(cudaMemcpyToSymbol(c_zr, &p->zr, sizeof(ZrConsts)));
     CUDA_OK(cudaMemcpyToSymbol(c_hash, &p->hash, sizeof(HashConsts)));
-    if (p->type == 'f' || p->type == 'd') CUDA_OK(cudaMemcpyToSymbol(c_cc, &p->cc, sizeof(CCConsts)));
+    if (p->type == 'f' || p->type == 'd' || p->type == 'g') CUDA_OK(cudaMemcpyToSymbol(c_cc, &p->cc, sizeof(CCConsts)));
     if (p->type == 'f') CUDA_OK(cudaMemcpyToSymbol(c_f, &p->f, sizeof(FConsts)));
     if (p->type == 'd') CUDA_OK(cudaMemcpyToSymbol(c_d, &p->d, sizeof(DConsts)));
+    if (p->type == 'g') CUDA_OK(cudaMemcpyToSymbol(c_g, &p->g, sizeof(GConsts)));
     CUDA_OK(cudaDeviceSynchronize());
     g_const_owner[dev] = p->id;
   }
@@ -655,9 +727,9 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
     CUDA_OK(cudaGetLastError());
     return 0;
   }
-  if (p->type == 'f' || p->type == 'd') {
-    const bool isf = p->type == 'f';
-    const size_t W = isf ? kF12Words : kF6DWords;
+  if (p->type == 'f' || p->type == 'd' || p->type == 'g') {
+    const bool isf = p->type == 'f', isg = p->type == 'g';
+    const size_t W = isf ? kF12Words : (isg ? kF10Words : kF6DWords);
     size_t m = job.mode == kProd ? n * job.k : n;
     uint32_t* mv = (uint32_t*)ws;                // [W][m]
     uint32_t* flag = mv + W * m;                 // [m]
@@ -665,6 +737,7 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
     unsigned gm = (unsigned)((m + kBlockCCMiller - 1) / kBlockCCMiller);
     STAGE(0);
     if (isf) k_f_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1);
+    else if (isg) k_g_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1);
     else k_d_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1);
     LAUNCHED();
     STAGE(1);
@@ -673,6 +746,7 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
       uint32_t* flago = mvo + W * n;
       unsigned gp = (unsigned)((n + kBlockCC - 1) / kBlockCC);
       if (isf) k_f_prod<kBlockCC><<<gp, kBlockCC, 0, st>>>(mv, flag, mvo, flago, job.k, n, m);
+      else if (isg) k_g_prod<kBlockCC><<<gp, kBlockCC, 0, st>>>(mv, flag, mvo, flago, job.k, n, m);
       else k_d_prod<kBlockCC><<<gp, kBlockCC, 0, st>>>(mv, flag, mvo, flago, job.k, n, m);
       LAUNCHED();
       mv = mvo; flag = flago;
@@ -681,6 +755,7 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
     unsigned gf = (unsigned)((n + kBlockCC - 1) / kBlockCC);
     unsigned gfm = (unsigned)((n + kBlockCCMiller - 1) / kBlockCCMiller);
     if (isf) k_f_finalexp<kBlockCCMiller><<<gfm, kBlockCCMiller, 0, st>>>(mv, flag, d_out, n);
+    else if (isg) k_g_finalexp<kBlockCC><<<gf, kBlockCC, 0, st>>>(mv, flag, d_out, n);
     else k_d_finalexp<kBlockCC><<<gf, kBlockCC, 0, st>>>(mv, flag, d_out, n);
     LAUNCHED();
     STAGE(3);
@@ -808,7 +883,8 @@ int pbc_b200_pairing_init_set_buf(pbc_b200_pairing_t** out, const char* param, s
   if (it->second == "a") rc = init_type_a(p, tab);
   else if (it->second == "f") rc = init_type_f(p, tab);
   else if (it->second == "d") rc = init_type_d(p, tab);
-  else rc = fail("pairing type `%s' is not on the B200 hot path (supported: a, d with k = 6, f)", it->second.c_str());
+  else if (it->second == "g") rc = init_type_g(p, tab);
+  else rc = fail("pairing type `%s' is not on the B200 hot path (supported: a, d with k = 6, f, g)", it->second.c_str());
   if (rc) { delete p; return 1; }
   *out = p;
   return 0;
@@ -1022,7 +1098,11 @@ static int enqueue_group(pbc_b200_pairing_s* p, int which /*0 = G1, 1 = GT, 2 = 
     }
   } else {
     unsigned g = (unsigned)((n + kBlockCC - 1) / kBlockCC);
-    if (which == 0) k_cc_g1_mul<kBlockCC><<<g, kBlockCC, 0, st>>>(d_in, d_k, d_out, n);
+    const bool isg = p->type == 'g';
+    if (which == 0 && isg) k_cc_g1_mul<kBlockCC, kWG><<<g, kBlockCC, 0, st>>>(d_in, d_k, d_out, n);
+    else if (which == 0) k_cc_g1_mul<kBlockCC, kWS><<<g, kBlockCC, 0, st>>>(d_in, d_k, d_out, n);
+    else if (which == 2 && isg) k_cc_g2_mul<KF5, kBlockCC><<<g, kBlockCC, 0, st>>>(d_in, d_k, d_out, n);
+    else if (which == 1 && isg) k_g_gt_pow<kBlockCC><<<g, kBlockCC, 0, st>>>(d_in, d_k, d_out, n);
     else if (which == 2 && p->type == 'f') k_cc_g2_mul<KF2, kBlockCC><<<g, kBlockCC, 0, st>>>(d_in, d_k, d_out, n);
     else if (which == 2) k_cc_g2_mul<KF3, kBlockCC><<<g, kBlockCC, 0, st>>>(d_in, d_k, d_out, n);
     else if (p->type == 'f') k_f_gt_pow<kBlockCC><<<g, kBlockCC, 0, st>>>(d_in, d_k, d_out, n);
@@ -1141,7 +1221,8 @@ static int run_from_hash(pbc_b200_pairing_s* p, unsigned char* out, const unsign
     LAUNCHED();
   } else {
     unsigned g = (unsigned)((n + kBlockCC - 1) / kBlockCC);
-    k_cc_g1_from_hash<kBlockCC><<<g, kBlockCC, 0, st>>>(d_data, (int)len, d_out, n);
+    if (p->type == 'g') k_cc_g1_from_hash<kBlockCC, kWG><<<g, kBlockCC, 0, st>>>(d_data, (int)len, d_out, n);
+    else k_cc_g1_from_hash<kBlockCC, kWS><<<g, kBlockCC, 0, st>>>(d_data, (int)len, d_out, n);
     LAUNCHED();
   }
   CUDA_OK(cudaGetLastError());
@@ -1193,7 +1274,8 @@ extern "C" int pbc_b200_g1_from_bytes_compressed(pbc_b200_pairing_t* p, unsigned
     k_a_g1_decompress<kBlockMiller><<<g, kBlockMiller, (size_t)5 * 64 * kBlockMiller, st>>>(d_in, d_out, n);
   } else {
     unsigned g = (unsigned)((n + kBlockCC - 1) / kBlockCC);
-    k_cc_g1_decompress<kBlockCC><<<g, kBlockCC, 0, st>>>(d_in, d_out, n);
+    if (p->type == 'g') k_cc_g1_decompress<kBlockCC, kWG><<<g, kBlockCC, 0, st>>>(d_in, d_out, n);
+    else k_cc_g1_decompress<kBlockCC, kWS><<<g, kBlockCC, 0, st>>>(d_in, d_out, n);
   }
   LAUNCHED();
   CUDA_OK(cudaGetLastError());
@@ -1270,6 +1352,7 @@ __global__ void k_fqmul_chain(uint32_t* __restrict__ out, const uint32_t* __rest
 extern "C" int pbc_b200_fp_op(pbc_b200_pairing_t* p, int op, unsigned char* out,
                               const unsigned char* a, const unsigned char* b, size_t n) {
   if (!p) return fail("null argument");
+  if (p->type == 'g') return fail("fp_op: not wired for the 19-byte coordinates of type g (the field code is type d's)");
   if (n == 0) return 0;
   int dev = 0;
   CUDA_OK(cudaGetDevice(&dev));
@@ -1300,7 +1383,7 @@ extern "C" int pbc_b200_fp_op(pbc_b200_pairing_t* p, int op, unsigned char* out,
 extern "C" int pbc_b200_tower_op(pbc_b200_pairing_t* p, int op, unsigned char* out,
                                  const unsigned char* a, const unsigned char* b, size_t n) {
   if (!p) return fail("null argument");
-  if (p->type != 'f' && p->type != 'd') return fail("tower_op: types f and d only");
+  if (p->type != 'f' && p->type != 'd' && p->type != 'g') return fail("tower_op: types f, d and g only");
   if (n == 0) return 0;
   int dev = 0;
   CUDA_OK(cudaGetDevice(&dev));
@@ -1314,6 +1397,7 @@ extern "C" int pbc_b200_tower_op(pbc_b200_pairing_t* p, int op, unsigned char* o
   CUDA_OK(cudaMemcpy(db, b ? b : a, n * wb, cudaMemcpyHostToDevice));
   unsigned g = (unsigned)((n + 63) / 64);
   if (p->type == 'f') k_f_tower_op<<<g, 64>>>(op, dout, da, db, n);
+  else if (p->type == 'g') k_g_tower_op<<<g, 64>>>(op, dout, da, db, n);
   else k_d_tower_op<<<g, 64>>>(op, dout, da, db, n);
   LAUNCHED();
   CUDA_OK(cudaDeviceSynchronize());

@@ -188,6 +188,44 @@ __device__ __forceinline__ void fq_to_wire(uint8_t* p, const Fq& a) {
   limbs_to_be<kNS, kWS>(p, x);
 }
 
+// the same for a coordinate width that is not a multiple of four bytes (g149: 19), byte by byte
+template <int WB>
+__device__ __forceinline__ void fq_from_wire_b(Fq& r, const uint8_t* p) {
+#pragma unroll
+  for (int k = 0; k < kNS; k++) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      int pos = WB - 1 - (4 * k + b);        // byte of weight 256^(4k+b), counted from the end
+      if (pos >= 0) w |= (uint32_t)p[pos] << (8 * b);
+    }
+    r.v[k] = w;
+  }
+  mont_mul_ps<kNS, false>(r.v, r.v, c_fp.r2);
+}
+template <int WB>
+__device__ __forceinline__ void fq_to_wire_b(uint8_t* p, const Fq& a) {
+  uint32_t one[kNS] = {1}, x[kNS];
+  mont_mul_ps<kNS, false>(x, a.v, one);
+#pragma unroll
+  for (int i = 0; i < WB; i++) {
+    int byte = WB - 1 - i;                   // weight of output byte i
+    p[i] = (uint8_t)(x[byte >> 2] >> (8 * (byte & 3)));
+  }
+}
+
+// width-generic front ends: the word-wise path when the width allows it, else byte by byte
+template <int WB>
+__device__ __forceinline__ void fq_from_wire_w(Fq& r, const uint8_t* p) {
+  if constexpr (WB % 4 == 0) { limbs_from_be<kNS, WB>(r.v, p); mont_mul_ps<kNS, false>(r.v, r.v, c_fp.r2); }
+  else fq_from_wire_b<WB>(r, p);
+}
+template <int WB>
+__device__ __forceinline__ void fq_to_wire_w(uint8_t* p, const Fq& a) {
+  if constexpr (WB % 4 == 0) { uint32_t one[kNS] = {1}, x[kNS]; mont_mul_ps<kNS, false>(x, a.v, one); limbs_to_be<kNS, WB>(p, x); }
+  else fq_to_wire_b<WB>(p, a);
+}
+
 // a^(q-2) (the reference calls mpz_invert, arith/montfp.c:401-422; the value is the same)
 __device__ __noinline__ void fq_inv(Fq* r, const Fq* a) {
   Fq x = *a, acc;

@@ -15,8 +15,9 @@
 namespace pbcb200 {
 
 struct ZrConsts {
-  uint32_t r[5];         // group order, little-endian words (all three types have r < 2^160)
-  uint32_t pad[3];
+  uint32_t r[5];         // group order, little-endian words (every supported type has r < 2^160)
+  uint32_t zlen;         // Zr wire bytes: ceil(bits(r)/8) (20 for a, f, d159; 19 for g149)
+  uint32_t pad[2];
 };
 __constant__ ZrConsts c_zr;
 
@@ -70,16 +71,23 @@ __device__ __forceinline__ void hash_to_words(uint32_t* x, const uint8_t* data, 
   }
 }
 
-constexpr int kWZ = 20;  // Zr wire bytes
+constexpr int kWZ = 20;  // Zr wire bytes of a.param, f.param, d159.param (c_zr.zlen is authoritative)
 
-// 20 big-endian bytes -> five little-endian words, reduced mod r (r > 2^157: at most 7 subtractions)
+// c_zr.zlen big-endian bytes -> five little-endian words, reduced mod r (r > 2^(8 zlen - 11): a few
+// subtractions at most)
 __device__ __forceinline__ void zr_from_wire(uint32_t* k, const uint8_t* p) {
+  const int zlen = (int)c_zr.zlen;
 #pragma unroll
   for (int i = 0; i < 5; i++) {
-    const uint8_t* b = p + kWZ - 4 - 4 * i;
-    k[i] = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+    uint32_t w = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      int pos = zlen - 1 - (4 * i + b);
+      if (pos >= 0) w |= (uint32_t)p[pos] << (8 * b);
+    }
+    k[i] = w;
   }
-  for (int it = 0; it < 8; it++) {
+  for (int it = 0; it < 4096; it++) {
     uint32_t d[5], borrow;
     PBC_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(d[0]) : "r"(k[0]), "r"(c_zr.r[0]));
 #pragma unroll
@@ -154,7 +162,7 @@ k_a_g1_mul(const uint8_t* __restrict__ P, const uint8_t* __restrict__ K, uint4* 
   size_t src = live ? idx : 0;
   bool okP = a_load_point<O>(gPX, gPY, gT0, gT1, P + src * (2 * kWA));
   uint32_t k[5];
-  zr_from_wire(k, K + src * kWZ);
+  zr_from_wire(k, K + src * c_zr.zlen);
   int top = zr_top_bit(k);
   O::copy(gX, gPX);
   O::copy(gY, gPY);
@@ -318,7 +326,7 @@ k_a_gt_pow(const uint8_t* __restrict__ G, const uint8_t* __restrict__ K, uint8_t
   mont_mul<kNA, true>(x, x, c_fp.r2);
   O::st(sB1, x);
   uint32_t k[5];
-  zr_from_wire(k, K + src * kWZ);
+  zr_from_wire(k, K + src * c_zr.zlen);
   int top = zr_top_bit(k);
   O::copy(sA0, sB0);
   O::copy(sA1, sB1);

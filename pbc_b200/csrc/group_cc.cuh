@@ -11,22 +11,23 @@
 #include "group_a.cuh"
 #include "pairing_d.cuh"
 #include "pairing_f.cuh"
+#include "pairing_g.cuh"
 
 namespace pbcb200 {
 
 // out[i] = k[i] * in[i] on y^2 = x^3 + A x + B over the five-limb field.  O -> zero bytes.
-template <int BLOCK>
+template <int BLOCK, int W>
 __global__ void __launch_bounds__(BLOCK, PBC_CC_MINBLOCKS)
 k_cc_g1_mul(const uint8_t* __restrict__ P, const uint8_t* __restrict__ K, uint8_t* __restrict__ out,
             size_t n) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (idx >= n) return;
   Fq xP, yP, X, Y, Z, Z2, M, Y2, t, u, H, R;
-  fq_from_wire(xP, P + idx * (2 * kWS));
-  fq_from_wire(yP, P + idx * (2 * kWS) + kWS);
+  fq_from_wire_w<W>(xP, P + idx * (2 * W));
+  fq_from_wire_w<W>(yP, P + idx * (2 * W) + W);
   bool ok = cc_on_curve(xP, yP);
   uint32_t k[5];
-  zr_from_wire(k, K + idx * kWZ);
+  zr_from_wire(k, K + idx * c_zr.zlen);
   int top = zr_top_bit(k);
   X = xP;
   Y = yP;
@@ -88,14 +89,14 @@ k_cc_g1_mul(const uint8_t* __restrict__ P, const uint8_t* __restrict__ K, uint8_
   fq_mul(u, u, t);
   fq_mul(Y, Y, u);
   if (inf) { fq_zero(X); fq_zero(Y); }
-  fq_to_wire(out + idx * (2 * kWS), X);
-  fq_to_wire(out + idx * (2 * kWS) + kWS, Y);
+  fq_to_wire_w<W>(out + idx * (2 * W), X);
+  fq_to_wire_w<W>(out + idx * (2 * W) + W, Y);
 }
 
 // element_from_hash on G1 for the five-limb fields (ecc/curve.c:455-482): try-and-increment, the odd
 // square root (q = 3 mod 4: t^((q+1)/4); q = 5 mod 8: Atkin's b = (2t)^((q-5)/8), i = 2 t b^2,
 // root = t b (i - 1)), then the cofactor multiple (d159: h = 3; type f: none).
-template <int BLOCK>
+template <int BLOCK, int W>
 __global__ void __launch_bounds__(BLOCK, PBC_CC_MINBLOCKS)
 k_cc_g1_from_hash(const uint8_t* __restrict__ data, int len, uint8_t* __restrict__ out, size_t n) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -141,8 +142,8 @@ k_cc_g1_from_hash(const uint8_t* __restrict__ data, int len, uint8_t* __restrict
     if (!(c[0] & 1u) && !fp_is_zero<kNS>(c)) fq_neg(y, y);
   }
   if (c_hash.cofbits <= 1) {               // cofactor 1: the point itself
-    fq_to_wire(out + idx * (2 * kWS), x);
-    fq_to_wire(out + idx * (2 * kWS) + kWS, y);
+    fq_to_wire_w<W>(out + idx * (2 * W), x);
+    fq_to_wire_w<W>(out + idx * (2 * W) + W, y);
     return;
   }
   X = x;
@@ -202,22 +203,20 @@ k_cc_g1_from_hash(const uint8_t* __restrict__ data, int len, uint8_t* __restrict
   fq_mul(u, u, t);
   fq_mul(Y, Y, u);
   if (inf) { fq_zero(X); fq_zero(Y); }
-  fq_to_wire(out + idx * (2 * kWS), X);
-  fq_to_wire(out + idx * (2 * kWS) + kWS, Y);
+  fq_to_wire_w<W>(out + idx * (2 * W), X);
+  fq_to_wire_w<W>(out + idx * (2 * W) + W, Y);
 }
 
 // element_from_bytes_compressed on G1 for the five-limb fields (ecc/curve.c:799-813): x (20 bytes) ||
 // sign byte -> x || y.  No square root -> zero bytes.
-template <int BLOCK>
+template <int BLOCK, int W>
 __global__ void __launch_bounds__(BLOCK, PBC_CC_MINBLOCKS)
 k_cc_g1_decompress(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t n) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (idx >= n) return;
-  const uint8_t* p = in + idx * (kWS + 1);
+  const uint8_t* p = in + idx * (W + 1);
   Fq x, y, t, b, u, w, one, k;
-  limbs_from_be_bytes<kNS, kWS>(x.v, p);
-  fq_set(k, c_fp.r2);
-  fq_mul(x, x, k);
+  fq_from_wire_b<W>(x, p);             // items are W + 1 bytes apart: byte loads
   fq_one(one);
   fq_sqr(t, x);
   fq_set(k, c_cc.A);
@@ -245,11 +244,11 @@ k_cc_g1_decompress(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, si
   bool ok = fq_eq(w, t);
   uint32_t c[kNS], o1[kNS] = {1};
   mont_mul_ps<kNS, false>(c, y.v, o1);
-  bool odd = (c[0] & 1u) != 0, want_odd = p[kWS] != 0;
+  bool odd = (c[0] & 1u) != 0, want_odd = p[W] != 0;
   if (odd != want_odd && !fp_is_zero<kNS>(c)) fq_neg(y, y);
   if (!ok) { fq_zero(x); fq_zero(y); }
-  fq_to_wire(out + idx * (2 * kWS), x);
-  fq_to_wire(out + idx * (2 * kWS) + kWS, y);
+  fq_to_wire_w<W>(out + idx * (2 * W), x);
+  fq_to_wire_w<W>(out + idx * (2 * W) + W, y);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -320,6 +319,38 @@ struct KF3 {                       // type d
   }
 };
 
+struct KF5 {                       // type g (19-byte coordinates)
+  typedef F5 El;
+  static constexpr int kWire = 5 * kWG;
+  static __device__ __forceinline__ void mul(El* r, const El* a, const El* b) { f5_mul(r, a, b); }
+  static __device__ __forceinline__ void sqr(El* r, const El* a) { f5_sqr(r, a); }
+  static __device__ __forceinline__ void inv(El* r, const El* a) { f5_inv(r, a); }
+  static __device__ __forceinline__ void add(El& r, const El& a, const El& b) { f5_add(r, a, b); }
+  static __device__ __forceinline__ void sub(El& r, const El& a, const El& b) { f5_sub(r, a, b); }
+  static __device__ __forceinline__ void one(El& r) { f5_zero(r); fq_one(r.c[0]); }
+  static __device__ __forceinline__ bool is_zero(const El& a) {
+    bool z = true;
+#pragma unroll
+    for (int i = 0; i < 5; i++) z = z && fq_is_zero(a.c[i]);
+    return z;
+  }
+  static __device__ __forceinline__ bool eq(const El& a, const El& b) { return f5_eq(a, b); }
+  static __device__ __forceinline__ bool a_is_zero() { return false; }
+  static __device__ __forceinline__ void add_curve_a(El& r) { Fq k; fq_set(k, c_g.twist_a); fq_add(r.c[0], r.c[0], k); }
+  static __device__ __forceinline__ void mul_curve_a(El& r) { Fq k; fq_set(k, c_g.twist_a); f5_scale(r, r, k); }
+  static __device__ __forceinline__ void add_curve_b(El& r) { Fq k; fq_set(k, c_g.twist_b); fq_add(r.c[0], r.c[0], k); }
+  static __device__ __forceinline__ void from_wire(El& r, const uint8_t* p) {
+#pragma unroll 1
+    for (int i = 0; i < 5; i++) fq_from_wire_b<kWG>(r.c[i], p + i * kWG);
+  }
+  static __device__ __forceinline__ void to_wire(uint8_t* p, const El& a, bool zero) {
+    El o = a;
+    if (zero) f5_zero(o);
+#pragma unroll 1
+    for (int i = 0; i < 5; i++) fq_to_wire_b<kWG>(p + i * kWG, o.c[i]);
+  }
+};
+
 // out[i] = k[i] * in[i] on the twist.  One thread per point; all temporaries that are passed by
 // address live at function scope (stack discipline note in pairing_f.cuh).
 template <class KF, int BLOCK>
@@ -339,7 +370,7 @@ k_cc_g2_mul(const uint8_t* __restrict__ P, const uint8_t* __restrict__ K, uint8_
   KF::sqr(&u, &yP);
   bool ok = KF::eq(t, u);
   uint32_t k[5];
-  zr_from_wire(k, K + idx * kWZ);
+  zr_from_wire(k, K + idx * c_zr.zlen);
   int top = zr_top_bit(k);
   X = xP;
   Y = yP;
@@ -414,7 +445,7 @@ k_f_gt_pow(const uint8_t* __restrict__ G, const uint8_t* __restrict__ K, uint8_t
   uint32_t k[5];
   f12_from_wire(base, G + idx * (12 * kWS));
   f12_to_internal(base);
-  zr_from_wire(k, K + idx * kWZ);
+  zr_from_wire(k, K + idx * c_zr.zlen);
   int top = zr_top_bit(k);
   acc = base;
   for (int j = top - 1; j >= 0; j--) {
@@ -438,7 +469,7 @@ k_d_gt_pow(const uint8_t* __restrict__ G, const uint8_t* __restrict__ K, uint8_t
   f6d_from_wire(base, G + idx * (6 * kWS));
   f3_to_internal(base.a);
   f3_to_internal(base.b);
-  zr_from_wire(k, K + idx * kWZ);
+  zr_from_wire(k, K + idx * c_zr.zlen);
   int top = zr_top_bit(k);
   acc = base;
   for (int j = top - 1; j >= 0; j--) {
@@ -449,6 +480,27 @@ k_d_gt_pow(const uint8_t* __restrict__ G, const uint8_t* __restrict__ K, uint8_t
   f3_to_reference(acc.a);
   f3_to_reference(acc.b);
   f6d_to_wire(out + idx * (6 * kWS), acc);
+}
+
+// type g: 190-byte F_q^10 elements
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, PBC_CC_MINBLOCKS)
+k_g_gt_pow(const uint8_t* __restrict__ G, const uint8_t* __restrict__ K, uint8_t* __restrict__ out,
+           size_t n) {
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  F10 base, acc;
+  uint32_t k[5];
+  f10_from_wire(base, G + idx * (10 * kWG));
+  zr_from_wire(k, K + idx * c_zr.zlen);
+  int top = zr_top_bit(k);
+  acc = base;
+  for (int j = top - 1; j >= 0; j--) {
+    f10_sqr(&acc);
+    if ((k[j >> 5] >> (j & 31)) & 1u) f10_mul(&acc, &acc, &base);
+  }
+  if (top < 0) f10_one(acc);
+  f10_to_wire(out + idx * (10 * kWG), acc);
 }
 
 }  // namespace pbcb200

@@ -81,4 +81,36 @@ struct HostF3Field {
   }
 };
 
+// F_q[x]/(x^n + m[n-1] x^(n-1) + ... + m[0]) for any n (type g: n = 5)
+struct HostPolyField {
+  BigUInt q;
+  std::vector<BigUInt> m;
+  typedef std::vector<BigUInt> El;
+  size_t n() const { return m.size(); }
+  El mul(const El& x, const El& y) const {
+    size_t N = n();
+    std::vector<BigUInt> d(2 * N - 1);
+    for (size_t i = 0; i < N; i++)
+      for (size_t j = 0; j < N; j++)
+        d[i + j] = BigUInt::addmod(d[i + j], BigUInt::mulmod(x[i], y[j], q), q);
+    for (size_t k = 2 * N - 2; k >= N; k--) {
+      BigUInt t = d[k];
+      d[k] = BigUInt();
+      for (size_t i = 0; i < N; i++)
+        d[k - N + i] = BigUInt::submod(d[k - N + i], BigUInt::mulmod(t, m[i], q), q);
+    }
+    d.resize(N);
+    return d;
+  }
+  El pow(const El& x, const BigUInt& e) const {
+    El r(n());
+    r[0] = BigUInt(1);
+    for (size_t i = e.bits(); i-- > 0;) {
+      r = mul(r, r);
+      if (e.bit(i)) r = mul(r, x);
+    }
+    return r;
+  }
+};
+
 }  // namespace pbcb200

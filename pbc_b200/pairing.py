@@ -207,6 +207,14 @@ class Pairing:
             raise PairingError(last_error())
         return [int.from_bytes(buf.raw[i:i + width], "big") for i in range(0, got, width)]
 
+    def derived_constant_n(self, name: str, width: int, count: int):
+        """the same for constants with up to `count` entries"""
+        buf = C.create_string_buffer(count * width)
+        got = lib.pbc_b200_derived_constant(self._h, name.encode(), C.addressof(buf), width, len(buf))
+        if got < 0:
+            raise PairingError(last_error())
+        return [int.from_bytes(buf.raw[i:i + width], "big") for i in range(0, got, width)]
+
     def set_stage_profiling(self, on: bool):
         if lib.pbc_b200_set_stage_profiling(self._h, 1 if on else 0):
             raise PairingError(last_error())

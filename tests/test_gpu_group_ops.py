@@ -11,7 +11,8 @@ from pbc_b200.params import PARAMS
 pytestmark = pytest.mark.gpu
 
 VARIANTS = {"a": ("a", ""), "f": ("f", ""), "f_refbasis": ("f", "b200_reference_basis 1\n"), "d159": ("d159", ""),
-            "d159_refbasis": ("d159", "b200_reference_basis 1\n")}
+            "d159_refbasis": ("d159", "b200_reference_basis 1\n"),
+            "g149": ("g149", "")}
 
 
 @pytest.fixture(scope="module", params=sorted(VARIANTS))
@@ -26,7 +27,7 @@ def _cat(xs):
 
 
 def test_zr_length(env):
-    assert env["dev"].zr_len == env["g"]["lengths"]["zr"] == 20
+    assert env["dev"].zr_len == env["g"]["lengths"]["zr"] == (env["orc"].r.bit_length() + 7) // 8
 
 
 def test_g1_pow_reference_fixtures(env):
@@ -43,10 +44,10 @@ def test_g1_pow_matches_oracle_edge_scalars(env):
          [rnd.randrange(r) for _ in range(28)]
     n = len(ks)
     pts = [bytes.fromhex(g["pairing"]["P"][i % len(g["pairing"]["P"])]) for i in range(n)]
-    got = d.g1_pow_zn(b"".join(pts), b"".join(k.to_bytes(20, "big") for k in ks), n)
+    got = d.g1_pow_zn(b"".join(pts), b"".join((k % (1 << (8 * d.zr_len))).to_bytes(d.zr_len, "big") for k in ks), n)
     L = d.g1_len
     for i, (k, pb) in enumerate(zip(ks, pts)):
-        R = orc.G1.mul(k % r, orc.G1.from_bytes(pb))
+        R = orc.G1.mul((k % (1 << (8 * d.zr_len))) % r, orc.G1.from_bytes(pb))
         want = bytes(L) if R is None else orc.G1.to_bytes(R)
         assert got[i * L:(i + 1) * L] == want, "scalar %d" % i
 
@@ -54,7 +55,7 @@ def test_g1_pow_matches_oracle_edge_scalars(env):
 def test_g1_pow_offcurve_is_infinity_and_empty(env):
     g, d = env["g"], env["dev"]
     bad = bytes.fromhex(g["offcurve"]["badP"])
-    assert d.g1_pow_zn(bad, (7).to_bytes(20, "big"), 1) == bytes(d.g1_len)
+    assert d.g1_pow_zn(bad, (7).to_bytes(d.zr_len, "big"), 1) == bytes(d.g1_len)
     assert d.g1_pow_zn(b"", b"", 0) == b""
 
 
@@ -72,10 +73,11 @@ def test_gt_pow_matches_oracle_edge_scalars(env):
     ks = [0, 1, 2, r - 1, r, r + 3, 1 << 159, 0xFFFFFFFF00000000] + [rnd.randrange(r) for _ in range(8)]
     n = len(ks)
     es = [bytes.fromhex(g["pairing"]["e"][i % len(g["pairing"]["e"])]) for i in range(n)]
-    got = d.gt_pow_zn(b"".join(es), b"".join(k.to_bytes(20, "big") for k in ks), n)
+    got = d.gt_pow_zn(b"".join(es), b"".join((k % (1 << (8 * d.zr_len))).to_bytes(d.zr_len, "big") for k in ks), n)
     L = d.gt_len
     for i, (k, eb) in enumerate(zip(ks, es)):
-        want = orc.GT.to_bytes(orc.GT.pow(orc.GT.from_bytes(eb), k % r)) if k % r else orc.GT.to_bytes(orc.GT.one)
+        kk = (k % (1 << (8 * d.zr_len))) % r
+        want = orc.GT.to_bytes(orc.GT.pow(orc.GT.from_bytes(eb), kk)) if kk else orc.GT.to_bytes(orc.GT.one)
         assert got[i * L:(i + 1) * L] == want, "scalar %d" % i
 
 
@@ -84,7 +86,7 @@ def test_pow_then_pair_is_bilinear_on_device(env):
     g, d = env["g"], env["dev"]
     rnd = random.Random(23)
     n = 8
-    ks = b"".join(rnd.randrange(1, env["orc"].r).to_bytes(20, "big") for _ in range(n))
+    ks = b"".join(rnd.randrange(1, env["orc"].r).to_bytes(d.zr_len, "big") for _ in range(n))
     P, Q = _cat(g["pairing"]["P"][:n]), _cat(g["pairing"]["Q"][:n])
     lhs = d.apply(d.g1_pow_zn(P, ks, n), Q, n)
     rhs = d.gt_pow_zn(d.apply(P, Q, n), ks, n)
@@ -105,14 +107,14 @@ def test_g2_pow_matches_oracle_edge_scalars(env):
     ks = [0, 1, 2, 3, r - 1, r, r + 5, 1 << 159, 0xFFFFFFFF] + [rnd.randrange(r) for _ in range(7)]
     n = len(ks)
     pts = [bytes.fromhex(g["pairing"]["Q"][i % len(g["pairing"]["Q"])]) for i in range(n)]
-    got = d.g2_pow_zn(b"".join(pts), b"".join(k.to_bytes(20, "big") for k in ks), n)
+    got = d.g2_pow_zn(b"".join(pts), b"".join((k % (1 << (8 * d.zr_len))).to_bytes(d.zr_len, "big") for k in ks), n)
     L = d.g2_len
     for i, (k, pb) in enumerate(zip(ks, pts)):
-        R = orc.G2.mul(k % r, orc.G2.from_bytes(pb))
+        R = orc.G2.mul((k % (1 << (8 * d.zr_len))) % r, orc.G2.from_bytes(pb))
         want = bytes(L) if R is None else orc.G2.to_bytes(R)
         assert got[i * L:(i + 1) * L] == want, "scalar %d" % i
     bad = bytes.fromhex(g["offcurve"]["badQ"])
-    assert d.g2_pow_zn(bad, (5).to_bytes(20, "big"), 1) == bytes(L)
+    assert d.g2_pow_zn(bad, (5).to_bytes(d.zr_len, "big"), 1) == bytes(L)
 
 
 def test_both_arguments_powered_on_device(env):
@@ -151,7 +153,7 @@ def test_bls_style_verification_entirely_on_device(env):
     g, d, orc = env["g"], env["dev"], env["orc"]
     n = 6
     rnd = random.Random(41)
-    sk = rnd.randrange(1, orc.r).to_bytes(20, "big")
+    sk = rnd.randrange(1, orc.r).to_bytes(d.zr_len, "big")
     g2 = bytes.fromhex(g["pairing"]["Q"][0])
     pk = d.g2_pow_zn(g2, sk, 1)
     msgs = b"".join(hashlib.sha256(b"bls-%d" % i).digest() for i in range(n))
@@ -160,7 +162,7 @@ def test_bls_style_verification_entirely_on_device(env):
     lhs = d.apply(sig, g2 * n, n)
     rhs = d.apply(H, pk * n, n)
     assert lhs == rhs
-    forged = d.g1_pow_zn(H, (int.from_bytes(sk, "big") ^ 1).to_bytes(20, "big") * n, n)
+    forged = d.g1_pow_zn(H, (int.from_bytes(sk, "big") ^ 1).to_bytes(d.zr_len, "big") * n, n)
     assert d.apply(forged, g2 * n, n) != rhs
 
 

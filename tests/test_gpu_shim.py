@@ -20,7 +20,7 @@ def _need(name):
     return path
 
 
-@pytest.mark.parametrize("name", ["a", "f", "d159"])
+@pytest.mark.parametrize("name", ["a", "f", "d159", "g149"])
 def test_pbc_api_on_gpu_matches_reference_vtable(tmp_path, name):
     exe = _need("shim_test")
     pf = tmp_path / (name + ".param")
@@ -39,7 +39,7 @@ def test_reference_benchmark_program_links_unchanged_and_runs_on_gpu(tmp_path):
     assert "BUG" not in r.stdout and "average pairing time" in r.stdout
 
 
-@pytest.mark.parametrize("name", ["a", "f", "d159"])
+@pytest.mark.parametrize("name", ["a", "f", "d159", "g149"])
 def test_plain_c_caller_of_the_c_abi(tmp_path, name, golden):
     """examples/batch_pairing_demo.c: a C program that includes only include/pbc_b200.h"""
     exe = os.path.join(ROOT, "examples", "_build", "batch_pairing_demo")
@@ -55,7 +55,7 @@ def test_plain_c_caller_of_the_c_abi(tmp_path, name, golden):
     assert (tmp_path / "E.bin").read_bytes() == b"".join(bytes.fromhex(x) for x in g["e"])
 
 
-@pytest.mark.parametrize("name", ["a", "f", "d159"])
+@pytest.mark.parametrize("name", ["a", "f", "d159", "g149"])
 def test_bls_batch_verify_example(name):
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "bls_batch_verify.py"), name, "96"],

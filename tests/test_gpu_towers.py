@@ -121,3 +121,40 @@ def test_f6d_ops(d_env, op):
         else:
             r = (F3.inv(x[0]), F3.zero)
         assert got[i * L:(i + 1) * L] == F6.to_bytes(r), "op %d element %d" % (op, i)
+
+
+@pytest.fixture(scope="module")
+def g_env():
+    from pbc_b200.pairing import Pairing
+    return Pairing(PARAMS["g149"]), O.pairing_from_param(PARAMS["g149"])
+
+
+@pytest.mark.parametrize("op", [5, 6, 0, 1, 2, 3])
+def test_f10_ops(g_env, op):
+    """F_q^5 / F_q^10 of type g (19-byte coordinates) vs the oracle"""
+    dev, orc = g_env
+    rnd = random.Random(300 + op)
+    q = orc.q
+    n = 6 if op == 3 else 32
+    A = [[rnd.randrange(q) for _ in range(10)] for _ in range(n)]
+    B = [[rnd.randrange(q) for _ in range(10)] for _ in range(n)]
+    A[0] = [1] + [0] * 9
+    enc = lambda es: b"".join(b"".join(c.to_bytes(19, "big") for c in e) for e in es)
+    got = dev.tower_op(op, enc(A), enc(B), n)
+    F5, F10 = orc.Fq5, orc.Fq10
+    L = orc.gt_len
+    for i, (a, b) in enumerate(zip(A, B)):
+        x, y = (tuple(a[:5]), tuple(a[5:])), (tuple(b[:5]), tuple(b[5:]))
+        if op == 0:
+            r = F10.mul(x, y)
+        elif op == 1:
+            r = F10.sqr(x)
+        elif op == 2:
+            r = F10.inv(x)
+        elif op == 3:
+            r = orc.tatepower(x)
+        elif op == 5:
+            r = (F5.mul(x[0], y[0]), F5.zero)
+        else:
+            r = (F5.inv(x[0]), F5.zero)
+        assert got[i * L:(i + 1) * L] == F10.to_bytes(r), "op %d element %d" % (op, i)

@@ -167,3 +167,27 @@ def test_internal_cubic_basis_constants_match_prototype(built):
     assert tuple(ref.derived_constant("xpowq_in_use", 20)) == od.xpowq
     with pytest.raises(built.PairingError):
         ref.derived_constant("basis_cubic", 20)
+
+
+def test_type_g_init_and_constants(built):
+    """g_init_pairing (ecc/g_param.c:1248-1353): sizes, the reduction rows x^5..x^8, the Frobenius
+    constants x^q..x^(4q) and (q^4 - q^3 + q^2 - q + 1)/r vs the oracle."""
+    from pbc_b200.params import PARAMS
+    from oracle import pbc_oracle as O
+    g, og = built.Pairing(PARAMS["g149"]), O.pairing_from_param(PARAMS["g149"])
+    assert (g.type, g.g1_len, g.g2_len, g.gt_len, g.zr_len) == ("g", 38, 190, 190, 19)
+    F5 = og.Fq5
+    x = (0, 1, 0, 0, 0)
+    xp = F5.pow(x, 5)
+    want = []
+    for _ in range(4):
+        want.extend(xp)
+        xp = F5.mul(xp, x)
+    assert g.derived_constant_n("xpwr", 19, 20) == want
+    want = []
+    for i in range(1, 5):
+        want.extend(og.xpowq[i])
+    assert g.derived_constant_n("xpowq", 19, 20) == want
+    assert g.derived_constant("phikonr", 64) == [og.phikonr]
+    with pytest.raises(built.PairingError, match="k = "):
+        built.Pairing(PARAMS["g149"].replace("\nk 10\n", "\nk 12\n"))
