@@ -52,9 +52,10 @@ __device__ __forceinline__ void hash_to_words(uint32_t* x, const uint8_t* data, 
 #pragma unroll
   for (int w = 0; w < NW; w++) {
     uint32_t v = 0;
-    if (4 * w < count) {
-      const uint8_t* b = buf + count - 4 - 4 * w;
-      v = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      int pos = count - 1 - (4 * w + b);       // byte of weight 256^(4w+b); count need not be a multiple of 4
+      if (pos >= 0) v |= (uint32_t)buf[pos] << (8 * b);
     }
     x[w] = v;
   }

@@ -61,15 +61,13 @@ __device__ __forceinline__ bool f5_eq(const F5& x, const F5& y) {
   return e;
 }
 // multiplication by an element of F_q
-__device__ __noinline__ void f5_scale_call(F5* r, const F5* x, const Fq* k) {
-  Fq kk = *k;
+// (the scalar travels by value: an inlined helper must not take the address of one of its own
+// locals -- stack discipline note in pairing_f.cuh)
+__device__ __noinline__ void f5_scale_call(F5* r, const F5* x, Fq k) {
 #pragma unroll 1
-  for (int i = 0; i < 5; i++) fq_mul(r->c[i], x->c[i], kk);
+  for (int i = 0; i < 5; i++) fq_mul(r->c[i], x->c[i], k);
 }
-__device__ __forceinline__ void f5_scale(F5& r, const F5& x, const Fq& k) {
-  Fq kk = k;
-  f5_scale_call(&r, &x, &kk);
-}
+__device__ __forceinline__ void f5_scale(F5& r, const F5& x, const Fq& k) { f5_scale_call(&r, &x, k); }
 
 // x y: schoolbook, the nine coefficients of the product accumulated double-width, the four high
 // ones reduced and folded in with the rows x^5 .. x^8, one reduction per output coefficient.
