@@ -57,6 +57,10 @@ WORKLOADS = {
               exec_unit_ops_main=None, cpu_rate=350.0, port_rate=10.0,
               name="type D (param/d159.param, MNT k=6) element_pairing, batch 2^18 pairs per GPU, 159-bit F_q",
               dtype="u32 limbs (5 x 32-bit = 160-bit F_q, exact integer)", kernels=("k_d_miller", "-", "k_d_finalexp")),
+    "g": dict(param="g149", mode="single", k=1, n=1 << 18, unit=78, ref_mulmods=None, ref_main=None,
+              exec_unit_ops_main=None, cpu_rate=110.0, port_rate=3.0,
+              name="type G (param/g149.param, Freeman k=10) element_pairing, batch 2^18 pairs per GPU, 149-bit F_q",
+              dtype="u32 limbs (5 x 32-bit = 160-bit F_q, exact integer)", kernels=("k_g_miller", "-", "k_g_finalexp")),
     "prod16": dict(param="a", mode="prod", k=16, n=1 << 16, unit=528, ref_mulmods=41536, ref_main=41536 - 719,
                    exec_unit_ops_main=16 * (1616 * 528 + 1121 * 408), cpu_rate=130.0, port_rate=8.0,
                    name="type A element_prod_pairing n=16, 2^16 outputs (2^20 Miller loops) over all GPUs",
@@ -68,7 +72,7 @@ WORKLOADS = {
                dtype="u32 limbs (16 x 32-bit = 512-bit F_q, exact integer)",
                kernels=("k_a_pp_init+k_a_pp_apply", "k_batch_invert", "k_a_finalexp")),
 }
-WIRE = {"a": (128, 128, 128), "f": (40, 80, 240), "d159": (40, 120, 120)}
+WIRE = {"a": (128, 128, 128), "f": (40, 80, 240), "d159": (40, 120, 120), "g149": (38, 190, 190)}
 
 
 def make_inputs(w, n_out, offset_out=0):
@@ -424,11 +428,11 @@ def main():
             # types f, d: SURVEY 8(d) gives the reference's mulmod count for the whole pairing only,
             # so the roofline is taken over the whole kernel sequence (Miller + final exponentiation)
             kern, kms = "+".join(x for x in w["kernels"] if x != "-"), sum(stage)
-            ach_ref = n * w["ref_mulmods"] * unit / (kms * 1e-3)
+            ach_ref = n * (w["ref_mulmods"] or 0) * unit / (kms * 1e-3)
             ach_exec = None
-            work = ("reference-equivalent %d mulmods x %d unit ops per pairing over the whole kernel sequence; "
-                    "dominant kernel %s = %.0f%% of the step" % (w["ref_mulmods"], unit, w["kernels"][dom],
-                                                                 100 * stage[dom] / max(sum(stage), 1e-9)))
+            work = ("reference-equivalent %s mulmods x %d unit ops per pairing over the whole kernel sequence "
+                    "(None: SURVEY has no probe for this type, frac is 0); dominant kernel %s = %.0f%% of the step"
+                    % (w["ref_mulmods"], unit, w["kernels"][dom], 100 * stage[dom] / max(sum(stage), 1e-9)))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -453,7 +457,7 @@ def main():
         if ach_exec is not None:
             roof["achieved_executed"] = ach_exec / 1e12
             roof["frac_executed"] = ach_exec / peak
-        ws_per = 576 * k if w["param"] == "a" else (61 * 4 if w["param"] == "f" else 31 * 4)
+        ws_per = 576 * k if w["param"] == "a" else {"f": 61 * 4, "d159": 31 * 4, "g149": 51 * 4}[w["param"]]
         line = {
             "metric": "pairings/sec", "value": value, "unit": unit_name, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,

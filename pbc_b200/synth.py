@@ -193,13 +193,15 @@ class _ExtCurve:
         return K.mul(y, y) == K.add(K.mul(K.add(K.mul(x, x), self.a), x), self.b)
 
 
-def _dec(K, bs, width=20):
+def _dec(K, bs, width=None):
     n = K.n
+    width = width or len(bs) // (2 * n)
     xs = [int.from_bytes(bs[i * width:(i + 1) * width], "big") for i in range(2 * n)]
     return (tuple(xs[:n]), tuple(xs[n:]))
 
 
 def _enc(P, width=20):
+    # width = bytes per F_q coordinate (20 for f.param / d159.param, 19 for g149.param)
     return b"".join(c.to_bytes(width, "big") for c in P[0]) + b"".join(c.to_bytes(width, "big") for c in P[1])
 
 
@@ -223,10 +225,12 @@ def type_fd_points(param: dict, seeds_g1, seeds_g2, g: int):
         E2 = _ExtCurve(K2, K2.zero, K2.mul(xi, K2.embed(param["b"])))
     else:
         E1 = _ExtCurve(Fq, Fq.embed(param["a"]), Fq.embed(param["b"]))
-        K2 = _ExtField(q, [param["coeff0"], param["coeff1"], param["coeff2"]])
+        ncoef = 5 if param["type"] == "g" else 3
+        K2 = _ExtField(q, [param["coeff%d" % i] for i in range(ncoef)])
         v = param["nqr"] % q
         E2 = _ExtCurve(K2, K2.embed(param["a"] * v * v), K2.embed(param["b"] * v * v * v))
     P0, G = (_dec(Fq, s) for s in seeds_g1[:2])
     Q0, H = (_dec(K2, s) for s in seeds_g2[:2])
     assert all(E1.on_curve(p) for p in (P0, G)) and all(E2.on_curve(p) for p in (Q0, H))
-    return [_enc(p) for p in _walk(E1, P0, G, g)], [_enc(p) for p in _walk(E2, Q0, H, g)]
+    wb = (q.bit_length() + 7) // 8
+    return [_enc(p, wb) for p in _walk(E1, P0, G, g)], [_enc(p, wb) for p in _walk(E2, Q0, H, g)]
