@@ -99,7 +99,39 @@ __device__ __noinline__ void f5_mul(F5* r, const F5* x, const F5* y) {
   }
   *r = o;
 }
-__device__ __forceinline__ void f5_sqr(F5* r, const F5* x) { f5_mul(r, x, x); }
+// x^2: the 10 cross products once and doubled, the 5 squares, then the same folding (15 + 20 products)
+__device__ __noinline__ void f5_sqr(F5* r, const F5* x) {
+  FqW d[9], t;
+  Fq hi[4], k;
+  F5 o;
+#pragma unroll 1
+  for (int s = 0; s < 9; s++) {
+    bool first = true;
+#pragma unroll 1
+    for (int i = (s < 5 ? 0 : s - 4); 2 * i < s; i++) {          // i < s - i
+      t = fq_mulw_call(x->c[i], x->c[s - i]);
+      if (first) { d[s] = t; first = false; } else fqw_add(d[s], d[s], t);
+    }
+    if (!first) fqw_add(d[s], d[s], d[s]);
+    if ((s & 1) == 0) {
+      t = fq_mulw_call(x->c[s / 2], x->c[s / 2]);
+      if (first) { d[s] = t; first = false; } else fqw_add(d[s], d[s], t);
+    }
+  }
+#pragma unroll 1
+  for (int s = 0; s < 4; s++) hi[s] = fq_redc_call(d[5 + s]);
+#pragma unroll 1
+  for (int i = 0; i < 5; i++) {
+#pragma unroll 1
+    for (int s = 0; s < 4; s++) {
+      fq_set(k, c_g.xpwr[s][i]);
+      t = fq_mulw_call(hi[s], k);
+      fqw_add(d[i], d[i], t);
+    }
+    o.c[i] = fq_redc_call(d[i]);
+  }
+  *r = o;
+}
 
 // (sum c_i x^i)^q = c0 + sum_{i >= 1} c_i x^(iq)   (ecc/g_param.c:483-493)
 __device__ __noinline__ void f5_frob(F5* r, const F5* x) {
@@ -317,6 +349,7 @@ __device__ __noinline__ void f10_final_exp(F5& out0, F5& out1, F10& f) {
   v0 = two;
   v1 = t1;
   for (int j = (int)c_g.phibits - 1; j >= 0; j--) {
+    if (PBC_CC_LOCKSTEP) __syncthreads();        // uniform ladder: keep the block's warps in step
     bool bit = j > 0 && ((c_g.phikonr[j >> 5] >> (j & 31)) & 1u);   // last step: clear branch
     f5_mul(&tmp, &v0, &v1);
     f5_sub(tmp, tmp, t1);
@@ -345,17 +378,19 @@ __device__ __noinline__ void f10_final_exp(F5& out0, F5& out1, F10& f) {
 
 // out: n x 190 bytes: real half (5 coefficients) then imaginary half
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, PBC_CC_MINBLOCKS)
+__global__ void __launch_bounds__(BLOCK, (PBC_CC_MINBLOCKS * 128) / BLOCK)
 k_g_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
              uint8_t* __restrict__ out, size_t n) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (idx >= n) return;
   F10 f;
   F5 out0, out1;
-  if (flag[idx]) {
-    f10_ld_global(f, mv, n, idx);
-    f10_final_exp(out0, out1, f);
-  } else {
+  const bool ok = flag[idx] != 0;
+  // every thread runs the ladder (block-wide barriers inside); flagged-off entries power 1
+  f10_ld_global(f, mv, n, idx);
+  if (!ok) f10_one(f);
+  f10_final_exp(out0, out1, f);
+  if (!ok) {
     f5_zero(out0);
     f5_zero(out1);
     fq_one(out0.c[0]);
