@@ -99,8 +99,18 @@ __device__ __noinline__ void f5_mul(F5* r, const F5* x, const F5* y) {
   }
   *r = o;
 }
+// Two things that did not pay here (profiles/r1_variants_g_finalexp.jsonl): a dedicated squaring with the
+// ten cross products doubled (15 + 20 products but more code: -4%) and the lock-step barrier in the Lucas
+// ladder (-3%); both stay behind switches.
+#ifndef PBC_G_SQR
+#define PBC_G_SQR 0
+#endif
+#ifndef PBC_G_FINAL_LOCKSTEP
+#define PBC_G_FINAL_LOCKSTEP 0
+#endif
 // x^2: the 10 cross products once and doubled, the 5 squares, then the same folding (15 + 20 products)
 __device__ __noinline__ void f5_sqr(F5* r, const F5* x) {
+  if (!PBC_G_SQR) { f5_mul(r, x, x); return; }
   FqW d[9], t;
   Fq hi[4], k;
   F5 o;
@@ -349,7 +359,7 @@ __device__ __noinline__ void f10_final_exp(F5& out0, F5& out1, F10& f) {
   v0 = two;
   v1 = t1;
   for (int j = (int)c_g.phibits - 1; j >= 0; j--) {
-    if (PBC_CC_LOCKSTEP) __syncthreads();        // uniform ladder: keep the block's warps in step
+    if (PBC_CC_LOCKSTEP && PBC_G_FINAL_LOCKSTEP) __syncthreads();   // uniform ladder: keep the block's warps in step
     bool bit = j > 0 && ((c_g.phikonr[j >> 5] >> (j & 31)) & 1u);   // last step: clear branch
     f5_mul(&tmp, &v0, &v1);
     f5_sub(tmp, tmp, t1);
