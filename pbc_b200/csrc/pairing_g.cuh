@@ -109,8 +109,8 @@ __device__ __noinline__ void f5_mul(F5* r, const F5* x, const F5* y) {
 #define PBC_G_FINAL_LOCKSTEP 0
 #endif
 // x^2: the 10 cross products once and doubled, the 5 squares, then the same folding (15 + 20 products)
+#if PBC_G_SQR
 __device__ __noinline__ void f5_sqr(F5* r, const F5* x) {
-  if (!PBC_G_SQR) { f5_mul(r, x, x); return; }
   FqW d[9], t;
   Fq hi[4], k;
   F5 o;
@@ -142,6 +142,9 @@ __device__ __noinline__ void f5_sqr(F5* r, const F5* x) {
   }
   *r = o;
 }
+#else
+__device__ __forceinline__ void f5_sqr(F5* r, const F5* x) { f5_mul(r, x, x); }
+#endif
 
 // (sum c_i x^i)^q = c0 + sum_{i >= 1} c_i x^(iq)   (ecc/g_param.c:483-493)
 __device__ __noinline__ void f5_frob(F5* r, const F5* x) {
