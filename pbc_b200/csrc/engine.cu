@@ -51,6 +51,15 @@ static int fail(const char* fmt, ...) {
       return fail("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
   } while (0)
 
+// device allocation released at scope exit (the test hooks allocate per call; an early error
+// return must not leak)
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
 static std::atomic<uint64_t> g_launches{0};
 #define LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
 
@@ -1316,13 +1325,14 @@ k_fp_op(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a, const 
   limbs_to_be<N, WB>(out + idx * WB, x);
 }
 // same hook for the five-limb field of types f and d
+template <int W>
 __global__ void k_fq_op(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a,
                         const uint8_t* __restrict__ b, size_t n) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   Fq x, y;
-  fq_from_wire(x, a + idx * kWS);
-  fq_from_wire(y, b + idx * kWS);
+  fq_from_wire_w<W>(x, a + idx * W);
+  fq_from_wire_w<W>(y, b + idx * W);
   switch (op) {
     case 0: fq_mul(x, x, y); break;
     case 1: fq_add(x, x, y); break;
@@ -1333,7 +1343,7 @@ __global__ void k_fq_op(int op, uint8_t* __restrict__ out, const uint8_t* __rest
     case 6: fq_sqr(x, x); break;
     case 7: fq_mul(x, x, y); fq_sub(x, x, y); break;
   }
-  fq_to_wire(out + idx * kWS, x);
+  fq_to_wire_w<W>(out + idx * W, x);
 }
 
 // dependent chain of five-limb Montgomery multiplications (mode 0) / squarings (mode 1)
@@ -1351,30 +1361,31 @@ __global__ void k_fqmul_chain(uint32_t* __restrict__ out, const uint32_t* __rest
 
 extern "C" int pbc_b200_fp_op(pbc_b200_pairing_t* p, int op, unsigned char* out,
                               const unsigned char* a, const unsigned char* b, size_t n) {
-  if (!p) return fail("null argument");
-  if (p->type == 'g') return fail("fp_op: not wired for the 19-byte coordinates of type g (the field code is type d's)");
+  if (!p || (n && (!out || !a))) return fail("null argument");
   if (n == 0) return 0;
   int dev = 0;
   CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> dev_lock(g_dev_mu[dev & 63]);
   if (ctx_prepare(p, dev)) return 1;
-  int wb = p->type == 'a' ? 64 : 20;
-  uint8_t *da, *db, *dout;
-  CUDA_OK(cudaMalloc(&da, n * wb));
-  CUDA_OK(cudaMalloc(&db, n * wb));
-  CUDA_OK(cudaMalloc(&dout, n * wb));
-  CUDA_OK(cudaMemcpy(da, a, n * wb, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(db, b ? b : a, n * wb, cudaMemcpyHostToDevice));
+  size_t wb = (size_t)p->g1_len / 2;             // bytes per F_q coordinate: 64, 20 or 19
+  DevBuf da, db, dout;
+  CUDA_OK(da.alloc(n * wb));
+  CUDA_OK(db.alloc(n * wb));
+  CUDA_OK(dout.alloc(n * wb));
+  CUDA_OK(cudaMemcpy(da.p, a, n * wb, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(db.p, b ? b : a, n * wb, cudaMemcpyHostToDevice));
   unsigned g = (unsigned)((n + 127) / 128);
   if (p->type == 'a') {
     CUDA_OK(allow_smem(k_fp_op<kNA, true, 64, 128>, 4 * 64 * 128));
-    k_fp_op<kNA, true, 64, 128><<<g, 128, 4 * 64 * 128>>>(op, dout, da, db, n);
+    k_fp_op<kNA, true, 64, 128><<<g, 128, 4 * 64 * 128>>>(op, dout.as<uint8_t>(), da.as<uint8_t>(), db.as<uint8_t>(), n);
+  } else if (p->type == 'g') {
+    k_fq_op<kWG><<<g, 128>>>(op, dout.as<uint8_t>(), da.as<uint8_t>(), db.as<uint8_t>(), n);
   } else {
-    k_fq_op<<<g, 128>>>(op, dout, da, db, n);
+    k_fq_op<kWS><<<g, 128>>>(op, dout.as<uint8_t>(), da.as<uint8_t>(), db.as<uint8_t>(), n);
   }
   LAUNCHED();
   CUDA_OK(cudaDeviceSynchronize());
-  CUDA_OK(cudaMemcpy(out, dout, n * wb, cudaMemcpyDeviceToHost));
-  cudaFree(da); cudaFree(db); cudaFree(dout);
+  CUDA_OK(cudaMemcpy(out, dout.p, n * wb, cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -1389,19 +1400,18 @@ extern "C" int pbc_b200_tower_op(pbc_b200_pairing_t* p, int op, unsigned char* o
   CUDA_OK(cudaGetDevice(&dev));
   if (ctx_prepare(p, dev)) return 1;
   size_t wb = (size_t)p->gt_len;
-  uint8_t *da, *db, *dout;
-  CUDA_OK(cudaMalloc(&da, n * wb));
-  CUDA_OK(cudaMalloc(&db, n * wb));
-  CUDA_OK(cudaMalloc(&dout, n * wb));
-  CUDA_OK(cudaMemcpy(da, a, n * wb, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(db, b ? b : a, n * wb, cudaMemcpyHostToDevice));
+  DevBuf da, db, dout;
+  CUDA_OK(da.alloc(n * wb));
+  CUDA_OK(db.alloc(n * wb));
+  CUDA_OK(dout.alloc(n * wb));
+  CUDA_OK(cudaMemcpy(da.p, a, n * wb, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(db.p, b ? b : a, n * wb, cudaMemcpyHostToDevice));
   unsigned g = (unsigned)((n + 63) / 64);
-  if (p->type == 'f') k_f_tower_op<<<g, 64>>>(op, dout, da, db, n);
-  else if (p->type == 'g') k_g_tower_op<<<g, 64>>>(op, dout, da, db, n);
-  else k_d_tower_op<<<g, 64>>>(op, dout, da, db, n);
+  if (p->type == 'f') k_f_tower_op<<<g, 64>>>(op, dout.as<uint8_t>(), da.as<uint8_t>(), db.as<uint8_t>(), n);
+  else if (p->type == 'g') k_g_tower_op<<<g, 64>>>(op, dout.as<uint8_t>(), da.as<uint8_t>(), db.as<uint8_t>(), n);
+  else k_d_tower_op<<<g, 64>>>(op, dout.as<uint8_t>(), da.as<uint8_t>(), db.as<uint8_t>(), n);
   LAUNCHED();
   CUDA_OK(cudaDeviceSynchronize());
-  CUDA_OK(cudaMemcpy(out, dout, n * wb, cudaMemcpyDeviceToHost));
-  cudaFree(da); cudaFree(db); cudaFree(dout);
+  CUDA_OK(cudaMemcpy(out, dout.p, n * wb, cudaMemcpyDeviceToHost));
   return 0;
 }

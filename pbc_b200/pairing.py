@@ -187,7 +187,7 @@ class Pairing:
 
     # -- test / bench hooks -----------------------------------------------------------------------
     def fp_op(self, op: int, a: bytes, b, n: int) -> bytes:
-        wb = 64 if self.type == "a" else 20
+        wb = self.g1_len // 2          # bytes per F_q coordinate
         out = C.create_string_buffer(n * wb)
         if lib.pbc_b200_fp_op(self._h, op, C.addressof(out), _addr(a), _addr(b), n):
             raise PairingError(last_error())
