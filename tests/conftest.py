@@ -20,4 +20,4 @@ def load_golden(name):
 
 @pytest.fixture(scope="session")
 def golden():
-    return {n: load_golden(n) for n in ("a", "f", "d159", "g149")}
+    return {n: load_golden(n) for n in ("a", "f", "d159", "g149", "a1")}

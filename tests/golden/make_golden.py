@@ -19,8 +19,8 @@ from oracle import ref as R  # noqa: E402
 from pbc_b200.params import PARAMS  # noqa: E402
 
 SEED = 20260922
-N_SINGLE = {"a": 24, "f": 12, "d159": 16, "g149": 12}
-PROD = {"a": (4, 3), "f": (3, 2), "d159": (4, 3), "g149": (3, 2)}  # (k, n_out)
+N_SINGLE = {"a": 24, "f": 12, "d159": 16, "g149": 12, "a1": 8}
+PROD = {"a": (4, 3), "f": (3, 2), "d159": (4, 3), "g149": (3, 2), "a1": (3, 2)}  # (k, n_out)
 
 
 def chunks(b, n):
@@ -71,6 +71,22 @@ def main():
                     "e_Pa_Qa": chunks(Eaa, rp.gt_len)},
             "offcurve": {"badP": badP.hex(), "badQ": badQ.hex(), "identity": e_badP.hex()},
         }
+        # element_from_hash on G1 (ecc/curve.c:455-482) for a few input lengths
+        import random
+        rnd = random.Random(SEED)
+        doc["hash"] = {}
+        for ln in (20, 32, 70, 3):
+            data = [bytes(rnd.randrange(256) for _ in range(ln)) for _ in range(6)]
+            H = rp.from_hash(R.G1, b"".join(data), ln, len(data))
+            doc["hash"][str(ln)] = {"data": [d.hex() for d in data], "G1": chunks(H, rp.g1_len)}
+        # element_to_bytes_compressed / element_from_bytes_compressed (ecc/curve.c:762-813)
+        nc = min(8, n)
+        comp = rp.compress(R.G1, P[:nc * rp.g1_len], nc)
+        clen = len(comp) // nc
+        flipped = b"".join(comp[i * clen:(i + 1) * clen - 1] + bytes([comp[(i + 1) * clen - 1] ^ 1])
+                           for i in range(nc))
+        doc["compressed"] = {"len": clen, "G1": chunks(comp, clen),
+                             "G1_flipped_sign": chunks(rp.decompress(R.G1, flipped, nc), rp.g1_len)}
         with open(os.path.join(ROOT, "tests", "golden", name + ".json"), "w") as f:
             json.dump(doc, f, indent=0)
         print(name, "ok")

@@ -49,7 +49,7 @@ def test_kat_prod_and_pp_agree(pa):
     assert e2 == pa.Fq2.mul(KAT_E_GH, KAT_RES)
 
 
-@pytest.mark.parametrize("name,limit", [("a", 24), ("d159", 8), ("f", 3), ("g149", 4)])
+@pytest.mark.parametrize("name,limit", [("a", 24), ("d159", 8), ("f", 3), ("g149", 4), ("a1", 3)])
 def test_oracle_matches_reference_fixtures(golden, name, limit):
     g = golden[name]
     pr = O.pairing_from_param(PARAMS[name])
@@ -58,7 +58,7 @@ def test_oracle_matches_reference_fixtures(golden, name, limit):
         assert O.pairing_bytes(pr, bytes.fromhex(P), bytes.fromhex(Q)).hex() == e
 
 
-@pytest.mark.parametrize("name,limit", [("a", 3), ("d159", 2), ("f", 1)])
+@pytest.mark.parametrize("name,limit", [("a", 3), ("d159", 2), ("f", 1), ("a1", 1)])
 def test_oracle_prod_matches_reference_fixtures(golden, name, limit):
     g = golden[name]["prod"]
     pr = O.pairing_from_param(PARAMS[name])
@@ -69,7 +69,7 @@ def test_oracle_prod_matches_reference_fixtures(golden, name, limit):
         assert O.prod_pairing_bytes(pr, Ps, Qs).hex() == e
 
 
-@pytest.mark.parametrize("name", ["a", "d159", "f"])
+@pytest.mark.parametrize("name", ["a", "d159", "f", "a1"])
 def test_oracle_offcurve_is_identity(golden, name):
     g = golden[name]
     pr = O.pairing_from_param(PARAMS[name])
@@ -82,7 +82,7 @@ def test_oracle_offcurve_is_identity(golden, name):
 
 
 def test_pp_fixture_equals_plain_pairing(golden):
-    for name in ("a", "d159", "f"):
+    for name in ("a", "d159", "f", "a1"):
         g = golden[name]
         assert g["pp"]["e"] == g["pairing"]["e"][:1] + g["pp"]["e"][1:]  # first Q pairs with P[0]
 
@@ -99,9 +99,19 @@ def test_from_hash_restatement_matches_reference_fixtures(golden):
     oracle's restatement vs G1 elements the compiled reference derived from the same bytes."""
     from oracle import pbc_oracle as O
     from pbc_b200.params import PARAMS
-    for name in ("a", "f", "d159", "g149"):
+    for name in ("a", "f", "d159", "g149", "a1"):
         orc = O.pairing_from_param(PARAMS[name])
         for ln, blk in golden[name]["hash"].items():
             for d, want in zip(blk["data"], blk["G1"]):
                 assert len(d) == 2 * int(ln)
                 assert orc.G1.to_bytes(O.g1_from_hash(orc, bytes.fromhex(d))).hex() == want
+
+
+def test_type_a1_pp_restatement_matches_reference_fixture(golden):
+    """a1_pairing_pp_init / _apply (ecc/a_param.c:1632-1818, tangent and chord merged into one
+    conic per set bit of n) restated in the oracle vs the compiled reference's pp outputs."""
+    g = golden["a1"]
+    pr = O.pairing_from_param(PARAMS["a1"])
+    P0 = pr.G1.from_bytes(bytes.fromhex(g["pp"]["P"]))
+    for Q, e in list(zip(g["pairing"]["Q"], g["pp"]["e"]))[:2]:
+        assert pr.GT.to_bytes(pr.pp_pairing(P0, pr.G2.from_bytes(bytes.fromhex(Q)))).hex() == e
