@@ -22,6 +22,7 @@
 #include "host_bigint.hpp"
 #include "host_fields.hpp"
 #include "pairing_a.cuh"
+#include "pairing_a1.cuh"
 #include "pairing_d.cuh"
 #include "pairing_f.cuh"
 #include "pairing_g.cuh"
@@ -104,12 +105,14 @@ struct DevCtx {
 };
 
 struct pbc_b200_pairing_s {
-  int type = 0;                // 'a', 'f', 'd'
+  int type = 0;                // 'a', 'f', 'd', 'g'; '1' = a1
   int g1_len = 0, g2_len = 0, gt_len = 0;
   int nlimbs = 0;
   bool full = false;
   FpConsts fp;
   AConsts a;
+  A1Consts a1;
+  size_t a1_rows = 0;          // rows of the fixed-argument line table (3 per tangent / chord)
   CCConsts cc;
   FConsts f;
   DConsts d;
@@ -154,6 +157,13 @@ struct Job {
 
 // workspace bytes for n_out outputs of `job`
 static size_t ws_bytes(const pbc_b200_pairing_s* p, const Job& job, size_t n_out) {
+  if (p->type == '1') {
+    // f [2], dprod, prefix per output; Miller inputs add f [2], d and the Montgomery P [2]
+    const size_t fq = (size_t)kNA1 * 4;
+    if (job.mode == kSingle) return n_out * (2 + 1 + 1 + 2) * fq;
+    if (job.mode == kProd) return n_out * job.k * (2 + 1 + 2) * fq + n_out * (2 + 1 + 1) * fq;
+    return n_out * (2 + 1 + 1) * fq + (p->a1_rows * kNA1 + 4) * 4;
+  }
   if (p->type == 'a') {
     const size_t fq = 64;
     if (job.mode == kSingle) return n_out * (2 + 1 + 1 + 5) * fq;
@@ -202,6 +212,7 @@ static bool get_int(const std::map<std::string, std::string>& tab, const char* k
 }
 
 static void fill_hash(pbc_b200_pairing_s* p, const BigUInt& q, const BigUInt& cofac);
+static void to_mont(uint32_t* out, const BigUInt& x, const BigUInt& q, int n);
 
 static int init_type_a(pbc_b200_pairing_s* p, const std::map<std::string, std::string>& tab) {
   BigUInt q, r, h;
@@ -229,6 +240,43 @@ static int init_type_a(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   fill_hash(p, q, h);                      // G1 cofactor = h (ecc/a_param.c:1451)
   BigUInt R = BigUInt(1).shl(512);
   ((R * BigUInt(2)) % q).to_words(p->a.two, kNA);
+  return 0;
+}
+
+// Type A1 (a1_init_pairing, ecc/a_param.c:2230-2273; parameters p, n, l with p = l n - 1)
+static int init_type_a1(pbc_b200_pairing_s* p, const std::map<std::string, std::string>& tab) {
+  BigUInt q, n;
+  int l;
+  if (!get_big(tab, "p", &q) || !get_big(tab, "n", &n) || !get_int(tab, "l", &l)) return 1;
+  if (q.bits() > 32 * (size_t)kNA1 - 1) return fail("type a1: this build supports p below 2^%d (got %zu bits)", 32 * kNA1 - 1, q.bits());
+  if (q.bits() < 64) return fail("type a1: p too small");
+  if (q.word(0) % 4 != 3) return fail("type a1: p must be 3 mod 4");
+  if (l <= 0 || (l & 1)) return fail("type a1: l must be positive and even");
+  if (!((n * BigUInt((uint64_t)l)) == (q + BigUInt(1)))) return fail("type a1: l*n != p+1");
+  if (n.bits() < 3) return fail("type a1: n too small");
+  p->type = '1';
+  memset(&p->zr, 0, sizeof p->zr);
+  p->zr.zlen = (uint32_t)((n.bits() + 7) / 8);
+  p->zr_len = (int)p->zr.zlen;
+  p->nlimbs = kNA1;
+  p->full = false;
+  int wb = (int)((q.bits() + 7) / 8);
+  p->g1_len = p->g2_len = p->gt_len = 2 * wb;
+  fill_fp_consts(&p->fp, q, kNA1);
+  A1Consts& c = p->a1;
+  memset(&c, 0, sizeof c);
+  n.to_words(c.n, kNA1);
+  c.nbits = (uint32_t)n.bits();
+  BigUInt L((uint64_t)l);
+  L.to_words(c.l, 2);
+  c.lbits = (uint32_t)L.bits();
+  c.wb = (uint32_t)wb;
+  to_mont(c.two, BigUInt(2), q, kNA1);
+  // one tangent per loop step, one chord per set bit strictly between the top bit and bit 0
+  size_t lines = n.bits() - 1;
+  for (size_t m = 1; m + 1 < n.bits(); m++) lines += n.bit(m) ? 1 : 0;
+  p->a1_rows = 3 * lines;
+  p->hash_ok = false;
   return 0;
 }
 
@@ -625,6 +673,17 @@ static constexpr size_t kSmemAProd = (size_t)kAPSlots * 64 * kBlockProd;
 static constexpr size_t kSmemAPPInit = (size_t)kASlots * 64 * 32;
 static constexpr size_t kSmemAPPApply = (size_t)kAPPSlots * 64 * kBlockMiller;
 
+// type a1: 34-limb slots (136 bytes per thread and slot)
+static constexpr int kBlockA1 = 96;            // 14 slots * 136 B * 96 threads = 178.5 KB of shared memory
+static constexpr int kBlockA1Small = 128;      // kernels with at most 9 slots
+static constexpr size_t kSlotA1 = (size_t)kNA1 * 4;
+static constexpr size_t kSmemA1Miller = (size_t)kASlots * kSlotA1 * kBlockA1;
+static constexpr size_t kSmemA1Final = (size_t)kA1FinalSlots * kSlotA1 * kBlockA1Small;
+static constexpr size_t kSmemA1Prod = (size_t)kA1ProdSlots * kSlotA1 * kBlockA1Small;
+static constexpr size_t kSmemA1PP = (size_t)kA1PPSlots * kSlotA1 * kBlockA1Small;
+static constexpr size_t kSmemA1PPInit = (size_t)kASlots * kSlotA1 * 32;
+static constexpr size_t kSmemInv34 = (size_t)5 * kSlotA1 * kBlockA1Small;
+
 static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
   if ((int)p->ctx.size() <= dev) p->ctx.resize(dev + 1);
   DevCtx& c = p->ctx[dev];
@@ -646,6 +705,15 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
       CUDA_OK(allow_smem(k_a_g1_from_hash<kBlockMiller>, (size_t)kGSlots * 64 * kBlockMiller));
       CUDA_OK(allow_smem(k_a_g1_decompress<kBlockMiller>, (size_t)5 * 64 * kBlockMiller));
     }
+    if (p->type == '1') {
+      CUDA_OK(allow_smem(k_a1_miller<kBlockA1>, kSmemA1Miller));
+      CUDA_OK(allow_smem(k_a1_finalexp<kBlockA1Small>, kSmemA1Final));
+      CUDA_OK(allow_smem(k_a1_prod<kBlockA1Small>, kSmemA1Prod));
+      CUDA_OK(allow_smem(k_a1_pp_init<32>, kSmemA1PPInit));
+      CUDA_OK(allow_smem(k_a1_pp_apply<kBlockA1Small>, kSmemA1PP));
+      CUDA_OK(allow_smem(k_batch_invert<kNA1, false, kBlockA1Small>, kSmemInv34));
+      CUDA_OK(allow_smem(k_a1_fp_op<kBlockA1Small>, (size_t)4 * kSlotA1 * kBlockA1Small));
+    }
     c.ready = true;
   }
   // make this handle's constants resident on the device
@@ -654,6 +722,7 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
     CUDA_OK(cudaDeviceSynchronize());
     CUDA_OK(cudaMemcpyToSymbol(c_fp, &p->fp, sizeof(FpConsts)));
     if (p->type == 'a') CUDA_OK(cudaMemcpyToSymbol(c_a, &p->a, sizeof(AConsts)));
+    if (p->type == '1') CUDA_OK(cudaMemcpyToSymbol(c_a1, &p->a1, sizeof(A1Consts)));
     CUDA_OK(cudaMemcpyToSymbol(c_zr, &p->zr, sizeof(ZrConsts)));
     CUDA_OK(cudaMemcpyToSymbol(c_hash, &p->hash, sizeof(HashConsts)));
     if (p->type == 'f' || p->type == 'd' || p->type == 'g') CUDA_OK(cudaMemcpyToSymbol(c_cc, &p->cc, sizeof(CCConsts)));
@@ -687,6 +756,58 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
                             cudaEvent_t* ev = nullptr) {
   if (n == 0) return 0;
 #define STAGE(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
+  if (p->type == '1') {
+    // limb-major arrays of 34-limb elements: E = 17 uint2 vectors per element
+    const size_t E = kNA1 / 2;
+    uint2 *f, *dprod, *prefix;
+    const size_t wire = (size_t)p->g1_len;
+    STAGE(0);
+    if (job.mode == kSingle) {
+      f = (uint2*)ws;                            // [2][E][n]
+      dprod = f + 2 * E * n;                     // [E][n]
+      prefix = dprod + E * n;                    // [E][n]
+      uint2* pm = prefix + E * n;                // [2][E][n]
+      unsigned gm = (unsigned)((n + kBlockA1 - 1) / kBlockA1);
+      k_a1_miller<kBlockA1><<<gm, kBlockA1, kSmemA1Miller, st>>>(d_in1, d_in2, f, dprod, pm, n, wire);
+      LAUNCHED();
+    } else if (job.mode == kProd) {
+      size_t m = n * job.k;
+      uint2* fi = (uint2*)ws;                    // [2][E][m]
+      uint2* di = fi + 2 * E * m;                // [E][m]
+      uint2* pm = di + E * m;                    // [2][E][m]
+      f = pm + 2 * E * m;                        // [2][E][n]
+      dprod = f + 2 * E * n;
+      prefix = dprod + E * n;
+      unsigned gm = (unsigned)((m + kBlockA1 - 1) / kBlockA1);
+      k_a1_miller<kBlockA1><<<gm, kBlockA1, kSmemA1Miller, st>>>(d_in1, d_in2, fi, di, pm, m, wire);
+      LAUNCHED();
+      unsigned gp = (unsigned)((n + kBlockA1Small - 1) / kBlockA1Small);
+      k_a1_prod<kBlockA1Small><<<gp, kBlockA1Small, kSmemA1Prod, st>>>(fi, di, f, dprod, job.k, n, m);
+      LAUNCHED();
+    } else {
+      f = (uint2*)ws;
+      dprod = f + 2 * E * n;
+      prefix = dprod + E * n;
+      uint32_t* tab = (uint32_t*)(prefix + E * n);
+      k_a1_pp_init<32><<<1, 32, kSmemA1PPInit, st>>>(d_in1, tab, p->a1_rows);
+      LAUNCHED();
+      unsigned gm = (unsigned)((n + kBlockA1Small - 1) / kBlockA1Small);
+      k_a1_pp_apply<kBlockA1Small><<<gm, kBlockA1Small, kSmemA1PP, st>>>(tab, d_in2, f, dprod, n, p->a1_rows);
+      LAUNCHED();
+    }
+    STAGE(1);
+    size_t T = n < (size_t)148 * 128 ? n : (size_t)148 * 128;
+    unsigned gi = (unsigned)((T + kBlockA1Small - 1) / kBlockA1Small);
+    k_batch_invert<kNA1, false, kBlockA1Small><<<gi, kBlockA1Small, kSmemInv34, st>>>(dprod, prefix, n, T);
+    LAUNCHED();
+    STAGE(2);
+    unsigned gf = (unsigned)((n + kBlockA1Small - 1) / kBlockA1Small);
+    k_a1_finalexp<kBlockA1Small><<<gf, kBlockA1Small, kSmemA1Final, st>>>(f, dprod, d_out, n);
+    LAUNCHED();
+    STAGE(3);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (p->type == 'a') {
     uint4 *f, *dprod, *prefix;
     STAGE(0);
@@ -890,10 +1011,11 @@ int pbc_b200_pairing_init_set_buf(pbc_b200_pairing_t** out, const char* param, s
   p->force_reference_basis = tab.count("b200_reference_basis") && tab["b200_reference_basis"] != "0";
   p->force_generic_final_exp = tab.count("b200_generic_final_exp") && tab["b200_generic_final_exp"] != "0";
   if (it->second == "a") rc = init_type_a(p, tab);
+  else if (it->second == "a1") rc = init_type_a1(p, tab);
   else if (it->second == "f") rc = init_type_f(p, tab);
   else if (it->second == "d") rc = init_type_d(p, tab);
   else if (it->second == "g") rc = init_type_g(p, tab);
-  else rc = fail("pairing type `%s' is not on the B200 hot path (supported: a, d with k = 6, f, g)", it->second.c_str());
+  else rc = fail("pairing type `%s' is not on the B200 hot path (supported: a, a1, d with k = 6, f, g)", it->second.c_str());
   if (rc) { delete p; return 1; }
   *out = p;
   return 0;
@@ -1009,6 +1131,7 @@ void pbc_b200_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
 // ---- roofline probes ----
 double pbc_b200_bench_fpmul(pbc_b200_pairing_t* p, int mode, int blocks, int iters, int reps) {
   if (!p) { fail("null argument"); return -1; }
+  if (p->type == '1') { fail("bench_fpmul: not built for type a1"); return -1; }
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || ctx_prepare(p, dev)) return -1;
   const int threads = 128;
@@ -1125,6 +1248,7 @@ static int enqueue_group(pbc_b200_pairing_s* p, int which /*0 = G1, 1 = GT, 2 = 
 static int run_group(pbc_b200_pairing_s* p, int which, unsigned char* out, const unsigned char* in,
                      const unsigned char* k, size_t n, bool device, void* stream) {
   if (!p || (n && (!out || !in || !k))) return fail("null argument");
+  if (p->type == '1') return fail("element_pow_zn: not built for type a1 yet (pairings, products and fixed-argument pairings are)");
   if (n == 0) return 0;
   std::lock_guard<std::mutex> lk(p->mu);
   int dev = 0;
@@ -1190,6 +1314,7 @@ int pbc_b200_gt_pow_zn_device(pbc_b200_pairing_t* p, void* d_out, const void* d_
 static int run_from_hash(pbc_b200_pairing_s* p, unsigned char* out, const unsigned char* data, size_t len, size_t n,
                          bool device, void* stream) {
   if (!p || (n && (!out || !data))) return fail("null argument");
+  if (p->type == '1') return fail("element_from_hash: not built for type a1 yet");
   if (!p->hash_ok) return fail("element_from_hash: needs q = 3 mod 4 or q = 5 mod 8 and a cofactor below 2^384");
   if (len == 0 || len > (1u << 20)) return fail("element_from_hash: hash length must be 1..2^20 bytes");
   if (n == 0) return 0;
@@ -1258,6 +1383,7 @@ extern "C" int pbc_b200_pairing_length_in_bytes_compressed_G1(const pbc_b200_pai
 extern "C" int pbc_b200_g1_from_bytes_compressed(pbc_b200_pairing_t* p, unsigned char* out, const unsigned char* in,
                                                  size_t n) {
   if (!p || (n && (!out || !in))) return fail("null argument");
+  if (p->type == '1') return fail("element_from_bytes_compressed: not built for type a1 yet");
   if (!p->hash_ok) return fail("element_from_bytes_compressed: needs q = 3 mod 4 or q = 5 mod 8");
   if (n == 0) return 0;
   std::lock_guard<std::mutex> lk(p->mu);
@@ -1367,7 +1493,7 @@ extern "C" int pbc_b200_fp_op(pbc_b200_pairing_t* p, int op, unsigned char* out,
   CUDA_OK(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> dev_lock(g_dev_mu[dev & 63]);
   if (ctx_prepare(p, dev)) return 1;
-  size_t wb = (size_t)p->g1_len / 2;             // bytes per F_q coordinate: 64, 20 or 19
+  size_t wb = (size_t)p->g1_len / 2;             // bytes per F_q coordinate: 64, 20, 19 or ceil(bits(p)/8)
   DevBuf da, db, dout;
   CUDA_OK(da.alloc(n * wb));
   CUDA_OK(db.alloc(n * wb));
@@ -1375,7 +1501,9 @@ extern "C" int pbc_b200_fp_op(pbc_b200_pairing_t* p, int op, unsigned char* out,
   CUDA_OK(cudaMemcpy(da.p, a, n * wb, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(db.p, b ? b : a, n * wb, cudaMemcpyHostToDevice));
   unsigned g = (unsigned)((n + 127) / 128);
-  if (p->type == 'a') {
+  if (p->type == '1') {
+    k_a1_fp_op<kBlockA1Small><<<g, kBlockA1Small, (size_t)4 * kSlotA1 * kBlockA1Small>>>(op, dout.as<uint8_t>(), da.as<uint8_t>(), db.as<uint8_t>(), n);
+  } else if (p->type == 'a') {
     CUDA_OK(allow_smem(k_fp_op<kNA, true, 64, 128>, 4 * 64 * 128));
     k_fp_op<kNA, true, 64, 128><<<g, 128, 4 * 64 * 128>>>(op, dout.as<uint8_t>(), da.as<uint8_t>(), db.as<uint8_t>(), n);
   } else if (p->type == 'g') {

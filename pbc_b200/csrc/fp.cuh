@@ -20,7 +20,7 @@
 
 namespace pbcb200 {
 
-constexpr int kMaxLimbs = 16;
+constexpr int kMaxLimbs = 36;     // type a1 uses 34; 36 keeps every field 16-byte aligned
 
 struct FpConsts {
   uint32_t p[kMaxLimbs];     // modulus

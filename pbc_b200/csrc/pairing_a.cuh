@@ -15,6 +15,7 @@
 // Pipeline per batch:  k_a_miller -> k_batch_invert -> k_a_finalexp.
 #pragma once
 #include "slots.cuh"
+#include "a_steps.cuh"
 
 namespace pbcb200 {
 
@@ -36,22 +37,6 @@ __constant__ AConsts c_a;
 constexpr int kNA = 16;        // 32-bit limbs of the 512-bit prime
 constexpr int kWA = 64;        // wire bytes per coordinate
 
-// slot map of the Miller kernel
-enum ASlot { aX, aY, aZ, aZ2, aF0, aF1, aQX, aQY, aT0, aT1, aT2, aT3, aT4, aT5, kASlots };
-
-// f *= (L0 + i L1), Karatsuba (arith/fieldquadratic.c:425-457 fi_mul), temporaries t0..t2
-template <class O>
-__device__ __forceinline__ void a_fmul(int f0, int f1, int l0, int l1, int t0, int t1, int t2) {
-  O::add(t0, f0, f1);
-  O::add(t1, l0, l1);
-  O::mul(t0, t0, t1);
-  O::mul(t1, f0, l0);
-  O::mul(t2, f1, l1);
-  O::sub(f0, t1, t2);
-  O::sub(t0, t0, t1);
-  O::sub(f1, t0, t2);
-}
-
 // Loads P and Q (wire format), converts to Montgomery form, validates y^2 = x^3 + x
 // (ecc/curve.c:57-76, :611-623: off-curve input becomes O).  Returns false for O.
 template <class O>
@@ -69,46 +54,6 @@ __device__ __forceinline__ bool a_load_point(int sx, int sy, int st0, int st1, c
   O::mul(st0, st0, sx);       // x^3 + x
   O::sqr(st1, sy);
   return O::eq(st0, st1);
-}
-
-// One Miller doubling step:  f <- f^2 * l_{V,V}(phi(Q)),  V <- 2V   (Jacobian, a = 1).
-// 13 multiplications + 6 squarings (reference: 23 multiplications, ecc/a_param.c:1082-1139).
-template <class O>
-__device__ __forceinline__ void a_double_step() {
-  // f = f^2  (arith/fieldquadratic.c:459-477)
-  O::add(aT0, aF0, aF1);
-  O::sub(aT1, aF0, aF1);
-  O::mul(aF1, aF0, aF1);
-  O::dbl(aF1, aF1);
-  O::mul(aF0, aT0, aT1);
-  // M = 3 X^2 + Z^4
-  O::sqr(aT0, aX);
-  O::sqr(aT1, aZ2);
-  O::dbl(aT2, aT0);
-  O::add(aT0, aT0, aT2);
-  O::add(aT0, aT0, aT1);
-  O::sqr(aT1, aY);                 // Y^2
-  O::mul(aT2, aX, aT1);
-  O::dbl(aT2, aT2, 2);             // S = 4 X Y^2
-  O::mul(aT3, aT0, aZ2);           // M Z^2
-  O::mul(aT4, aT3, aQX);
-  O::mul(aT5, aX, aT0);
-  O::sub(aT5, aT5, aT1);
-  O::sub(aT5, aT5, aT1);
-  O::add(aT4, aT4, aT5);           // Re l = X M - 2 Y^2 + M Z^2 Qx
-  O::mul(aZ, aY, aZ);
-  O::dbl(aZ, aZ);                  // Z' = 2 Y Z
-  O::mul(aT3, aZ, aZ2);
-  O::mul(aT3, aT3, aQY);           // Im l = Z' Z^2 Qy
-  O::sqr(aZ2, aZ);
-  O::sqr(aT5, aT0);
-  O::sub(aX, aT5, aT2);
-  O::sub(aX, aX, aT2);             // X' = M^2 - 2 S
-  O::sqr(aT1, aT1);
-  O::dbl(aT1, aT1, 3);             // 8 Y^4
-  O::sub(aT2, aT2, aX);
-  O::mulsub(aY, aT0, aT2, aT1);    // Y' = M (S - X') - 8 Y^4
-  a_fmul<O>(aF0, aF1, aT4, aT3, aT0, aT1, aT2);
 }
 
 // The step in weight-(1,2) coordinates x = X/Z, y = Y/Z^2 (the doubling of Costello, Lange and

@@ -44,7 +44,8 @@ class Pairing:
         self.g1_len = lib.pbc_b200_pairing_length_in_bytes_G1(self._h)
         self.g2_len = lib.pbc_b200_pairing_length_in_bytes_G2(self._h)
         self.gt_len = lib.pbc_b200_pairing_length_in_bytes_GT(self._h)
-        self.type = chr(lib.pbc_b200_pairing_type(self._h))
+        t = chr(lib.pbc_b200_pairing_type(self._h))
+        self.type = "a1" if t == "1" else t
         self.zr_len = lib.pbc_b200_pairing_length_in_bytes_Zr(self._h)
 
     def clear(self):

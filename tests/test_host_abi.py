@@ -191,3 +191,17 @@ def test_type_g_init_and_constants(built):
     assert g.derived_constant("phikonr", 64) == [og.phikonr]
     with pytest.raises(built.PairingError, match="k = "):
         built.Pairing(PARAMS["g149"].replace("\nk 10\n", "\nk 12\n"))
+
+
+def test_type_a1_parameters_are_accepted_and_checked(built):
+    """a1_init_pairing (ecc/a_param.c:2230-2273): p, n, l with p = l n - 1; lengths follow p"""
+    from pbc_b200.params import PARAMS
+    p = built.Pairing(PARAMS["a1"])
+    assert (p.type, p.g1_len, p.g2_len, p.gt_len, p.zr_len) == ("a1", 260, 260, 260, 128)
+    with pytest.raises(built.PairingError, match="l\\*n != p\\+1"):
+        built.Pairing(PARAMS["a1"].replace("l 1340", "l 1344"))
+    with pytest.raises(built.PairingError, match="missing param"):
+        built.Pairing("\n".join(l for l in PARAMS["a1"].splitlines() if not l.startswith("n ")))
+    small = "type a1\np 153016138656427115508745024995162897686141683994003\nn 1416816098670621439895787268473730534130941518463\nl 108\n"
+    q = built.Pairing(small)
+    assert (q.g1_len, q.gt_len, q.zr_len) == (42, 42, 20)
