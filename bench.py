@@ -72,14 +72,31 @@ WORKLOADS = {
                dtype="u32 limbs (16 x 32-bit = 512-bit F_q, exact integer)",
                kernels=("k_a_pp_init+k_a_pp_apply", "k_batch_invert", "k_a_finalexp")),
 }
-WIRE = {"a": (128, 128, 128), "f": (40, 80, 240), "d159": (40, 120, 120), "g149": (38, 190, 190)}
+def _a1_exec_ops():
+    """unit ops k_a1_miller executes per pairing: 13 M + 6 S per bit of n, 16 M + 3 S per chord;
+    M = 2*34^2 + 34 (operand scanning), S = 34*35/2 + 34^2 + 34 (product scanning) IMAD.WIDE.U32"""
+    n = synth.parse_param(PARAMS["a1"])["n"]
+    steps = n.bit_length() - 1
+    chords = bin(n >> 1).count("1") - 1
+    M, S = 2 * 34 * 34 + 34, 34 * 35 // 2 + 34 * 34 + 34
+    return steps * (13 * M + 6 * S) + chords * (16 * M + 3 * S)
+
+
+WORKLOADS["a1"] = dict(
+    param="a1", mode="single", k=1, n=148 * 96 * 2, unit=2 * 34 * 34 + 34, ref_mulmods=None, ref_main=None,
+    exec_unit_ops_main=_a1_exec_ops(), cpu_rate=48.0, port_rate=6.0,
+    name="type A1 (param/a1.param, 1033-bit p, 1022-bit composite-order-capable n) element_pairing, "
+         "batch 2 x 148 x 96 pairs per GPU",
+    dtype="u32 limbs (34 x 32-bit, 1033-bit F_p, exact integer)",
+    kernels=("k_a1_miller", "k_batch_invert", "k_a1_finalexp"))
+WIRE = {"a1": (260, 260, 260), "a": (128, 128, 128), "f": (40, 80, 240), "d159": (40, 120, 120), "g149": (38, 190, 190)}
 
 
 def make_inputs(w, n_out, offset_out=0):
     """(P, Q) numpy uint8 arrays for outputs offset_out .. offset_out+n_out-1 of workload w."""
     prm = synth.parse_param(PARAMS[w["param"]])
-    if w["param"] == "a":
-        Pb, Qb = synth.type_a_points(prm, GRID, SEED)
+    if w["param"] in ("a", "a1"):
+        Pb, Qb = synth.type_a_points(prm, GRID if w["param"] == "a" else 512, SEED)
     else:
         g = json.load(open(os.path.join(ROOT, "tests", "golden", w["param"] + ".json")))["pairing"]
         Pb, Qb = synth.type_fd_points(prm, [bytes.fromhex(x) for x in g["P"][:2]],
@@ -424,6 +441,11 @@ def main():
             ach_exec = n * w["exec_unit_ops_main"] / (kms * 1e-3) if w["exec_unit_ops_main"] else None
             work = ("reference-equivalent %d mulmods x %d unit ops per output in this kernel; executed %s unit ops"
                     % (w["ref_main"], unit, w["exec_unit_ops_main"]))
+        elif w["exec_unit_ops_main"]:
+            # no reference probe for this type: the roofline is the work the Miller kernel executes
+            kern, kms = w["kernels"][0], stage[0]
+            ach_ref = ach_exec = n * w["exec_unit_ops_main"] / (kms * 1e-3)
+            work = "executed %d unit ops per output in this kernel (no reference mulmod probe for this type)" % w["exec_unit_ops_main"]
         else:
             # types f, d: SURVEY 8(d) gives the reference's mulmod count for the whole pairing only,
             # so the roofline is taken over the whole kernel sequence (Miller + final exponentiation)
@@ -457,7 +479,7 @@ def main():
         if ach_exec is not None:
             roof["achieved_executed"] = ach_exec / 1e12
             roof["frac_executed"] = ach_exec / peak
-        ws_per = 576 * k if w["param"] == "a" else {"f": 61 * 4, "d159": 31 * 4, "g149": 51 * 4}[w["param"]]
+        ws_per = 576 * k if w["param"] == "a" else {"f": 61 * 4, "d159": 31 * 4, "g149": 51 * 4, "a1": 6 * 136}[w["param"]]
         line = {
             "metric": "pairings/sec", "value": value, "unit": unit_name, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,

@@ -79,7 +79,7 @@ PBC_STEP void a_double_step() {
 //   H = xP Z^2 - X,  R = yP Z^3 - Y
 //   a = -R,  b = H Z (= Z of the sum),  c = yP Z X - xP Y;   l(phi(Q)) = (c - a Qx) + i (b Qy)
 //   X3 = R^2 - H^3 - 2 X H^2,  Y3 = R (X H^2 - X3) - Y H^3,  Z3 = b
-// 17 multiplications + 4 squarings including the f update.  Temporaries: aT0..aT3 and aZ2.
+// 16 multiplications + 3 squarings including the f update.  Temporaries: aT0..aT3 and aZ2.
 template <class O>
 PBC_STEP void a1_chord_add(int sPX, int sPY) {
   O::mul(aT0, aZ2, aZ);            // Z^3

@@ -58,8 +58,10 @@ class _Curve:
 
 
 def type_a_points(param: dict, g: int, seed: int):
-    """2 x g distinct points of the order-r subgroup of y^2 = x^3 + x (Type A, G1 = G2)."""
-    q, h = param["q"], param["h"]
+    """2 x g distinct points of the order-r subgroup of y^2 = x^3 + x (Type A, G1 = G2; Type A1
+    with its keys p, l in place of q, h)."""
+    q, h = (param["p"], param["l"]) if param.get("type") == "a1" else (param["q"], param["h"])
+    wb = (q.bit_length() + 7) // 8
     E = _Curve(q, 1, 0)
     rnd = random.Random(seed)
 
@@ -78,7 +80,7 @@ def type_a_points(param: dict, g: int, seed: int):
 
     Ps = walk(subgroup_point(), subgroup_point())
     Qs = walk(subgroup_point(), subgroup_point())
-    enc = lambda pt: pt[0].to_bytes(64, "big") + pt[1].to_bytes(64, "big")
+    enc = lambda pt: pt[0].to_bytes(wb, "big") + pt[1].to_bytes(wb, "big")
     return [enc(p) for p in Ps], [enc(p) for p in Qs]
 
 
