@@ -488,7 +488,7 @@ def main():
             "config": {"workload": w["name"], "param": w["param"] + ".param", "batch_per_gpu": n,
                        "global_batch": world * n, "pairings_per_output": k,
                        "parallelism": "shard%d (independent outputs, no collective)" % world,
-                       "inputs": "%dx%d grid of seeded subgroup points, all pairs distinct" % (GRID, GRID),
+                       "inputs": "%dx%d grid of seeded subgroup points, all pairs distinct" % ((GRID, GRID) if w["param"] != "a1" else (512, 512)),
                        "l2": "inputs+outputs+workspace %.0f MB per step vs 126 MB L2"
                              % ((n * (k * (g1 + g2) + gt + ws_per)) / 1e6)},
             "clocks": clocks,
