@@ -111,6 +111,83 @@ PBC_STEP void a1_chord_add(int sPX, int sPY) {
   O::sqr(aZ2, aZ);
 }
 
+// ---- the same two steps with five temporaries (aT0..aT4) -------------------------------------
+// Re-ordered so that aT5 is never touched: 13 slots instead of 14, which at 136 bytes per slot is
+// the difference between 96 and 128 threads per block for the 34-limb field (one warp per
+// scheduler instead of three warps on four).  Same operations, same values.
+template <class O>
+PBC_STEP void a_double_step_5t() {
+  // f = f^2
+  O::add(aT0, aF0, aF1);
+  O::sub(aT1, aF0, aF1);
+  O::mul(aF1, aF0, aF1);
+  O::dbl(aF1, aF1);
+  O::mul(aF0, aT0, aT1);
+  O::sqr(aT0, aX);
+  O::sqr(aT1, aZ2);
+  O::dbl(aT2, aT0);
+  O::add(aT0, aT0, aT2);
+  O::add(aT0, aT0, aT1);           // M = 3 X^2 + Z^4
+  O::sqr(aT1, aY);                 // Y^2
+  O::mul(aT4, aT0, aZ2);
+  O::mul(aT4, aT4, aQX);           // M Z^2 Qx
+  O::mul(aT3, aX, aT0);
+  O::sub(aT3, aT3, aT1);
+  O::sub(aT3, aT3, aT1);
+  O::add(aT4, aT4, aT3);           // Re l = X M - 2 Y^2 + M Z^2 Qx
+  O::mul(aT2, aX, aT1);
+  O::dbl(aT2, aT2, 2);             // S = 4 X Y^2   (last use of the old X)
+  O::mul(aZ, aY, aZ);
+  O::dbl(aZ, aZ);                  // Z' = 2 Y Z    (last use of the old Y)
+  O::mul(aT3, aZ, aZ2);
+  O::mul(aT3, aT3, aQY);           // Im l = Z' Z^2 Qy
+  O::sqr(aZ2, aZ);
+  O::sqr(aX, aT0);
+  O::sub(aX, aX, aT2);
+  O::sub(aX, aX, aT2);             // X' = M^2 - 2 S
+  O::sqr(aT1, aT1);
+  O::dbl(aT1, aT1, 3);             // 8 Y^4
+  O::sub(aT2, aT2, aX);
+  O::mul(aY, aT0, aT2);
+  O::sub(aY, aY, aT1);             // Y' = M (S - X') - 8 Y^4
+  a_fmul<O>(aF0, aF1, aT4, aT3, aT0, aT1, aT2);
+}
+// P is fetched through `ldP(slot, coordinate)` (0 = x, 1 = y) when it is needed: x into aT4, y into
+// the Z^2 slot once Z^2 has had its last use; the point addition is finished before the f update
+// so that the update finds three free temporaries.
+template <class O, class LoadP>
+PBC_STEP void a1_chord_add_5t(LoadP ldP) {
+  ldP(aT4, 0);                     // xP
+  O::mul(aT0, aZ2, aZ);            // Z^3
+  O::mul(aT1, aT4, aZ2);
+  O::sub(aT1, aT1, aX);            // H            (last use of Z^2)
+  ldP(aZ2, 1);                     // yP
+  O::mul(aT0, aZ2, aT0);           // yP Z^3
+  O::sub(aT2, aY, aT0);            // a = Y - yP Z^3
+  O::sub(aT0, aT0, aY);            // R
+  O::mul(aT3, aZ2, aZ);
+  O::mul(aT3, aT3, aX);            // yP Z X
+  O::mul(aT4, aT4, aY);            // xP Y
+  O::sub(aT3, aT3, aT4);           // c
+  O::mul(aZ, aT1, aZ);             // b = H Z = Z of the sum
+  O::mul(aT2, aT2, aQX);
+  O::sub(aT2, aT3, aT2);           // Re l = c - a Qx
+  O::mul(aT4, aZ, aQY);            // Im l = b Qy
+  O::sqr(aT3, aT1);                // H^2
+  O::mul(aZ2, aT3, aT1);           // H^3
+  O::mul(aT3, aT3, aX);            // X H^2
+  O::sqr(aX, aT0);
+  O::sub(aX, aX, aZ2);
+  O::sub(aX, aX, aT3);
+  O::sub(aX, aX, aT3);             // X3
+  O::sub(aT3, aT3, aX);
+  O::mul(aT3, aT3, aT0);           // R (X H^2 - X3)
+  O::mul(aZ2, aZ2, aY);            // Y H^3
+  O::sub(aY, aT3, aZ2);            // Y3
+  a_fmul<O>(aF0, aF1, aT2, aT4, aT0, aT1, aT3);
+  O::sqr(aZ2, aZ);
+}
+
 // ---- fixed first argument (pairing_pp_init / pairing_pp_apply, ecc/a_param.c:1632-1818) ----
 // Tab: line-coefficient table;  tab.template store<O>(row, slot) / tab.template load<O>(slot, row).
 // Rows come in groups of three (a, b, c), in loop order.

@@ -674,10 +674,10 @@ static constexpr size_t kSmemAPPInit = (size_t)kASlots * 64 * 32;
 static constexpr size_t kSmemAPPApply = (size_t)kAPPSlots * 64 * kBlockMiller;
 
 // type a1: 34-limb slots (136 bytes per thread and slot)
-static constexpr int kBlockA1 = 96;            // 14 slots * 136 B * 96 threads = 178.5 KB of shared memory
+static constexpr int kBlockA1 = kA1MillerBlock;  // 14 slots * 136 B * 96 threads = 178.5 KB of shared memory (13 * 136 * 128 = 221 KB with PBC_A1_SLOTS13)
 static constexpr int kBlockA1Small = 128;      // kernels with at most 9 slots
 static constexpr size_t kSlotA1 = (size_t)kNA1 * 4;
-static constexpr size_t kSmemA1Miller = (size_t)kASlots * kSlotA1 * kBlockA1;
+static constexpr size_t kSmemA1Miller = (size_t)kA1MillerSlots * kSlotA1 * kBlockA1;
 static constexpr size_t kSmemA1Final = (size_t)kA1FinalSlots * kSlotA1 * kBlockA1Small;
 static constexpr size_t kSmemA1Prod = (size_t)kA1ProdSlots * kSlotA1 * kBlockA1Small;
 static constexpr size_t kSmemA1PP = (size_t)kA1PPSlots * kSlotA1 * kBlockA1Small;

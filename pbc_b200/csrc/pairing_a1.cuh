@@ -26,6 +26,16 @@ namespace pbcb200 {
 
 constexpr int kNA1 = 34;       // 32-bit limbs: p < 2^1087
 
+// PBC_A1_SLOTS13 = 1: Miller kernel on the five-temporary slot programs (13 slots, 128 threads per
+// block = one warp per scheduler) instead of 14 slots and 96 threads.  The programs are pinned on
+// the CPU (tests/test_a_steps_host.py, mode "5t"); the kernel variant has not run on a GPU yet, so
+// the measured configuration stays the default.
+#ifndef PBC_A1_SLOTS13
+#define PBC_A1_SLOTS13 0
+#endif
+constexpr int kA1MillerSlots = PBC_A1_SLOTS13 ? 13 : 14;
+constexpr int kA1MillerBlock = PBC_A1_SLOTS13 ? 128 : 96;
+
 struct alignas(16) A1Consts {
   uint32_t n[kMaxLimbs];       // group order (plain integer, little-endian words)
   uint32_t two[kMaxLimbs];     // Montgomery 2
@@ -122,12 +132,18 @@ k_a1_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, void* 
   // ecc/a_param.c:1979-1993: tangent; V = 2V; chord and V += P where the bit is set; f = f^2.
   // a_double_step squares first, which is the same product because f starts at 1.
   for (int m = (int)c_a1.nbits - 2; m >= 0; m--) {
+#if PBC_A1_SLOTS13
+    a_double_step_5t<O>();
+    if (m > 0 && ((c_a1.n[m >> 5] >> (m & 31)) & 1u))
+      a1_chord_add_5t<O>([&](int slot, int coord) { O::ld_global(slot, pm, coord, n, idx); });
+#else
     a_double_step<O>();
     if (m > 0 && ((c_a1.n[m >> 5] >> (m & 31)) & 1u)) {
       O::ld_global(aT4, pm, 0, n, idx);
       O::ld_global(aT5, pm, 1, n, idx);
       a1_chord_add<O>(aT4, aT5);
     }
+#endif
   }
   a1_publish<O>(aF0, aF1, aT0, aT1, okP && okQ, f, dprod, n, idx);
 }

@@ -4,7 +4,7 @@
 // memory slots, Montgomery limbs); here the same templates run against a big-integer policy class,
 // following k_a1_miller / k_a1_finalexp step for step, so the formulas (Jacobian doubling with the
 // tangent, chord + mixed addition, Lucas final exponentiation) are pinned to reference fixtures
-// without a GPU.  Argument "pp": go through the fixed-argument table programs instead.  stdin: p n l count, then count lines "Px Py Qx Qy" (decimal); stdout: "Re Im" (hex).
+// without a GPU.  Argument "pp": go through the fixed-argument table programs instead; "5t": the five-temporary Miller programs.  stdin: p n l count, then count lines "Px Py Qx Qy" (decimal); stdout: "Re Im" (hex).
 #include <stdio.h>
 #include <iostream>
 #include <string>
@@ -64,6 +64,7 @@ static std::string hex(const BigUInt& x) {
 int main(int argc, char** argv) {
   using namespace pbcb200;
   const bool pp_mode = argc > 1 && std::string(argv[1]) == "pp";
+  const bool five = argc > 1 && std::string(argv[1]) == "5t";   // the five-temporary programs
   using O = HostOps;
   std::string sp, sn, sl;
   int count;
@@ -86,14 +87,22 @@ int main(int argc, char** argv) {
     O::s[aX] = Px; O::s[aY] = Py;
     O::s[aZ] = BigUInt(1); O::s[aZ2] = BigUInt(1);
     O::s[aF0] = BigUInt(1); O::s[aF1] = BigUInt();
+    if (five) O::s[aT5] = BigUInt(0xdead);              // must never be read or written
     for (int m = (int)n.bits() - 2; m >= 0; m--) {
-      a_double_step<O>();
-      if (m > 0 && n.bit((size_t)m)) {
-        O::s[aT4] = Px;
-        O::s[aT5] = Py;
-        a1_chord_add<O>(aT4, aT5);
+      if (five) {
+        a_double_step_5t<O>();
+        if (m > 0 && n.bit((size_t)m))
+          a1_chord_add_5t<O>([&](int slot, int coord) { O::s[slot] = coord ? Py : Px; });
+      } else {
+        a_double_step<O>();
+        if (m > 0 && n.bit((size_t)m)) {
+          O::s[aT4] = Px;
+          O::s[aT5] = Py;
+          a1_chord_add<O>(aT4, aT5);
+        }
       }
     }
+    if (five && !(O::s[aT5] == BigUInt(0xdead))) { fprintf(stderr, "aT5 was touched\n"); return 2; }
     if (pp_mode) {
       // k_a1_pp_init for P, then k_a1_pp_apply for Q: must give the same pairing
       HostTable T;
