@@ -21,6 +21,7 @@
 #include "common_kernels.cuh"
 #include "host_bigint.hpp"
 #include "host_fields.hpp"
+#include "host_naf.hpp"
 #include "pairing_a.cuh"
 #include "pairing_a1.cuh"
 #include "pairing_d.cuh"
@@ -112,6 +113,9 @@ struct pbc_b200_pairing_s {
   FpConsts fp;
   AConsts a;
   A1Consts a1;
+#if PBC_A1_NAF
+  A1Naf a1naf;
+#endif
   size_t a1_rows = 0;          // rows of the fixed-argument line table (3 per tangent / chord)
   CCConsts cc;
   FConsts f;
@@ -276,6 +280,18 @@ static int init_type_a1(pbc_b200_pairing_s* p, const std::map<std::string, std::
   size_t lines = n.bits() - 1;
   for (size_t m = 1; m + 1 < n.bits(); m++) lines += n.bit(m) ? 1 : 0;
   p->a1_rows = 3 * lines;
+#if PBC_A1_NAF
+  {
+    std::vector<int8_t> dg = naf_digits(n);
+    if (dg.size() > 32 * (size_t)kMaxLimbs) return fail("type a1: n too large for the signed-digit table");
+    memset(&p->a1naf, 0, sizeof p->a1naf);
+    for (size_t i = 0; i < dg.size(); i++) {
+      if (dg[i]) p->a1naf.nz[i >> 5] |= 1u << (i & 31);
+      if (dg[i] < 0) p->a1naf.neg[i >> 5] |= 1u << (i & 31);
+    }
+    p->a1naf.len = (uint32_t)dg.size();
+  }
+#endif
   p->hash_ok = false;
   return 0;
 }
@@ -723,6 +739,9 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
     CUDA_OK(cudaMemcpyToSymbol(c_fp, &p->fp, sizeof(FpConsts)));
     if (p->type == 'a') CUDA_OK(cudaMemcpyToSymbol(c_a, &p->a, sizeof(AConsts)));
     if (p->type == '1') CUDA_OK(cudaMemcpyToSymbol(c_a1, &p->a1, sizeof(A1Consts)));
+#if PBC_A1_NAF
+    if (p->type == '1') CUDA_OK(cudaMemcpyToSymbol(c_a1naf, &p->a1naf, sizeof(A1Naf)));
+#endif
     CUDA_OK(cudaMemcpyToSymbol(c_zr, &p->zr, sizeof(ZrConsts)));
     CUDA_OK(cudaMemcpyToSymbol(c_hash, &p->hash, sizeof(HashConsts)));
     if (p->type == 'f' || p->type == 'd' || p->type == 'g') CUDA_OK(cudaMemcpyToSymbol(c_cc, &p->cc, sizeof(CCConsts)));

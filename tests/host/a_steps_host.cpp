@@ -4,12 +4,13 @@
 // memory slots, Montgomery limbs); here the same templates run against a big-integer policy class,
 // following k_a1_miller / k_a1_finalexp step for step, so the formulas (Jacobian doubling with the
 // tangent, chord + mixed addition, Lucas final exponentiation) are pinned to reference fixtures
-// without a GPU.  Argument "pp": go through the fixed-argument table programs instead; "5t": the five-temporary Miller programs.  stdin: p n l count, then count lines "Px Py Qx Qy" (decimal); stdout: "Re Im" (hex).
+// without a GPU.  Argument "pp": go through the fixed-argument table programs instead; "5t": the five-temporary Miller programs; "naf" / "5t-naf": the signed-digit scan of n.  stdin: p n l count, then count lines "Px Py Qx Qy" (decimal); stdout: "Re Im" (hex).
 #include <stdio.h>
 #include <iostream>
 #include <string>
 
 #include "../../pbc_b200/csrc/host_bigint.hpp"
+#include "../../pbc_b200/csrc/host_naf.hpp"
 #include "../../pbc_b200/csrc/a_steps.cuh"
 
 using pbcb200::BigUInt;
@@ -64,7 +65,9 @@ static std::string hex(const BigUInt& x) {
 int main(int argc, char** argv) {
   using namespace pbcb200;
   const bool pp_mode = argc > 1 && std::string(argv[1]) == "pp";
-  const bool five = argc > 1 && std::string(argv[1]) == "5t";   // the five-temporary programs
+  const std::string mode = argc > 1 ? argv[1] : "";
+  const bool five = mode == "5t" || mode == "5t-naf";           // the five-temporary programs
+  const bool naf = mode == "naf" || mode == "5t-naf";           // signed-digit scan of n (host_naf.hpp)
   using O = HostOps;
   std::string sp, sn, sl;
   int count;
@@ -88,16 +91,31 @@ int main(int argc, char** argv) {
     O::s[aZ] = BigUInt(1); O::s[aZ2] = BigUInt(1);
     O::s[aF0] = BigUInt(1); O::s[aF1] = BigUInt();
     if (five) O::s[aT5] = BigUInt(0xdead);              // must never be read or written
-    for (int m = (int)n.bits() - 2; m >= 0; m--) {
+    std::vector<int8_t> dg = naf_digits(n);
+    if (naf) {
+      // self-check of the digit table: sum d_i 2^i == n, no two adjacent non-zero digits
+      BigUInt pos, negs;
+      for (size_t i = 0; i < dg.size(); i++) {
+        if (dg[i] > 0) pos = pos + BigUInt(1).shl(i);
+        if (dg[i] < 0) negs = negs + BigUInt(1).shl(i);
+        if (i && dg[i] && dg[i - 1]) { fprintf(stderr, "adjacent digits\n"); return 3; }
+      }
+      if (!(pos - negs == n) || dg.back() != 1) { fprintf(stderr, "bad digit table\n"); return 3; }
+    }
+    const int top = naf ? (int)dg.size() - 2 : (int)n.bits() - 2;
+    const BigUInt mPy = O::p - Py;
+    for (int m = top; m >= 0; m--) {
+      const bool chord = m > 0 && (naf ? dg[m] != 0 : n.bit((size_t)m));
+      const bool minus = naf && dg[m] < 0;
       if (five) {
         a_double_step_5t<O>();
-        if (m > 0 && n.bit((size_t)m))
-          a1_chord_add_5t<O>([&](int slot, int coord) { O::s[slot] = coord ? Py : Px; });
+        if (chord)
+          a1_chord_add_5t<O>([&](int slot, int coord) { O::s[slot] = coord ? (minus ? mPy : Py) : Px; });
       } else {
         a_double_step<O>();
-        if (m > 0 && n.bit((size_t)m)) {
+        if (chord) {
           O::s[aT4] = Px;
-          O::s[aT5] = Py;
+          O::s[aT5] = minus ? mPy : Py;
           a1_chord_add<O>(aT4, aT5);
         }
       }
