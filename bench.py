@@ -118,19 +118,19 @@ def _ref_worker(args):
     name, mode, k, Pb, Qb, n = args
     from oracle import ref as R
     rp = R.RefPairing(PARAMS[name])
-    t0 = time.perf_counter()
+    t0, c0 = time.perf_counter(), time.process_time()
     if mode == "pp":
         out = rp.pp_pairing(Pb, Qb, n)
     else:
         out = rp.pairing(Pb, Qb, n) if mode == "single" else rp.prod_pairing(Pb, Qb, k, n)
-    return out, time.perf_counter() - t0
+    return out, time.perf_counter() - t0, time.process_time() - c0
 
 
 def _port_worker(args):
     name, mode, k, Pb, Qb, n = args
     from oracle import pbc_oracle as O
     pr = O.pairing_from_param(PARAMS[name])
-    t0 = time.perf_counter()
+    t0, c0 = time.perf_counter(), time.process_time()
     if mode == "pp":
         out = O.pairing_batch(pr, Pb[:pr.g1_len] * n, Qb, n)
     elif mode == "single":
@@ -140,7 +140,7 @@ def _port_worker(args):
         out = b"".join(O.prod_pairing_bytes(pr, [Pb[(i * k + j) * a:(i * k + j + 1) * a] for j in range(k)],
                                             [Qb[(i * k + j) * b:(i * k + j + 1) * b] for j in range(k)])
                        for i in range(n))
-    return out, time.perf_counter() - t0
+    return out, time.perf_counter() - t0, time.process_time() - c0
 
 
 def cpu_kind():
@@ -155,7 +155,8 @@ def cpu_kind():
 
 def cpu_pairings(w, P, Q, n, cores, pool=None):
     """n outputs of workload w on `cores` processes (each with its own pairing_t: the library is
-    not thread-safe).  Returns (bytes, wall seconds)."""
+    not thread-safe).  Returns (bytes, wall seconds, CPU seconds summed over the
+    workers): CPU seconds / wall is how many cores the box actually delivered."""
     import multiprocessing as mp
     g1, g2, _ = WIRE[w["param"]]
     k = w["k"]
@@ -177,14 +178,38 @@ def cpu_pairings(w, P, Q, n, cores, pool=None):
     if own:
         pool.close()
         pool.join()
-    return b"".join(r[0] for r in res), wall
+    return b"".join(r[0] for r in res), wall, sum(r[2] for r in res)
+
+
+def _cgroup_cpu_quota():
+    """CPUs the container may use according to its cgroup (v2 cpu.max, v1 cfs quota), or None"""
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max" and float(p) > 0:
+            return float(q) / float(p)
+    except Exception:
+        pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0 and p > 0:
+            return q / p
+    except Exception:
+        pass
+    return None
 
 
 def host_cores():
+    """worker processes for the CPU legs: the CPUs this process may run on, capped by the
+    container's CPU quota when it has one (more runnable processes than quota only thrash)"""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        cores = max(1, len(os.sched_getaffinity(0)))
     except Exception:
-        return max(1, os.cpu_count() or 1)
+        cores = max(1, os.cpu_count() or 1)
+    quota = _cgroup_cpu_quota()
+    if quota:
+        cores = max(1, min(cores, int(quota + 0.999)))
+    return cores
 
 
 def cpu_rate_guess(w, kind):
@@ -264,10 +289,11 @@ def reference_arm(args):
     P, Q = P.tobytes(), Q.tobytes()
     pool = mp.get_context("fork").Pool(cores)
     for _ in range(args.warmup):
-        cpu_pairings(w, P, Q, min(per_step, cores * 2), cores, pool)
+        cpu_pairings(w, P, Q, min(per_step, cores * 2), cores, pool)   # warm-up
     t0 = time.perf_counter()
+    cpu_s = 0.0
     for _ in range(args.steps):
-        cpu_pairings(w, P, Q, per_step, cores, pool)
+        cpu_s += cpu_pairings(w, P, Q, per_step, cores, pool)[2]
     wall = time.perf_counter() - t0
     pool.close()
     pool.join()
@@ -283,7 +309,8 @@ def reference_arm(args):
         "config": {"workload": w["name"], "batch_per_step": per_step, "param": w["param"] + ".param",
                    "note": "bounded sample of the workload per step; CPU only"},
         "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": kind,
-                         "sample": "%d outputs per step x %d steps, %d processes" % (per_step, args.steps, cores)},
+                         "sample": "%d outputs per step x %d steps, %d processes" % (per_step, args.steps, cores),
+                         "cpu_seconds": cpu_s, "effective_cores": cpu_s / max(wall, 1e-9)},
         "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -328,10 +355,11 @@ def main():
         cores = host_cores()
         kind = cpu_kind()
         sample_n = int(min(n, max(cores * 2, args.cpu_seconds * cpu_rate_guess(w, kind) * cores)))
-        cpu_out, wall = cpu_pairings(w, Ph[:sample_n * k * g1].tobytes(), Qh[:sample_n * k * g2].tobytes(),
-                                     sample_n, cores)
+        cpu_out, wall, cpu_s = cpu_pairings(w, Ph[:sample_n * k * g1].tobytes(), Qh[:sample_n * k * g2].tobytes(),
+                                            sample_n, cores)
         cpu = {"value": sample_n / wall, "unit": unit_name, "cores": cores, "kind": kind,
-               "sample": "first %d outputs of the step's batch, %d processes, %.1f s wall" % (sample_n, cores, wall)}
+               "sample": "first %d outputs of the step's batch, %d processes, %.1f s wall" % (sample_n, cores, wall),
+               "cpu_seconds": cpu_s, "effective_cores": cpu_s / max(wall, 1e-9)}
 
     import torch
     import torch.distributed as dist
