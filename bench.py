@@ -489,10 +489,13 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        traffic = None
+        traffic = traffic_src = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))[
-                w["kernels"][0].split("+")[0]]["dram_bytes_per_launch"]
+            t = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))[w["kernels"][0].split("+")[0]]
+            # one ncu --set full capture of this kernel (dram__bytes_read.sum + dram__bytes_write.sum);
+            # every thread moves the same bytes, so the capture's per-pairing figure scales to this launch
+            traffic = t["dram_bytes_per_pairing"] * n * k
+            traffic_src = "%s (n = %d), scaled to this launch's %d Miller loops" % (t["capture"], t["capture_n"], n * k)
         except Exception:
             pass
         hbm_ach = n * (k * (g1 + g2) + gt) / (sum(stage) * 1e-3) / 1e9
@@ -500,7 +503,7 @@ def main():
                 "achieved": ach_ref / 1e12, "peak": peak / 1e12, "unit": "T IMAD.WIDE.U32/s",
                 "frac": ach_ref / peak,
                 "peak_source": "live microkernel k_imad_peak (MEASURED_PEAKS.json has no integer peak)",
-                "work": work, "traffic": traffic,
+                "work": work, "traffic": traffic, "traffic_source": traffic_src,
                 "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
                         "frac": hbm_ach / hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                         "note": "%d wire bytes per output: does not bound the path" % (k * (g1 + g2) + gt)}}
