@@ -1,0 +1,89 @@
+// limb_arith_host.cpp -- runs the limb-level field arithmetic of fp.cuh / fq_small.cuh on the CPU.
+//
+// TEST INFRASTRUCTURE.  Compiled against the header tests/host/make_host_fp.py generates (the
+// device templates with their inline PTX routed through tests/host/ptx_emul.hpp).  One request per
+// line on stdin:   N FULL op p a b c d      (hex, little-endian words are rebuilt here)
+// one result per line on stdout (hex).  ops:
+//   mul_os  mont_mul<N,FULL>(a, b)        mul_ps  mont_mul_ps<N,FULL>(a, b)     sqr_ps  mont_sqr_ps<N,FULL>(a)
+//   add sub neg halve                      fp_add / fp_sub / fp_neg / fp_halve
+//   fq_mul  fq_redc_call(fq_mulw_call(a, b))                       (N = kNS only)
+//   fq_mac  fq_redc2_call(a b + c d)  fq_msb  fq_redc2_call(a b + (q R - c d))... see the test
+#include HOST_FP_HEADER
+
+#include <iostream>
+#include <string>
+#include <vector>
+
+using namespace pbcb200;
+
+static void from_hex(const std::string& s, uint32_t* w, int n) {
+  for (int i = 0; i < n; i++) w[i] = 0;
+  int bit = 0;
+  for (size_t i = s.size(); i-- > 0;) {
+    char c = s[i];
+    uint32_t v = c <= '9' ? c - '0' : (c | 32) - 'a' + 10;
+    if (bit / 32 < n) w[bit / 32] |= v << (bit % 32);
+    bit += 4;
+  }
+}
+static std::string to_hex(const uint32_t* w, int n) {
+  std::string r;
+  char buf[16];
+  for (int i = n; i-- > 0;) { snprintf(buf, sizeof buf, "%08x", w[i]); r += buf; }
+  return r;
+}
+static uint32_t neg_inv32(uint32_t p0) {
+  uint32_t x = 1;
+  for (int i = 0; i < 6; i++) x *= 2u - p0 * x;
+  return 0u - x;
+}
+
+template <int N, bool FULL>
+static std::string run(const std::string& op, const std::string& a_, const std::string& b_) {
+  uint32_t a[N], b[N], r[N];
+  from_hex(a_, a, N);
+  from_hex(b_, b, N);
+  if (op == "mul_os") { if constexpr (N % 2 == 0) mont_mul<N, FULL>(r, a, b); else return "odd"; }
+  else if (op == "mul_ps") mont_mul_ps<N, FULL>(r, a, b);
+  else if (op == "sqr_ps") mont_sqr_ps<N, FULL>(r, a);
+  else if (op == "add") fp_add<N, FULL>(r, a, b);
+  else if (op == "sub") fp_sub<N>(r, a, b);
+  else if (op == "neg") fp_neg<N>(r, a);
+  else if (op == "halve") fp_halve<N, FULL>(r, a);
+  else return "?";
+  return to_hex(r, N);
+}
+
+int main() {
+  std::string sN, sF, op, p, a, b, c, d;
+  while (std::cin >> sN >> sF >> op >> p >> a >> b >> c >> d) {
+    int N = atoi(sN.c_str());
+    bool full = sF == "1";
+    memset(&c_fp, 0, sizeof c_fp);
+    from_hex(p, c_fp.p, kMaxLimbs);
+    c_fp.np0 = neg_inv32(c_fp.p[0]);
+    c_fp.nlimbs = (uint32_t)N;
+    std::string out = "?";
+    if (op.rfind("fq_", 0) == 0) {
+      if (N != kNS) { out = "kNS"; }
+      else {
+        Fq A, B, C, D;
+        from_hex(a, A.v, kNS); from_hex(b, B.v, kNS); from_hex(c, C.v, kNS); from_hex(d, D.v, kNS);
+        Fq R;
+        if (op == "fq_mul") R = fq_redc_call(fq_mulw_call(A, B));
+        else if (op == "fq_mac") { FqW s, t = fq_mulw_call(A, B), u = fq_mulw_call(C, D); fqw_add(s, t, u); R = fq_redc2_call(s); }
+        else if (op == "fq_mulcall") R = fq_mul_call(A, B);
+        else if (op == "fq_sqrcall") R = fq_sqr_call(A);
+        else { std::cout << "?" << "\n"; continue; }
+        out = to_hex(R.v, kNS);
+      }
+    } else {
+#define CASE(n, f) if (N == n && full == f) out = run<n, f>(op, a, b);
+      CASE(5, false) CASE(6, false) CASE(16, true) CASE(16, false) CASE(34, false) CASE(34, true)
+#undef CASE
+    }
+    std::cout << out << "\n";
+  }
+  fprintf(stderr, "ptx instructions interpreted: %llu\n", (unsigned long long)ptxemu::executed());
+  return 0;
+}
