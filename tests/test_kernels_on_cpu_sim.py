@@ -1,0 +1,84 @@
+"""The product library -- engine.cu's host code and every kernel it launches -- compiled for the CPU
+and run against the reference fixtures and the GPU parity tests themselves.
+
+tests/host/make_host_sim.py turns engine.cu plus its headers into one C++ file: inline PTX goes
+through tests/host/ptx_emul.hpp, kernel launches and the CUDA runtime through tests/host/cuda_sim.hpp
+(device memory = host memory, one simulated thread at a time).  The result exports the same C ABI, so
+PBC_B200_LIB=<simulator> lets pbc_b200.pairing and the `-m gpu` tests run unchanged -- the small
+cases, here, without a GPU.  This pins the kernels' logic (formulas, indexing, wire conversion,
+workspace layout, host-side constants); clocks, occupancy and the real PTX->SASS path are what the
+B200 runs add.  TEST INFRASTRUCTURE: nothing in the product links or loads the simulator."""
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "tests", "host")
+
+
+def _build(tmp, *defs):
+    cpp, so = str(tmp / "host_sim.cpp"), str(tmp / "libpbc_b200_sim.so")
+    subprocess.check_call([sys.executable, os.path.join(HOST, "make_host_sim.py"), cpp] + list(defs))
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-pthread",
+                           "-o", so, cpp])
+    return so
+
+
+def _env(so):
+    env = dict(os.environ)
+    env["PBC_B200_LIB"] = so
+    env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
+    return env
+
+
+@pytest.fixture(scope="module")
+def sim(tmp_path_factory):
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    return _build(tmp_path_factory.mktemp("sim"))
+
+
+def _battery(so, *args):
+    out = subprocess.run([sys.executable, os.path.join(HOST, "sim_driver.py")] + list(args), env=_env(so),
+                         capture_output=True, text=True, timeout=1800)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def test_every_entry_point_reproduces_the_reference_fixtures(sim):
+    res = _battery(sim)
+    assert len(res) >= 38 and all(res.values()), {k: v for k, v in res.items() if not v}
+
+
+def test_gpu_parity_tests_pass_on_the_simulator(sim):
+    """the `-m gpu` tests, unchanged, with the simulator in place of libpbc_b200.so; left out: the
+    cases sized for a GPU (2^14 .. 2^18 outputs), the device-pointer entry points (they take
+    torch.cuda tensors) and the C programs of the shim (they link the real library)"""
+    files = [os.path.join(ROOT, "tests", f) for f in ("test_gpu_towers.py", "test_gpu_type_a.py", "test_gpu_type_a1.py",
+                                                       "test_gpu_type_fd.py", "test_gpu_group_ops.py")]
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider",
+           "-k", "not large_batch and not device_pointer and not tiles and not across_blocks"] + files
+    try:
+        import xdist  # noqa: F401
+        cmd += ["-n", str(max(1, min(8, len(os.sched_getaffinity(0)))))]
+    except Exception:
+        pass
+    out = subprocess.run(cmd, env=_env(sim), capture_output=True, text=True, timeout=3000, cwd=ROOT)
+    tail = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-500:]
+    assert out.returncode == 0, out.stdout[-3000:]
+    passed = int(tail.split(" passed")[0].split()[-1])
+    assert passed >= 300, tail
+
+
+def test_a1_kernel_variants_give_the_same_bytes(tmp_path):
+    """PBC_A1_SLOTS13 (five-temporary programs, 128 threads per block) and PBC_A1_NAF (signed-digit
+    scan of n) are off in the measured build: here the whole kernel path runs with both on"""
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    so = _build(tmp_path, "-DPBC_A1_SLOTS13=1", "-DPBC_A1_NAF=1")
+    res = _battery(so, "a1")
+    assert len(res) == 6 and all(res.values()), res
