@@ -28,6 +28,7 @@
 #include "pairing_f.cuh"
 #include "pairing_g.cuh"
 #include "group_a.cuh"
+#include "group_a1.cuh"
 #include "group_cc.cuh"
 
 namespace pbcb200 {
@@ -113,6 +114,7 @@ struct pbc_b200_pairing_s {
   FpConsts fp;
   AConsts a;
   A1Consts a1;
+  A1GroupConsts a1g;
 #if PBC_A1_NAF
   A1Naf a1naf;
 #endif
@@ -280,6 +282,15 @@ static int init_type_a1(pbc_b200_pairing_s* p, const std::map<std::string, std::
   size_t lines = n.bits() - 1;
   for (size_t m = 1; m + 1 < n.bits(); m++) lines += n.bit(m) ? 1 : 0;
   p->a1_rows = 3 * lines;
+  A1GroupConsts& gc = p->a1g;
+  memset(&gc, 0, sizeof gc);
+  n.to_words(gc.n, kNA1);
+  q.to_words(gc.q, kNA1);
+  BigUInt se = (q + BigUInt(1)) / BigUInt(4);      // p = 3 mod 4: t^((p+1)/4) is a root of a square t
+  se.to_words(gc.sqrt_exp, kNA1);
+  gc.expbits = (uint32_t)se.bits();
+  gc.zlen = p->zr.zlen;
+  gc.count = (uint32_t)wb;
 #if PBC_A1_NAF
   {
     std::vector<int8_t> dg = naf_digits(n);
@@ -699,6 +710,10 @@ static constexpr size_t kSmemA1Prod = (size_t)kA1ProdSlots * kSlotA1 * kBlockA1S
 static constexpr size_t kSmemA1PP = (size_t)kA1PPSlots * kSlotA1 * kBlockA1Small;
 static constexpr size_t kSmemA1PPInit = (size_t)kASlots * kSlotA1 * 32;
 static constexpr size_t kSmemInv34 = (size_t)5 * kSlotA1 * kBlockA1Small;
+// group operations of type a1 run 64 threads per block: their own instantiation of the slot machine,
+// so the code generated for the measured pairing kernels does not move when these change
+static constexpr int kBlockA1G = 64;
+static constexpr size_t kSmemA1G = (size_t)kGSlots * kSlotA1 * kBlockA1G;   // 11 slots: 93.5 KB, two blocks per SM
 
 static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
   if ((int)p->ctx.size() <= dev) p->ctx.resize(dev + 1);
@@ -729,6 +744,11 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
       CUDA_OK(allow_smem(k_a1_pp_apply<kBlockA1Small>, kSmemA1PP));
       CUDA_OK(allow_smem(k_batch_invert<kNA1, false, kBlockA1Small>, kSmemInv34));
       CUDA_OK(allow_smem(k_a1_fp_op<kBlockA1Small>, (size_t)4 * kSlotA1 * kBlockA1Small));
+      CUDA_OK(allow_smem(k_a1_g1_mul<kBlockA1G>, kSmemA1G));
+      CUDA_OK(allow_smem(k_a1_g1_from_hash<kBlockA1G>, kSmemA1G));
+      CUDA_OK(allow_smem(k_a1_g1_finish<kBlockA1G>, (size_t)4 * kSlotA1 * kBlockA1G));
+      CUDA_OK(allow_smem(k_a1_gt_pow<kBlockA1G>, (size_t)7 * kSlotA1 * kBlockA1G));
+      CUDA_OK(allow_smem(k_a1_g1_decompress<kBlockA1G>, (size_t)5 * kSlotA1 * kBlockA1G));
     }
     c.ready = true;
   }
@@ -739,6 +759,7 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
     CUDA_OK(cudaMemcpyToSymbol(c_fp, &p->fp, sizeof(FpConsts)));
     if (p->type == 'a') CUDA_OK(cudaMemcpyToSymbol(c_a, &p->a, sizeof(AConsts)));
     if (p->type == '1') CUDA_OK(cudaMemcpyToSymbol(c_a1, &p->a1, sizeof(A1Consts)));
+    if (p->type == '1') CUDA_OK(cudaMemcpyToSymbol(c_a1g, &p->a1g, sizeof(A1GroupConsts)));
 #if PBC_A1_NAF
     if (p->type == '1') CUDA_OK(cudaMemcpyToSymbol(c_a1naf, &p->a1naf, sizeof(A1Naf)));
 #endif
@@ -1227,6 +1248,28 @@ double pbc_b200_bench_imad(int blocks, int threads, int iters, int reps) {
 static int enqueue_group(pbc_b200_pairing_s* p, int which /*0 = G1, 1 = GT, 2 = G2*/, uint8_t* d_out, const uint8_t* d_in,
                          const uint8_t* d_k, size_t n, void* ws, cudaStream_t st) {
   if (n == 0) return 0;
+  if (p->type == '1') {
+    unsigned g = (unsigned)((n + kBlockA1G - 1) / kBlockA1G);
+    if (which == 0 || which == 2) {                // type a1: G2 = G1 (ecc/a_param.c:2261)
+      const size_t E = kNA1 / 2;
+      uint2* xyz = (uint2*)ws;                  // [2][E][n]  (X, Y)
+      uint2* zarr = xyz + 2 * E * n;            // [E][n]
+      uint2* prefix = zarr + E * n;             // [E][n]
+      k_a1_g1_mul<kBlockA1G><<<g, kBlockA1G, kSmemA1G, st>>>(d_in, d_k, xyz, zarr, n);
+      LAUNCHED();
+      size_t T = n < (size_t)148 * 128 ? n : (size_t)148 * 128;
+      unsigned gi = (unsigned)((T + kBlockA1Small - 1) / kBlockA1Small);
+      k_batch_invert<kNA1, false, kBlockA1Small><<<gi, kBlockA1Small, kSmemInv34, st>>>(zarr, prefix, n, T);
+      LAUNCHED();
+      k_a1_g1_finish<kBlockA1G><<<g, kBlockA1G, (size_t)4 * kSlotA1 * kBlockA1G, st>>>(xyz, zarr, d_out, n);
+      LAUNCHED();
+    } else {
+      k_a1_gt_pow<kBlockA1G><<<g, kBlockA1G, (size_t)7 * kSlotA1 * kBlockA1G, st>>>(d_in, d_k, d_out, n);
+      LAUNCHED();
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (p->type == 'a') {
     if (which == 0 || which == 2) {                // type a: G2 = G1 (ecc/a_param.c:1461-1462)
       uint4* xyz = (uint4*)ws;                 // [2][4][n]  (X, Y)
@@ -1267,7 +1310,6 @@ static int enqueue_group(pbc_b200_pairing_s* p, int which /*0 = G1, 1 = GT, 2 = 
 static int run_group(pbc_b200_pairing_s* p, int which, unsigned char* out, const unsigned char* in,
                      const unsigned char* k, size_t n, bool device, void* stream) {
   if (!p || (n && (!out || !in || !k))) return fail("null argument");
-  if (p->type == '1') return fail("element_pow_zn: not built for type a1 yet (pairings, products and fixed-argument pairings are)");
   if (n == 0) return 0;
   std::lock_guard<std::mutex> lk(p->mu);
   int dev = 0;
@@ -1278,6 +1320,7 @@ static int run_group(pbc_b200_pairing_s* p, int which, unsigned char* out, const
   DevCtx& c = p->ctx[dev];
   size_t elen = which == 0 ? (size_t)p->g1_len : (which == 2 ? (size_t)p->g2_len : (size_t)p->gt_len);
   size_t wsb = p->type == 'a' && which != 1 ? n * 64 * (2 + 1 + 1) : 16;
+  if (p->type == '1' && which != 1) wsb = n * kSlotA1 * (2 + 1 + 1);
   size_t stage = device ? 0 : n * (2 * elen + (size_t)p->zr_len);
   if (c.cap_dev < wsb + stage) {
     CUDA_OK(cudaDeviceSynchronize());
@@ -1333,8 +1376,7 @@ int pbc_b200_gt_pow_zn_device(pbc_b200_pairing_t* p, void* d_out, const void* d_
 static int run_from_hash(pbc_b200_pairing_s* p, unsigned char* out, const unsigned char* data, size_t len, size_t n,
                          bool device, void* stream) {
   if (!p || (n && (!out || !data))) return fail("null argument");
-  if (p->type == '1') return fail("element_from_hash: not built for type a1 yet");
-  if (!p->hash_ok) return fail("element_from_hash: needs q = 3 mod 4 or q = 5 mod 8 and a cofactor below 2^384");
+  if (p->type != '1' && !p->hash_ok) return fail("element_from_hash: needs q = 3 mod 4 or q = 5 mod 8 and a cofactor below 2^384");
   if (len == 0 || len > (1u << 20)) return fail("element_from_hash: hash length must be 1..2^20 bytes");
   if (n == 0) return 0;
   std::lock_guard<std::mutex> lk(p->mu);
@@ -1346,6 +1388,7 @@ static int run_from_hash(pbc_b200_pairing_s* p, unsigned char* out, const unsign
   DevCtx& c = p->ctx[dev];
   size_t elen = (size_t)p->g1_len;
   size_t wsb = p->type == 'a' ? n * 64 * (2 + 1 + 1) : 16;
+  if (p->type == '1') wsb = n * kSlotA1 * (2 + 1 + 1);
   size_t stage = device ? 0 : n * (elen + len);
   if (c.cap_dev < wsb + stage) {
     CUDA_OK(cudaDeviceSynchronize());
@@ -1358,7 +1401,21 @@ static int run_from_hash(pbc_b200_pairing_s* p, unsigned char* out, const unsign
   uint8_t* d_out = device ? (uint8_t*)out : (uint8_t*)c.ws_dev + wsb;
   const uint8_t* d_data = device ? (const uint8_t*)data : d_out + n * elen;
   if (!device) CUDA_OK(cudaMemcpyAsync((void*)d_data, data, n * len, cudaMemcpyHostToDevice, st));
-  if (p->type == 'a') {
+  if (p->type == '1') {
+    const size_t E = kNA1 / 2;
+    uint2* xyz = (uint2*)c.ws_dev;
+    uint2* zarr = xyz + 2 * E * n;
+    uint2* prefix = zarr + E * n;
+    unsigned g = (unsigned)((n + kBlockA1G - 1) / kBlockA1G);
+    k_a1_g1_from_hash<kBlockA1G><<<g, kBlockA1G, kSmemA1G, st>>>(d_data, (int)len, xyz, zarr, n);
+    LAUNCHED();
+    size_t T = n < (size_t)148 * 128 ? n : (size_t)148 * 128;
+    unsigned gi = (unsigned)((T + kBlockA1Small - 1) / kBlockA1Small);
+    k_batch_invert<kNA1, false, kBlockA1Small><<<gi, kBlockA1Small, kSmemInv34, st>>>(zarr, prefix, n, T);
+    LAUNCHED();
+    k_a1_g1_finish<kBlockA1G><<<g, kBlockA1G, (size_t)4 * kSlotA1 * kBlockA1G, st>>>(xyz, zarr, d_out, n);
+    LAUNCHED();
+  } else if (p->type == 'a') {
     uint4* xyz = (uint4*)c.ws_dev;
     uint4* zarr = xyz + 8 * n;
     uint4* prefix = zarr + 4 * n;
@@ -1402,8 +1459,7 @@ extern "C" int pbc_b200_pairing_length_in_bytes_compressed_G1(const pbc_b200_pai
 extern "C" int pbc_b200_g1_from_bytes_compressed(pbc_b200_pairing_t* p, unsigned char* out, const unsigned char* in,
                                                  size_t n) {
   if (!p || (n && (!out || !in))) return fail("null argument");
-  if (p->type == '1') return fail("element_from_bytes_compressed: not built for type a1 yet");
-  if (!p->hash_ok) return fail("element_from_bytes_compressed: needs q = 3 mod 4 or q = 5 mod 8");
+  if (p->type != '1' && !p->hash_ok) return fail("element_from_bytes_compressed: needs q = 3 mod 4 or q = 5 mod 8");
   if (n == 0) return 0;
   std::lock_guard<std::mutex> lk(p->mu);
   int dev = 0;
@@ -1423,7 +1479,10 @@ extern "C" int pbc_b200_g1_from_bytes_compressed(pbc_b200_pairing_t* p, unsigned
   uint8_t* d_out = (uint8_t*)c.ws_dev;               // element output first: keeps it 4-byte aligned
   uint8_t* d_in = d_out + n * elen;
   CUDA_OK(cudaMemcpyAsync(d_in, in, n * clen, cudaMemcpyHostToDevice, st));
-  if (p->type == 'a') {
+  if (p->type == '1') {
+    unsigned g = (unsigned)((n + kBlockA1G - 1) / kBlockA1G);
+    k_a1_g1_decompress<kBlockA1G><<<g, kBlockA1G, (size_t)5 * kSlotA1 * kBlockA1G, st>>>(d_in, d_out, n);
+  } else if (p->type == 'a') {
     unsigned g = (unsigned)((n + kBlockMiller - 1) / kBlockMiller);
     k_a_g1_decompress<kBlockMiller><<<g, kBlockMiller, (size_t)5 * 64 * kBlockMiller, st>>>(d_in, d_out, n);
   } else {

@@ -152,10 +152,3 @@ def test_fixed_argument_with_bad_point_is_identity(env):
     g, d = env["g"], env["dev"]
     out = d.pp_apply(bytes.fromhex(g["offcurve"]["badP"]), _cat(g["pairing"]["Q"][:2]), 2)
     assert out == bytes.fromhex(g["offcurve"]["identity"]) * 2
-
-
-def test_group_operations_say_so(env):
-    from pbc_b200.pairing import PairingError
-    d = env["dev"]
-    with pytest.raises(PairingError, match="a1"):
-        d.g1_pow_zn(bytes(d.g1_len), bytes(d.zr_len), 1)
