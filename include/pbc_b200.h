@@ -8,6 +8,9 @@
  *   type A  (param/a.param)     G1 128 B   G2 128 B   GT 128 B     x || y, 64-byte big-endian F_q
  *   type F  (param/f.param)     G1  40 B   G2  80 B   GT 240 B     20-byte big-endian F_q
  *   type D  (param/d159.param)  G1  40 B   G2 120 B   GT 120 B     20-byte big-endian F_q
+ *   type G  (param/g149.param)  G1  38 B   G2 190 B   GT 190 B     19-byte big-endian F_q
+ *   type A1 (param/a1.param)    G1 260 B   G2 260 B   GT 260 B     ceil(bits(p)/8) = 130-byte F_p; any
+ *                                                                  p = l n - 1 below 2^1087 is accepted
  *
  * Semantics that are reproduced exactly:
  *   - bytes that do not decode to a point on the curve are the point at infinity
@@ -41,15 +44,15 @@ typedef struct pbc_b200_pairing_s pbc_b200_pairing_t;
 
 /* pairing_init_set_buf / pairing_init_set_str (ecc/pairing.c:88-102): parse "key value" parameter
  * text (ecc/param.c:42-111), derive the field constants (arith/montfp.c:533-600,
- * ecc/a_param.c:1431-1472, ecc/f_param.c:335-447, ecc/d_param.c:993-1095) and upload them.
- * Types a, f, d (k = 6) are accepted.  Does not touch the GPU until the first compute call. */
+ * ecc/a_param.c:1431-1472 and :2230-2273, ecc/f_param.c:335-447, ecc/d_param.c:993-1095,
+ * ecc/g_param.c:1258) and upload them.  Types a, a1, f, d (k = 6) and g are accepted.  Does not touch the GPU until the first compute call. */
 int pbc_b200_pairing_init_set_buf(pbc_b200_pairing_t **out, const char *param, size_t len);
 int pbc_b200_pairing_init_set_str(pbc_b200_pairing_t **out, const char *param);
 
 /* pairing_clear (include/pbc_pairing.h:109-116) */
 void pbc_b200_pairing_clear(pbc_b200_pairing_t *p);
 
-/* pairing_length_in_bytes_G1 / _G2 / _GT (include/pbc_pairing.h:200-250); type letter 'a','f','d' */
+/* pairing_length_in_bytes_G1 / _G2 / _GT (include/pbc_pairing.h:200-250); type letter 'a', 'f', 'd', 'g'; '1' for a1 */
 int pbc_b200_pairing_length_in_bytes_G1(const pbc_b200_pairing_t *p);
 int pbc_b200_pairing_length_in_bytes_G2(const pbc_b200_pairing_t *p);
 int pbc_b200_pairing_length_in_bytes_GT(const pbc_b200_pairing_t *p);
