@@ -29,6 +29,9 @@ enum { ADD, SUB, MUL, MAD };
 
 inline uint32_t& CF() { static thread_local uint32_t cf = 0; return cf; }
 inline uint64_t& executed() { static uint64_t n = 0; return n; }
+// 32x32 products issued: every mul.lo / mad{c}.lo stands for one IMAD.WIDE.U32 on the device (its .hi
+// partner is the upper half of the same product)
+inline uint64_t& products() { static uint64_t n = 0; return n; }
 
 inline Operand parse_operand(const std::string& t) {
   Operand o{};
@@ -112,6 +115,7 @@ inline void ptx(const char* text, std::initializer_list<uint32_t*> outs, std::in
   };
   for (const Insn& in : it->second) {
     executed()++;
+    if ((in.op == MUL || in.op == MAD) && !in.hi) products()++;
     uint64_t r;
     uint32_t cin = in.carry_in ? CF() : 0;
     switch (in.op) {

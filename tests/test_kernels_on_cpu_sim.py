@@ -82,3 +82,37 @@ def test_a1_kernel_variants_give_the_same_bytes(tmp_path):
     so = _build(tmp_path, "-DPBC_A1_SLOTS13=1", "-DPBC_A1_NAF=1")
     res = _battery(so, "a1")
     assert len(res) == 6 and all(res.values()), res
+
+
+def test_multiplier_work_counted_by_the_simulator_matches_bench(sim):
+    """bench.py's roofline numerator (32x32 products the Miller kernel executes per pairing) against
+    the count the PTX interpreter takes while running that kernel"""
+    code = """
+import ctypes, json, sys
+sys.argv = ["bench.py"]
+import bench
+from pbc_b200 import _lib
+from pbc_b200.pairing import Pairing
+from pbc_b200.params import PARAMS
+lib = _lib.lib
+lib.pbc_b200_sim_products.restype = ctypes.c_ulonglong
+out = {}
+for wl in ("a", "a1"):
+    w = bench.WORKLOADS[wl]
+    g = json.load(open("tests/golden/%s.json" % wl))["pairing"]
+    pr = Pairing(PARAMS[wl])
+    P, Q = bytes.fromhex(g["P"][0]), bytes.fromhex(g["Q"][0])
+    pr.set_stage_profiling(False)
+    pr.apply(P, Q, 1)                      # warm: constants resident
+    c0 = lib.pbc_b200_sim_products()
+    pr.apply(P, Q, 1)
+    out[wl] = [lib.pbc_b200_sim_products() - c0, w["exec_unit_ops_main"]]
+print(json.dumps(out))
+"""
+    out = subprocess.run([sys.executable, "-c", code], env=_env(sim), capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    for wl, (counted, claimed) in res.items():
+        # counted = the whole call (Miller loop + batch inversion of one element + final exponentiation);
+        # the Miller kernel bench.py names is the bulk of it and can only be smaller than the total
+        assert claimed < counted < 1.6 * claimed, (wl, counted, claimed)
