@@ -116,3 +116,29 @@ print(json.dumps(out))
         # counted = the whole call (Miller loop + batch inversion of one element + final exponentiation);
         # the Miller kernel bench.py names is the bulk of it and can only be smaller than the total
         assert claimed < counted < 1.6 * claimed, (wl, counted, claimed)
+
+
+@pytest.mark.parametrize("name", ["a", "g149", "a1_small"])
+def test_pbc_api_through_the_shim_on_the_simulator(sim, tmp_path, name):
+    """shim/_build/shim_test (element_pairing, element_prod_pairing, pairing_pp_*, the batch entry
+    points and element_pow_zn_batch through the reference's own pbc.h, compared inside the program
+    with a pairing_t that keeps the reference's CPU vtable), the simulator standing in for
+    libpbc_b200.so.  Type A1 goes through the shim here as well."""
+    exe = os.path.join(ROOT, "shim", "_build", "shim_test")
+    if not os.path.exists(exe):
+        pytest.skip("shim/_build/shim_test not built (needs the reference headers: make -C shim)")
+    if name == "a1_small":
+        with open(os.path.join(ROOT, "tests", "golden", "a1_small.json")) as f:
+            text = json.load(f)["param_text"]
+    else:
+        sys.path.insert(0, ROOT)
+        from pbc_b200.params import PARAMS
+        text = PARAMS[name]
+    (tmp_path / "p.param").write_text(text)
+    libdir = tmp_path / "lib"
+    libdir.mkdir()
+    shutil.copy(sim, str(libdir / "libpbc_b200.so"))         # RUNPATH of the program yields to LD_LIBRARY_PATH
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = str(libdir) + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+    r = subprocess.run([exe, str(tmp_path / "p.param"), "24"], env=env, capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0 and "shim_test: OK" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
