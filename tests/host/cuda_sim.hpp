@@ -27,18 +27,23 @@ inline uint64_t& launches() { static uint64_t n = 0; return n; }
 // optional cap on simulated threads per launch (0 = all): kernels whose padding threads keep
 // computing (k_a_miller's `live` pattern) would otherwise cost a full block per launch
 inline size_t& live_threads() { static size_t n = 0; return n; }
+// shared memory is poisoned at the start of every block and device allocations at birth, so a
+// kernel that reads what it never wrote sees garbage here as it would on the GPU
+inline void (*&poison_shared())() { static void (*f)() = nullptr; return f; }
 template <class F>
 inline void launch(dim3 grid, dim3 block, F&& body) {
   launches()++;
   gdim() = grid; bdim() = block;
   size_t done = 0;
-  for (unsigned b = 0; b < grid.x; b++)
+  for (unsigned b = 0; b < grid.x; b++) {
+    if (poison_shared()) poison_shared()();
     for (unsigned t = 0; t < block.x; t++) {
       if (live_threads() && done >= live_threads()) return;
       bid() = dim3(b); tid() = dim3(t);
       body();
       done++;
     }
+  }
 }
 }  // namespace cusim
 #define threadIdx (::cusim::tid())
@@ -70,7 +75,7 @@ static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
-template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)malloc(n ? n : 1); return *p ? 0 : 2; }
+template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)malloc(n ? n : 1); if (*p) memset((void*)*p, 0xCD, n); return *p ? 0 : 2; }
 static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 template <class T> static inline cudaError_t cudaHostAlloc(T** p, size_t n, unsigned) { *p = (T*)malloc(n ? n : 1); return *p ? 0 : 2; }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
