@@ -120,6 +120,9 @@ struct pbc_b200_pairing_s {
 #endif
   size_t a1_rows = 0;          // rows of the fixed-argument line table (3 per tangent / chord)
   CCConsts cc;
+#if PBC_CC_NAF
+  CCNaf ccnaf;
+#endif
   FConsts f;
   DConsts d;
   GConsts g;
@@ -766,6 +769,21 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
     CUDA_OK(cudaMemcpyToSymbol(c_zr, &p->zr, sizeof(ZrConsts)));
     CUDA_OK(cudaMemcpyToSymbol(c_hash, &p->hash, sizeof(HashConsts)));
     if (p->type == 'f' || p->type == 'd' || p->type == 'g') CUDA_OK(cudaMemcpyToSymbol(c_cc, &p->cc, sizeof(CCConsts)));
+#if PBC_CC_NAF
+    if (p->type == 'f' || p->type == 'd' || p->type == 'g') {
+      // signed digits of the group order (host_naf.hpp); r is what fill_cc stored
+      BigUInt r;
+      for (int i = kNS; i-- > 0;) r = r.shl(32) + BigUInt((uint64_t)p->cc.r[i]);
+      std::vector<int8_t> dg = naf_digits(r);
+      memset(&p->ccnaf, 0, sizeof p->ccnaf);
+      for (size_t i = 0; i < dg.size() && i < 256; i++) {
+        if (dg[i]) p->ccnaf.nz[i >> 5] |= 1u << (i & 31);
+        if (dg[i] < 0) p->ccnaf.neg[i >> 5] |= 1u << (i & 31);
+      }
+      p->ccnaf.len = (uint32_t)dg.size();
+      CUDA_OK(cudaMemcpyToSymbol(c_ccnaf, &p->ccnaf, sizeof(CCNaf)));
+    }
+#endif
     if (p->type == 'f') CUDA_OK(cudaMemcpyToSymbol(c_f, &p->f, sizeof(FConsts)));
     if (p->type == 'd') CUDA_OK(cudaMemcpyToSymbol(c_d, &p->d, sizeof(DConsts)));
     if (p->type == 'g') CUDA_OK(cudaMemcpyToSymbol(c_g, &p->g, sizeof(GConsts)));

@@ -74,14 +74,15 @@ def test_gpu_parity_tests_pass_on_the_simulator(sim):
     assert passed >= 310, tail
 
 
-def test_a1_kernel_variants_give_the_same_bytes(tmp_path):
-    """PBC_A1_SLOTS13 (five-temporary programs, 128 threads per block) and PBC_A1_NAF (signed-digit
-    scan of n) are off in the measured build: here the whole kernel path runs with both on"""
+def test_kernel_variants_give_the_same_bytes(tmp_path):
+    """compile-time variants that are off in the measured build -- PBC_A1_SLOTS13 (five-temporary
+    programs, 128 threads per block), PBC_A1_NAF and PBC_CC_NAF (signed-digit scans of the group
+    order in the type A1 and type F/D/G Miller loops) -- all on: the whole battery again"""
     if not shutil.which("g++"):
         pytest.skip("no g++")
-    so = _build(tmp_path, "-DPBC_A1_SLOTS13=1", "-DPBC_A1_NAF=1")
-    res = _battery(so, "a1")
-    assert len(res) == 6 and all(res.values()), res
+    so = _build(tmp_path, "-DPBC_A1_SLOTS13=1", "-DPBC_A1_NAF=1", "-DPBC_CC_NAF=1")
+    res = _battery(so)
+    assert len(res) >= 38 and all(res.values()), {k: v for k, v in res.items() if not v}
 
 
 def test_multiplier_work_counted_by_the_simulator_matches_bench(sim):
