@@ -364,6 +364,9 @@ def main():
     import torch
     import torch.distributed as dist
     from pbc_b200.pairing import Pairing, kernel_launches, bench_imad
+    from pbc_b200 import _lib as _pbc_lib
+    if _pbc_lib.IS_SIMULATOR:
+        raise SystemExit("bench.py measures the CUDA library; PBC_B200_LIB points at the test suite's CPU simulator")
 
     torch.cuda.set_device(local)
     if world > 1:

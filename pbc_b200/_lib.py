@@ -8,7 +8,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("PBC_B200_LIB") or os.path.join(_HERE, "libpbc_b200.so")  # env: A/B builds only
+# PBC_B200_LIB selects another build of the SAME library: A/B kernel variants on the GPU box, and
+# the test suite's CPU simulator of it (tests/host/, never shipped or installed).  Nothing in the
+# product sets it; a simulator is refused unless the caller says it is a test (below).
+LIB_PATH = os.environ.get("PBC_B200_LIB") or os.path.join(_HERE, "libpbc_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -16,6 +19,9 @@ if not os.path.exists(LIB_PATH):
         "There is no CPU fallback." % LIB_PATH)
 
 lib = C.CDLL(LIB_PATH)
+IS_SIMULATOR = hasattr(lib, "pbc_b200_sim_live_threads")
+if IS_SIMULATOR and not os.environ.get("PBC_B200_LIB"):
+    raise ImportError("pbc_b200: %s is the test suite's CPU simulator, not the CUDA library" % LIB_PATH)
 
 _P = C.c_void_p
 lib.pbc_b200_pairing_init_set_buf.argtypes = [C.POINTER(_P), C.c_char_p, C.c_size_t]
