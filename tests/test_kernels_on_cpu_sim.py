@@ -143,3 +143,27 @@ def test_pbc_api_through_the_shim_on_the_simulator(sim, tmp_path, name):
     env["LD_LIBRARY_PATH"] = str(libdir) + os.pathsep + env.get("LD_LIBRARY_PATH", "")
     r = subprocess.run([exe, str(tmp_path / "p.param"), "24"], env=env, capture_output=True, text=True, timeout=1800)
     assert r.returncode == 0 and "shim_test: OK" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
+
+
+def test_plain_c_caller_of_the_c_abi_on_the_simulator(sim, tmp_path):
+    """examples/batch_pairing_demo.c (includes only include/pbc_b200.h; pinned staging buffers through
+    pbc_b200_host_alloc) with the simulator standing in for libpbc_b200.so"""
+    exe = os.path.join(ROOT, "examples", "_build", "batch_pairing_demo")
+    if not os.path.exists(exe):
+        pytest.skip("examples/_build/batch_pairing_demo not built (make -C examples)")
+    sys.path.insert(0, ROOT)
+    from pbc_b200.params import PARAMS
+    with open(os.path.join(ROOT, "tests", "golden", "d159.json")) as f:
+        g = json.load(f)["pairing"]
+    (tmp_path / "p.param").write_text(PARAMS["d159"])
+    (tmp_path / "P.bin").write_bytes(b"".join(bytes.fromhex(x) for x in g["P"]))
+    (tmp_path / "Q.bin").write_bytes(b"".join(bytes.fromhex(x) for x in g["Q"]))
+    libdir = tmp_path / "lib"
+    libdir.mkdir()
+    shutil.copy(sim, str(libdir / "libpbc_b200.so"))
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = str(libdir) + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+    r = subprocess.run([exe, str(tmp_path / "p.param"), str(tmp_path / "P.bin"), str(tmp_path / "Q.bin"),
+                        str(tmp_path / "E.bin")], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert (tmp_path / "E.bin").read_bytes() == b"".join(bytes.fromhex(x) for x in g["e"])
