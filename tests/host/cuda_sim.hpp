@@ -6,7 +6,7 @@
 // once per (block, thread) with blockIdx / threadIdx set.  Threads of a block therefore never run
 // concurrently: fine for these kernels (one pairing per thread; the only barriers are the lock-step
 // ones of miller_cc.cuh, which order instruction fetch, not data).  Shared memory is one static
-// buffer sized like the largest opt-in allocation of an SM.
+// buffer per host thread, sized like the largest opt-in allocation of an SM.
 #pragma once
 #include <stdint.h>
 #include <stdlib.h>
@@ -19,10 +19,14 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3() {} dim3(unsigned a) : x(a) {} dim3(int a) : x((unsigned)a) {} dim3(size_t a) : x((unsigned)a) {} };
 
 namespace cusim {
-inline dim3& tid() { static dim3 v; return v; }
-inline dim3& bid() { static dim3 v; return v; }
-inline dim3& bdim() { static dim3 v; return v; }
-inline dim3& gdim() { static dim3 v; return v; }
+// per host thread: the engine drives each simulated device from its own thread
+inline dim3& tid() { static thread_local dim3 v; return v; }
+inline dim3& bid() { static thread_local dim3 v; return v; }
+inline dim3& bdim() { static thread_local dim3 v; return v; }
+inline dim3& gdim() { static thread_local dim3 v; return v; }
+inline int& current_device() { static thread_local int d = 0; return d; }
+// PBC_SIM_DEVICES=N makes the simulator report N devices (they share the host's memory)
+inline int device_count() { const char* e = getenv("PBC_SIM_DEVICES"); int n = e ? atoi(e) : 1; return n > 0 ? n : 1; }
 inline uint64_t& launches() { static uint64_t n = 0; return n; }
 // optional cap on simulated threads per launch (0 = all): kernels whose padding threads keep
 // computing (k_a_miller's `live` pattern) would otherwise cost a full block per launch
@@ -71,9 +75,9 @@ enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpy
 enum { cudaStreamNonBlocking = 1, cudaHostAllocPortable = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 static inline const char* cudaGetErrorString(cudaError_t) { return "simulated"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
-static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = ::cusim::current_device(); return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int d) { if (d < 0 || d >= ::cusim::device_count()) return 101; ::cusim::current_device() = d; return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = ::cusim::device_count(); return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)malloc(n ? n : 1); if (*p) memset((void*)*p, 0xCD, n); return *p ? 0 : 2; }
 static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }

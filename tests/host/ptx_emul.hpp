@@ -99,7 +99,7 @@ inline std::vector<Insn> parse(const char* text) {
 
 // operands are numbered outputs first, then inputs (GCC extended-asm rule); "+r" outputs are read too
 inline void ptx(const char* text, std::initializer_list<uint32_t*> outs, std::initializer_list<uint32_t> ins) {
-  static std::map<const char*, std::vector<Insn>> cache;
+  static thread_local std::map<const char*, std::vector<Insn>> cache;
   auto it = cache.find(text);
   if (it == cache.end()) it = cache.emplace(text, parse(text)).first;
   uint32_t* o[8];

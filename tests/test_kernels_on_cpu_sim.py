@@ -167,3 +167,35 @@ def test_plain_c_caller_of_the_c_abi_on_the_simulator(sim, tmp_path):
                         str(tmp_path / "E.bin")], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert (tmp_path / "E.bin").read_bytes() == b"".join(bytes.fromhex(x) for x in g["e"])
+
+
+def test_single_process_fan_out_over_two_simulated_devices(sim):
+    """pbc_b200_set_devices (the one-process front end): one host thread and two streams
+    per device, contiguous output slices written at their offset of the caller's buffer.  The
+    simulator reports two devices (PBC_SIM_DEVICES=2): same bytes as one device, twice the launches."""
+    code = """
+import json
+from pbc_b200.pairing import Pairing, kernel_launches
+from pbc_b200.params import PARAMS
+cat = lambda xs: b"".join(bytes.fromhex(x) for x in xs)
+out = {}
+for name in ("a", "f", "d159"):
+    g = json.load(open("tests/golden/%s.json" % name))
+    n = len(g["pairing"]["e"])
+    P, Q, E = cat(g["pairing"]["P"]), cat(g["pairing"]["Q"]), cat(g["pairing"]["e"])
+    pr = Pairing(PARAMS[name])
+    l0 = kernel_launches(); one = pr.apply(P, Q, n); l1 = kernel_launches()
+    pr.set_devices(2)
+    two = pr.apply(P, Q, n); l2 = kernel_launches()
+    odd = pr.apply(P, Q, n - 1)                       # uneven slices
+    k, no = g["prod"]["k"], len(g["prod"]["e"])
+    prod = pr.prod_apply(cat(g["prod"]["P"]), cat(g["prod"]["Q"]), k, no)
+    out[name] = [one == E, two == E, odd == E[:len(odd)], prod == cat(g["prod"]["e"]), l2 - l1 == 2 * (l1 - l0)]
+print(json.dumps(out))
+"""
+    env = _env(sim)
+    env["PBC_SIM_DEVICES"] = "2"
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert all(all(v) for v in res.values()), res
