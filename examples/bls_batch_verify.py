@@ -6,7 +6,7 @@ up): every step is one of the batched entry points of include/pbc_b200.h.
     sign     sigma_i = sk * H(m_i)                          pbc_b200_g1_from_hash, pbc_b200_g1_pow_zn
     verify   e(sigma_i, g2) * e(-H(m_i), pk) == 1           pbc_b200_g1_from_hash, pbc_b200_prod_pairings_apply (k = 2)
 
-usage: python examples/bls_batch_verify.py [a|f|d159|g149] [n]
+usage: python examples/bls_batch_verify.py [a|a1|f|d159|g149] [n]
 """
 import hashlib
 import json
@@ -40,7 +40,9 @@ def main():
     g = json.load(open(os.path.join(ROOT, "tests", "golden", name + ".json")))
     g2 = bytes.fromhex(g["pairing"]["Q"][0])                    # a fixed generator of G2
     rnd = random.Random(2026)
-    sk = rnd.randrange(1, prm["r"]).to_bytes(pr.zr_len, "big")
+    order = prm["n"] if name == "a1" else prm["r"]              # a1.param names the group order n, the field p
+    field = prm["p"] if name == "a1" else prm["q"]
+    sk = rnd.randrange(1, order).to_bytes(pr.zr_len, "big")
     pk = pr.g2_pow_zn(g2, sk, 1)
     msgs = b"".join(hashlib.sha256(b"message %d" % i).digest() for i in range(n))
 
@@ -57,7 +59,7 @@ def main():
 
     t0 = time.perf_counter()
     H2 = pr.g1_from_hash(msgs, 32, n)
-    negH = negate_points(H2, pr.g1_len, prm["q"])
+    negH = negate_points(H2, pr.g1_len, field)
     in1 = b"".join(sig_in[i * pr.g1_len:(i + 1) * pr.g1_len] + negH[i * pr.g1_len:(i + 1) * pr.g1_len] for i in range(n))
     in2 = (g2 + pk) * n
     res = pr.prod_apply(in1, in2, 2, n)
