@@ -98,10 +98,7 @@ inline std::vector<Insn> parse(const char* text) {
 }
 
 // operands are numbered outputs first, then inputs (GCC extended-asm rule); "+r" outputs are read too
-inline void ptx(const char* text, std::initializer_list<uint32_t*> outs, std::initializer_list<uint32_t> ins) {
-  static thread_local std::map<const char*, std::vector<Insn>> cache;
-  auto it = cache.find(text);
-  if (it == cache.end()) it = cache.emplace(text, parse(text)).first;
+inline void run(const std::vector<Insn>& prog, std::initializer_list<uint32_t*> outs, std::initializer_list<uint32_t> ins) {
   uint32_t* o[8];
   uint32_t iv[8];
   int no = 0, ni = 0;
@@ -113,24 +110,35 @@ inline void ptx(const char* text, std::initializer_list<uint32_t*> outs, std::in
     if (x.idx - no >= ni) { fprintf(stderr, "ptx_emul: operand %%%d out of range\n", x.idx); abort(); }
     return iv[x.idx - no];
   };
-  for (const Insn& in : it->second) {
-    executed()++;
-    if ((in.op == MUL || in.op == MAD) && !in.hi) products()++;
+  uint32_t cf = CF();
+  for (const Insn& in : prog) {
     uint64_t r;
-    uint32_t cin = in.carry_in ? CF() : 0;
+    uint32_t cin = in.carry_in ? cf : 0;
     switch (in.op) {
-      case ADD: r = (uint64_t)rd(in.src[0]) + rd(in.src[1]) + cin; if (in.cc) CF() = (uint32_t)(r >> 32); break;
-      case SUB: r = (uint64_t)rd(in.src[0]) - rd(in.src[1]) - cin; if (in.cc) CF() = (uint32_t)((r >> 32) & 1); break;
-      case MUL: { uint64_t m = (uint64_t)rd(in.src[0]) * rd(in.src[1]); r = in.hi ? m >> 32 : (uint32_t)m; break; }
+      case ADD: r = (uint64_t)rd(in.src[0]) + rd(in.src[1]) + cin; if (in.cc) cf = (uint32_t)(r >> 32); break;
+      case SUB: r = (uint64_t)rd(in.src[0]) - rd(in.src[1]) - cin; if (in.cc) cf = (uint32_t)((r >> 32) & 1); break;
+      case MUL: { uint64_t m = (uint64_t)rd(in.src[0]) * rd(in.src[1]); r = in.hi ? m >> 32 : (uint32_t)m; if (!in.hi) products()++; break; }
       default: {
         uint64_t m = (uint64_t)rd(in.src[0]) * rd(in.src[1]);
         r = (uint64_t)(in.hi ? (uint32_t)(m >> 32) : (uint32_t)m) + rd(in.src[2]) + cin;
-        if (in.cc) CF() = (uint32_t)(r >> 32);
+        if (in.cc) cf = (uint32_t)(r >> 32);
+        if (!in.hi) products()++;
       }
     }
     if (in.dst.idx >= no) { fprintf(stderr, "ptx_emul: write to an input operand\n"); abort(); }
     *o[in.dst.idx] = (uint32_t)r;
   }
+  CF() = cf;
+  executed() += prog.size();
+}
+// one parsed program per asm statement of the source (SITE numbers them): no lookup on the hot path
+template <int SITE>
+inline void ptx_at(const char* text, std::initializer_list<uint32_t*> outs, std::initializer_list<uint32_t> ins) {
+  static const std::vector<Insn> prog = parse(text);
+  run(prog, outs, ins);
+}
+inline void ptx(const char* text, std::initializer_list<uint32_t*> outs, std::initializer_list<uint32_t> ins) {
+  run(parse(text), outs, ins);
 }
 
 }  // namespace ptxemu
