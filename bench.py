@@ -50,15 +50,15 @@ WORKLOADS = {
               name="type A (param/a.param) element_pairing, batch 2^20 (P,Q) pairs per GPU, 512-bit F_q",
               dtype="u32 limbs (16 x 32-bit = 512-bit F_q, exact integer)", kernels=("k_a_miller", "k_batch_invert", "k_a_finalexp")),
     "f": dict(param="f", mode="single", k=1, n=1 << 20, unit=78, ref_mulmods=98183, ref_main=None,
-              exec_unit_ops_main=None, cpu_rate=70.0, port_rate=3.0,
+              exec_unit_ops_main=None, exec_unit_ops_all=883715, cpu_rate=70.0, port_rate=3.0,
               name="type F (param/f.param, BN k=12) element_pairing, batch 2^20 pairs per GPU, 158-bit F_q",
               dtype="u32 limbs (5 x 32-bit = 160-bit F_q, exact integer)", kernels=("k_f_miller", "-", "k_f_finalexp")),
     "d": dict(param="d159", mode="single", k=1, n=1 << 18, unit=78, ref_mulmods=23039, ref_main=None,
-              exec_unit_ops_main=None, cpu_rate=350.0, port_rate=10.0,
+              exec_unit_ops_main=None, exec_unit_ops_all=872910, cpu_rate=350.0, port_rate=10.0,
               name="type D (param/d159.param, MNT k=6) element_pairing, batch 2^18 pairs per GPU, 159-bit F_q",
               dtype="u32 limbs (5 x 32-bit = 160-bit F_q, exact integer)", kernels=("k_d_miller", "-", "k_d_finalexp")),
     "g": dict(param="g149", mode="single", k=1, n=1 << 18, unit=78, ref_mulmods=None, ref_main=None,
-              exec_unit_ops_main=None, cpu_rate=110.0, port_rate=3.0,
+              exec_unit_ops_main=None, exec_unit_ops_all=2933830, cpu_rate=110.0, port_rate=3.0,
               name="type G (param/g149.param, Freeman k=10) element_pairing, batch 2^18 pairs per GPU, 149-bit F_q",
               dtype="u32 limbs (5 x 32-bit = 160-bit F_q, exact integer)", kernels=("k_g_miller", "-", "k_g_finalexp")),
     "prod16": dict(param="a", mode="prod", k=16, n=1 << 16, unit=528, ref_mulmods=41536, ref_main=41536 - 719,
@@ -482,10 +482,14 @@ def main():
             # so the roofline is taken over the whole kernel sequence (Miller + final exponentiation)
             kern, kms = "+".join(x for x in w["kernels"] if x != "-"), sum(stage)
             ach_ref = n * (w["ref_mulmods"] or 0) * unit / (kms * 1e-3)
-            ach_exec = None
+            # executed work of the same sequence: 32x32 products per pairing counted by the CPU
+            # simulator of the library while it runs these kernels (tests/test_kernels_on_cpu_sim.py)
+            ach_exec = n * w["exec_unit_ops_all"] / (kms * 1e-3) if w.get("exec_unit_ops_all") else None
             work = ("reference-equivalent %s mulmods x %d unit ops per pairing over the whole kernel sequence "
-                    "(None: SURVEY has no probe for this type, frac is 0); dominant kernel %s = %.0f%% of the step"
-                    % (w["ref_mulmods"], unit, w["kernels"][dom], 100 * stage[dom] / max(sum(stage), 1e-9)))
+                    "(None: SURVEY has no probe for this type, frac is 0), executed %s 32x32 products per pairing; "
+                    "dominant kernel %s = %.0f%% of the step"
+                    % (w["ref_mulmods"], unit, w.get("exec_unit_ops_all"), w["kernels"][dom],
+                       100 * stage[dom] / max(sum(stage), 1e-9)))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
