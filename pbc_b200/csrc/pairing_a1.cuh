@@ -28,16 +28,16 @@ constexpr int kNA1 = 34;       // 32-bit limbs: p < 2^1087
 
 // PBC_A1_SLOTS13 = 1: Miller kernel on the five-temporary slot programs (13 slots, 128 threads per
 // block = one warp per scheduler) instead of 14 slots and 96 threads.  The programs are pinned on
-// the CPU (tests/test_a_steps_host.py, mode "5t"); the kernel variant has not run on a GPU yet, so
-// the measured configuration stays the default.
+// the CPU (tests/test_a_steps_host.py, mode "5t").  Measured on B200 (profiles/r2_variants_a1.jsonl):
+// the same time per block with four warps as with three, i.e. +33 % per SM; default since round 2.
 #ifndef PBC_A1_SLOTS13
-#define PBC_A1_SLOTS13 0
+#define PBC_A1_SLOTS13 1
 #endif
 // PBC_A1_NAF = 1: scan the non-adjacent form of n (host_naf.hpp) instead of its bits: a third fewer
-// chord steps (-11 % multiplier work for a1.param).  Same status as PBC_A1_SLOTS13: pinned on the
-// CPU (mode "naf" of the host harness), not yet run on a GPU.
+// chord steps (-11 % multiplier work for a1.param).  Pinned on the CPU (mode "naf" of the host
+// harness); measured +12 % on B200 (profiles/r2_variants_a1.jsonl), bit-exact; default since round 2.
 #ifndef PBC_A1_NAF
-#define PBC_A1_NAF 0
+#define PBC_A1_NAF 1
 #endif
 constexpr int kA1MillerSlots = PBC_A1_SLOTS13 ? 13 : 14;
 constexpr int kA1MillerBlock = PBC_A1_SLOTS13 ? 128 : 96;

@@ -45,4 +45,28 @@ def test_synthetic_a1_inputs_lie_in_the_order_n_subgroup():
         for i in range(3):
             pt = pr.G1.from_bytes(bytes(buf[i * 260:(i + 1) * 260]))
             assert pt is not None and pr.E.is_valid(pt) and pr.E.mul(pr.r, pt) is None
-    assert w["exec_unit_ops_main"] == 63347304
+    assert w["exec_unit_ops_main"] == 56225715      # signed-digit scan of n (PBC_A1_NAF, default since round 2)
+
+
+def test_parity_sample_is_seeded_distinct_and_reaches_the_last_chunk():
+    """the index sample bench.py checks against oracle/_ref on every rank: distinct, reproducible,
+    different per rank, and always containing the tail of the batch"""
+    sys.path.insert(0, ROOT)
+    import bench
+    a = bench.sample_indices(1 << 20, 20000, 7)
+    b = bench.sample_indices(1 << 20, 20000, 7)
+    c = bench.sample_indices(1 << 20, 20000, 8)
+    assert (a == b).all() and not (a == c).all()
+    assert len(set(a.tolist())) == 20000 and a[-1] == (1 << 20) - 1 and a[-256] == (1 << 20) - 256
+    assert (a[:-256] < (1 << 20) - 256).all() and a[0] >= 0
+    # spread over every 2^18-output pipeline chunk of the host path
+    assert all(((a >> 18) == ch).sum() > 1000 for ch in range(4))
+    assert list(bench.sample_indices(5, 100, 1)) == [0, 1, 2, 3, 4]
+
+
+def test_shard_sizes_follow_the_scaling_mode():
+    sys.path.insert(0, ROOT)
+    import bench
+    W = bench.WORKLOADS
+    assert bench.shard_size(W["a"], 8, "weak") == 1 << 20 and bench.shard_size(W["a"], 8, "strong") == 1 << 17
+    assert bench.shard_size(W["prod16"], 8, "weak") == 1 << 13 and bench.shard_size(W["d"], 2, "weak") == 1 << 18
