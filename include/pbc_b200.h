@@ -18,13 +18,21 @@
  *   - e(O, Q) = e(P, O) = 1 (pairing_apply, include/pbc_pairing.h:118-135); in a product of
  *     pairings ANY infinite input makes the whole product 1 (element_prod_pairing, :153-171);
  *   - every output is bit-identical to the reference CPU path.
+ * One input is DEFINED here rather than copied: a first or second argument with y = 0 (type a, a1: the
+ * 2-torsion point (0, 0); types d, g: a 2-torsion point of E(F_q) if the cofactor is even) lies on the
+ * curve but outside the order-r groups and has no tangent line; the reference's projective doubling
+ * inverts Z = 0 there and returns a by-product of that.  This library decodes such a point as the
+ * point at infinity: the pairing is 1 (tests/test_gpu_edge_cases.py).
  * There is no CPU fallback: without a CUDA device every compute entry point fails.
  *
  * Threading: like the reference (which is not thread-safe) a handle is used by one thread
  * at a time; calls on DIFFERENT handles may come from different threads -- the blocking host-buffer
  * entry points serialise per device (the curve constants of one handle at a time are resident in
  * __constant__ memory).  With the asynchronous _device entry points keep one handle active per
- * device until its stream has drained.
+ * device until its stream has drained.  The _device entry points of ONE handle share a per-device
+ * workspace; the library orders its users with an event (each enqueue records it, the next enqueue's
+ * stream waits for it), so calls of one handle on different streams serialise on the workspace
+ * rather than overlap.
  *
  * Return convention: 0 on success, non-zero on failure (pairing_init_set_buf returns 1 on
  * failure, ecc/pairing.c:88-98); pbc_b200_last_error() gives the message the reference would
@@ -89,6 +97,19 @@ int pbc_b200_pp_pairings_apply(pbc_b200_pairing_t *p, unsigned char *out, const 
                                const unsigned char *in2, size_t n);
 int pbc_b200_pp_pairings_apply_device(pbc_b200_pairing_t *p, void *d_out, const void *d_in1,
                                       const void *d_in2, size_t n, void *stream);
+
+/* pairing_pp_init / pairing_pp_apply / pairing_pp_clear (include/pbc_pairing.h:54-89 ->
+ * a_pairing_pp_init/apply/clear ecc/a_param.c:149-220 and :317-360, a1: :1632-1818,
+ * d_pairing_pp_* ecc/d_param.c:794-991): the preprocessing of one fixed first argument is done ONCE,
+ * kept in device memory by the handle, and reused by every apply until clear -- what pairing_pp_t
+ * is for.  Types a and a1 keep the table of line coefficients (160 / about 1 500 rows; an apply then
+ * costs 7 instead of 17-19 multiplications per step); types f, d and g keep the decoded point.
+ * The handle lives on the device that was current at init; apply switches to it. */
+typedef struct pbc_b200_pp_s pbc_b200_pp_t;
+int pbc_b200_pp_init(pbc_b200_pairing_t *p, pbc_b200_pp_t **pp, const unsigned char *in1);
+int pbc_b200_pp_apply(pbc_b200_pp_t *pp, unsigned char *out, const unsigned char *in2, size_t n);
+int pbc_b200_pp_apply_device(pbc_b200_pp_t *pp, void *d_out, const void *d_in2, size_t n, void *stream);
+void pbc_b200_pp_clear(pbc_b200_pp_t *pp);
 
 /* ---- the operations either side of the pairing ---------------------
  * Batched element_pow_zn (include/pbc_field.h:262-275 -> arith/field.c:113-126):

@@ -37,6 +37,11 @@ lib.pbc_b200_prod_pairings_apply.argtypes = [_P, _P, _P, _P, C.c_size_t, C.c_siz
 lib.pbc_b200_prod_pairings_apply_device.argtypes = [_P, _P, _P, _P, C.c_size_t, C.c_size_t, _P]
 lib.pbc_b200_pp_pairings_apply.argtypes = [_P, _P, _P, _P, C.c_size_t]
 lib.pbc_b200_pp_pairings_apply_device.argtypes = [_P, _P, _P, _P, C.c_size_t, _P]
+lib.pbc_b200_pp_init.argtypes = [_P, C.POINTER(_P), _P]
+lib.pbc_b200_pp_apply.argtypes = [_P, _P, _P, C.c_size_t]
+lib.pbc_b200_pp_apply_device.argtypes = [_P, _P, _P, C.c_size_t, _P]
+lib.pbc_b200_pp_clear.argtypes = [_P]
+lib.pbc_b200_pp_clear.restype = None
 lib.pbc_b200_pairing_length_in_bytes_Zr.argtypes = [_P]
 for _n in ("g1_pow_zn", "g2_pow_zn", "gt_pow_zn"):
     getattr(lib, "pbc_b200_" + _n).argtypes = [_P, _P, _P, _P, C.c_size_t]

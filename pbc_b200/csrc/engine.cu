@@ -26,6 +26,7 @@
 #include "pairing_a1.cuh"
 #include "pairing_d.cuh"
 #include "pairing_f.cuh"
+#include "pairing_f_slots.cuh"
 #include "pairing_g.cuh"
 #include "group_a.cuh"
 #include "group_a1.cuh"
@@ -99,9 +100,14 @@ struct DevCtx {
   uint8_t* d_out[2] = {nullptr, nullptr};
   void* ws[2] = {nullptr, nullptr};
   size_t cap_in1[2] = {0, 0}, cap_in2[2] = {0, 0}, cap_out[2] = {0, 0}, cap_ws[2] = {0, 0};   // bytes
-  // device-API workspace
+  // device-API workspace: one per handle and device, shared by every _device entry point and by the
+  // host paths of the group operations.  ws_ev orders its users: each enqueue records it on its
+  // stream and the next user's stream waits for it, so calls on different streams serialise on the
+  // workspace instead of racing on it.
   void* ws_dev = nullptr;
   size_t cap_dev = 0;          // bytes
+  cudaEvent_t ws_ev = nullptr;
+  bool ws_used = false;
   // optional per-stage timing of the device-API path (bench.py roofline)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -162,6 +168,11 @@ enum Mode { kSingle = 0, kProd = 1, kPP = 2 };
 struct Job {
   Mode mode = kSingle;
   size_t k = 1;                // kProd: pairings per output
+  // kPP through a pairing_pp_t (pbc_b200_pp_init): what the handle keeps on the device -- the
+  // line-coefficient table (types a, a1) and the wire bytes of the fixed first argument (all types).
+  // nullptr: the table is built inside the call (pbc_b200_pp_pairings_apply).
+  const void* pp_tab = nullptr;
+  const uint8_t* pp_in1 = nullptr;
 };
 
 // workspace bytes for n_out outputs of `job`
@@ -175,14 +186,17 @@ static size_t ws_bytes(const pbc_b200_pairing_s* p, const Job& job, size_t n_out
   }
   if (p->type == 'a') {
     const size_t fq = 64;
-    if (job.mode == kSingle) return n_out * (2 + 1 + 1 + 5) * fq;
-    if (job.mode == kProd) return n_out * job.k * (2 + 1 + 5) * fq + n_out * (2 + 1 + 1) * fq;
+    // f [2], dprod, prefix, save [5] (V1, f1), qm [2] (Montgomery-form Q of the nine-slot Miller kernel)
+    if (job.mode == kSingle) return n_out * (2 + 1 + 1 + 5 + 2) * fq;
+    if (job.mode == kProd) return n_out * job.k * (2 + 1 + 5 + 2) * fq + n_out * (2 + 1 + 1) * fq;
     return n_out * (2 + 1 + 1) * fq + (size_t)(3 * (p->a.exp2 + 1) * kNA + 4) * 4;
   }
   // types f, d: Miller values [W][n] words + one flag word each; products add the reduced arrays
   size_t W = p->type == 'f' ? kF12Words : (p->type == 'g' ? kF10Words : kF6DWords);
   size_t n_in = job.mode == kProd ? n_out * job.k : n_out;
   size_t bytes = n_in * (W + 1) * 4;
+  if (p->type == 'f') bytes += n_in * (size_t)kFGWords * 4;   // Q, P of the slot-machine Miller kernel
+  if (p->type == 'f') bytes += n_out * (size_t)kFStashWords * 4;   // parked F_q^12 values of the slot-machine final exponentiation
   if (job.mode == kProd) bytes += n_out * (W + 1) * 4;
   return bytes;
 }
@@ -229,15 +243,18 @@ static int init_type_a(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   if (!get_big(tab, "q", &q) || !get_big(tab, "r", &r) || !get_big(tab, "h", &h)) return 1;
   if (!get_int(tab, "exp2", &exp2) || !get_int(tab, "exp1", &exp1) ||
       !get_int(tab, "sign1", &sign1) || !get_int(tab, "sign0", &sign0)) return 1;
-  if (q.bits() > 512 || q.bits() <= 480) return fail("type a: this build supports 481..512-bit q (got %zu)", q.bits());
+  // 64-byte coordinates on the wire (arith/montfp.c fixed_length_in_bytes = ceil(bits(q) / 8)): 505..512 bits
+  if (q.bits() > 512 || q.bits() <= 504) return fail("type a: this build supports 505..512-bit q (64-byte coordinates; got %zu bits)", q.bits());
+  if (r.bits() > 160 || r.bits() < 3) return fail("type a: this build supports group orders of up to 160 bits (got %zu)", r.bits());
   if (q.word(0) % 4 != 3) return fail("type a: q must be 3 mod 4");
   if (!((r * h) == (q + BigUInt(1)))) return fail("type a: r*h != q+1");
   if (h.bits() > 384) return fail("type a: cofactor too large");
-  if (exp1 <= 0 || exp2 <= exp1) return fail("type a: bad exp1/exp2");
+  if (exp1 <= 0 || exp2 <= exp1 || exp2 > 512) return fail("type a: bad exp1/exp2");
   p->type = 'a';
   memset(&p->zr, 0, sizeof p->zr);
   r.to_words(p->zr.r, 5);
   p->zr.zlen = (uint32_t)((r.bits() + 7) / 8);
+  p->zr_len = (int)p->zr.zlen;               // host copies, the Python mirror and the kernels' stride agree
   p->nlimbs = kNA;
   p->full = true;
   p->g1_len = p->g2_len = p->gt_len = 128;
@@ -412,7 +429,8 @@ static int init_type_f(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   BigUInt q, r, b, beta, a0, a1;
   if (!get_big(tab, "q", &q) || !get_big(tab, "r", &r) || !get_big(tab, "b", &b) ||
       !get_big(tab, "beta", &beta) || !get_big(tab, "alpha0", &a0) || !get_big(tab, "alpha1", &a1)) return 1;
-  if (q.bits() > 159 || q.bits() < 129) return fail("type f: this build supports 129..159-bit q (got %zu)", q.bits());
+  // 20-byte coordinates on the wire (ceil(bits(q) / 8), arith/montfp.c:577): 153..159 bits
+  if (q.bits() > 159 || q.bits() < 153) return fail("type f: this build supports 153..159-bit q (20-byte coordinates; got %zu bits)", q.bits());
   if (r.bits() > 160 || r.bits() < 3) return fail("type f: bad group order");
   BigUInt six(6);
   if (!((q % six) == BigUInt(1))) return fail("type f: q must be 1 mod 6");
@@ -420,6 +438,7 @@ static int init_type_f(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   memset(&p->zr, 0, sizeof p->zr);
   r.to_words(p->zr.r, 5);
   p->zr.zlen = (uint32_t)((r.bits() + 7) / 8);
+  p->zr_len = (int)p->zr.zlen;
   p->nlimbs = kNS;
   p->full = false;
   p->g1_len = 2 * kWS; p->g2_len = 4 * kWS; p->gt_len = 12 * kWS;
@@ -476,6 +495,10 @@ static int init_type_f(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   put2(c.kx, kx);
   put2(c.ky, ky);
   (q * q).to_words(c.qsq, 2 * kNS);
+  for (int k = 0; k < 3; k++) (q * q * BigUInt((uint64_t)(k + 1))).to_words(c.qsqm[k], 2 * kNS);
+  // the slot-machine kernels accumulate up to three F_q^2 products (each below 2 q^2) before one
+  // reduction of a value below 2 q R: needs 6 q^2 < 2 q 2^160
+  c.slots_ok = (c.nice && (q * BigUInt(3)).bits() <= 160) ? 1u : 0u;
   to_mont(c.sigma, sigma, q, kNS);
   to_mont(c.sigma_inv, sigma_inv, q, kNS);
   for (int j = 1; j < 6; j++) { put2(c.tau[j - 1], taup[j]); put2(c.tau_inv[j - 1], tauinv[j]); }
@@ -537,12 +560,13 @@ static int init_type_d(pbc_b200_pairing_s* p, const std::map<std::string, std::s
       !get_int(tab, "k", &k) || !get_big(tab, "nqr", &nqr) || !get_big(tab, "coeff0", &c0) ||
       !get_big(tab, "coeff1", &c1) || !get_big(tab, "coeff2", &c2)) return 1;
   if (k != 6) return fail("type d: only embedding degree 6 is on the B200 hot path (got k = %d)", k);
-  if (q.bits() > 159 || q.bits() < 129) return fail("type d: this build supports 129..159-bit q (got %zu)", q.bits());
+  if (q.bits() > 159 || q.bits() < 153) return fail("type d: this build supports 153..159-bit q (20-byte coordinates; got %zu bits)", q.bits());
   if (r.bits() > 160 || r.bits() < 3) return fail("type d: bad group order");
   p->type = 'd';
   memset(&p->zr, 0, sizeof p->zr);
   r.to_words(p->zr.r, 5);
   p->zr.zlen = (uint32_t)((r.bits() + 7) / 8);
+  p->zr_len = (int)p->zr.zlen;
   p->nlimbs = kNS;
   p->full = false;
   p->g1_len = 2 * kWS; p->g2_len = 6 * kWS; p->gt_len = 6 * kWS;
@@ -696,6 +720,20 @@ static cudaError_t allow_smem(K kernel, size_t bytes) {
 }
 
 static constexpr size_t kSmemAMiller = (size_t)kASlots * 64 * kBlockMiller;
+// PBC_A_SLOTS9 = 1 (default): the nine-slot Miller kernel, three 128-thread blocks per SM; 0: the
+// 14-slot kernel of round 1 (two blocks per SM) -- kept for A/B runs
+#ifndef PBC_A_SLOTS9
+#define PBC_A_SLOTS9 1
+#endif
+static constexpr size_t kSmemAMiller9 = (size_t)kA9Slots * 64 * kBlockMiller;
+// PBC_F_SLOTS = 1 (default): type F Miller loop on the shared-memory slot machine (pairing_f_slots.cuh)
+// where the parameters allow it; 0: the round-1 kernel (local-memory frames)
+#ifndef PBC_F_SLOTS
+#define PBC_F_SLOTS 1
+#endif
+static constexpr int kBlockFS = 128;
+static constexpr size_t kSmemFMillerS = (size_t)kFSlots * kNS * 4 * kBlockFS;
+static constexpr size_t kSmemFFinalS = (size_t)kFFinalSlots * kNS * 4 * kBlockFS;
 static constexpr size_t kSmemAFinal = (size_t)kAFSlots * 64 * kBlockFinal;
 static constexpr size_t kSmemInv16 = (size_t)5 * 64 * kBlockInv;
 static constexpr int kBlockProd = 128;
@@ -727,6 +765,7 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
     for (int s = 0; s < 2; s++) CUDA_OK(cudaStreamCreateWithFlags(&c.stream[s], cudaStreamNonBlocking));
     if (p->type == 'a') {
       CUDA_OK(allow_smem(k_a_miller<kBlockMiller>, kSmemAMiller));
+      CUDA_OK(allow_smem(k_a_miller9<kBlockMiller>, kSmemAMiller9));
       CUDA_OK(allow_smem(k_a_finalexp<kBlockFinal>, kSmemAFinal));
       CUDA_OK(allow_smem(k_batch_invert<kNA, true, kBlockInv>, kSmemInv16));
       CUDA_OK(allow_smem(k_fpmul_slots<kNA, true, 128, 0>, 2 * 64 * 128));
@@ -739,6 +778,8 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
       CUDA_OK(allow_smem(k_a_g1_from_hash<kBlockMiller>, (size_t)kGSlots * 64 * kBlockMiller));
       CUDA_OK(allow_smem(k_a_g1_decompress<kBlockMiller>, (size_t)5 * 64 * kBlockMiller));
     }
+    if (p->type == 'f') CUDA_OK(allow_smem(k_f_miller_s<kBlockFS>, kSmemFMillerS));
+    if (p->type == 'f') CUDA_OK(allow_smem(k_f_finalexp_s<kBlockFS>, kSmemFFinalS));
     if (p->type == '1') {
       CUDA_OK(allow_smem(k_a1_miller<kBlockA1>, kSmemA1Miller));
       CUDA_OK(allow_smem(k_a1_finalexp<kBlockA1Small>, kSmemA1Final));
@@ -802,8 +843,21 @@ static void ctx_release(DevCtx& c) {
     if (c.stream[s]) cudaStreamDestroy(c.stream[s]);
   }
   cudaFree(c.ws_dev);
+  if (c.ws_ev) cudaEventDestroy(c.ws_ev);
   for (int i = 0; i < 4; i++) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
   c = DevCtx();
+}
+
+// the shared device workspace is about to be used by work enqueued on `st` / has just been used
+static int ws_acquire(DevCtx& c, cudaStream_t st) {
+  if (!c.ws_ev) CUDA_OK(cudaEventCreateWithFlags(&c.ws_ev, cudaEventDisableTiming));
+  if (c.ws_used) CUDA_OK(cudaStreamWaitEvent(st, c.ws_ev, 0));
+  return 0;
+}
+static int ws_release(DevCtx& c, cudaStream_t st) {
+  CUDA_OK(cudaEventRecord(c.ws_ev, st));
+  c.ws_used = true;
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -847,8 +901,8 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
       dprod = f + 2 * E * n;
       prefix = dprod + E * n;
       uint32_t* tab = (uint32_t*)(prefix + E * n);
-      k_a1_pp_init<32><<<1, 32, kSmemA1PPInit, st>>>(d_in1, tab, p->a1_rows);
-      LAUNCHED();
+      if (job.pp_tab) tab = (uint32_t*)job.pp_tab;
+      else { k_a1_pp_init<32><<<1, 32, kSmemA1PPInit, st>>>(d_in1, tab, p->a1_rows); LAUNCHED(); }
       unsigned gm = (unsigned)((n + kBlockA1Small - 1) / kBlockA1Small);
       k_a1_pp_apply<kBlockA1Small><<<gm, kBlockA1Small, kSmemA1PP, st>>>(tab, d_in2, f, dprod, n, p->a1_rows);
       LAUNCHED();
@@ -874,19 +928,23 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
       dprod = f + 8 * n;                         // [4][n]
       prefix = dprod + 4 * n;                    // [4][n]
       uint4* save = prefix + 4 * n;              // [5][4][n]
+      uint4* qm = save + 20 * n;                 // [2][4][n]
       unsigned gm = (unsigned)((n + kBlockMiller - 1) / kBlockMiller);
-      k_a_miller<kBlockMiller><<<gm, kBlockMiller, kSmemAMiller, st>>>(d_in1, d_in2, f, dprod, save, n);
+      if (PBC_A_SLOTS9) k_a_miller9<kBlockMiller><<<gm, kBlockMiller, kSmemAMiller9, st>>>(d_in1, d_in2, f, dprod, save, qm, n);
+      else k_a_miller<kBlockMiller><<<gm, kBlockMiller, kSmemAMiller, st>>>(d_in1, d_in2, f, dprod, save, n);
       LAUNCHED();
     } else if (job.mode == kProd) {
       size_t m = n * job.k;
       uint4* fi = (uint4*)ws;                    // [2][4][m]
       uint4* di = fi + 8 * m;                    // [4][m]
       uint4* save = di + 4 * m;                  // [5][4][m]
-      f = save + 20 * m;                         // [2][4][n]
+      uint4* qm = save + 20 * m;                 // [2][4][m]
+      f = qm + 8 * m;                            // [2][4][n]
       dprod = f + 8 * n;
       prefix = dprod + 4 * n;
       unsigned gm = (unsigned)((m + kBlockMiller - 1) / kBlockMiller);
-      k_a_miller<kBlockMiller><<<gm, kBlockMiller, kSmemAMiller, st>>>(d_in1, d_in2, fi, di, save, m);
+      if (PBC_A_SLOTS9) k_a_miller9<kBlockMiller><<<gm, kBlockMiller, kSmemAMiller9, st>>>(d_in1, d_in2, fi, di, save, qm, m);
+      else k_a_miller<kBlockMiller><<<gm, kBlockMiller, kSmemAMiller, st>>>(d_in1, d_in2, fi, di, save, m);
       LAUNCHED();
       unsigned gp = (unsigned)((n + kBlockProd - 1) / kBlockProd);
       k_a_prod<kBlockProd><<<gp, kBlockProd, kSmemAProd, st>>>(fi, di, f, dprod, job.k, n, m);
@@ -896,8 +954,8 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
       dprod = f + 8 * n;
       prefix = dprod + 4 * n;
       uint32_t* tab = (uint32_t*)(prefix + 4 * n);
-      k_a_pp_init<32><<<1, 32, kSmemAPPInit, st>>>(d_in1, tab);
-      LAUNCHED();
+      if (job.pp_tab) tab = (uint32_t*)job.pp_tab;
+      else { k_a_pp_init<32><<<1, 32, kSmemAPPInit, st>>>(d_in1, tab); LAUNCHED(); }
       unsigned gm = (unsigned)((n + kBlockMiller - 1) / kBlockMiller);
       k_a_pp_apply<kBlockMiller><<<gm, kBlockMiller, kSmemAPPApply, st>>>(tab, d_in2, f, dprod, n);
       LAUNCHED();
@@ -922,9 +980,13 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
     uint32_t* mv = (uint32_t*)ws;                // [W][m]
     uint32_t* flag = mv + W * m;                 // [m]
     size_t stride1 = job.mode == kPP ? 0 : (size_t)p->g1_len;
+    if (job.mode == kPP && job.pp_in1) d_in1 = job.pp_in1;
     unsigned gm = (unsigned)((m + kBlockCCMiller - 1) / kBlockCCMiller);
     STAGE(0);
-    if (isf) k_f_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1);
+    if (isf && PBC_F_SLOTS && p->f.slots_ok) {
+      uint32_t* gq = mv + (W + 1) * m + (job.mode == kProd ? (W + 1) * n : 0);   // after the Miller values and flags
+      k_f_miller_s<kBlockFS><<<(unsigned)((m + kBlockFS - 1) / kBlockFS), kBlockFS, kSmemFMillerS, st>>>(d_in1, d_in2, mv, flag, gq, m, stride1);
+    } else if (isf) k_f_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1);
     else if (isg) k_g_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1);
     else k_d_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1);
     LAUNCHED();
@@ -942,7 +1004,10 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
     STAGE(2);
     unsigned gf = (unsigned)((n + kBlockCC - 1) / kBlockCC);
     unsigned gfm = (unsigned)((n + kBlockCCMiller - 1) / kBlockCCMiller);
-    if (isf) k_f_finalexp<kBlockCCMiller><<<gfm, kBlockCCMiller, 0, st>>>(mv, flag, d_out, n);
+    if (isf && PBC_F_SLOTS && p->f.slots_ok && p->f.bn) {
+      uint32_t* stash = (uint32_t*)ws + (W + 1) * m + (job.mode == kProd ? (W + 1) * n : 0) + (size_t)kFGWords * m;
+      k_f_finalexp_s<kBlockFS><<<(unsigned)((n + kBlockFS - 1) / kBlockFS), kBlockFS, kSmemFFinalS, st>>>(mv, flag, d_out, stash, n);
+    } else if (isf) k_f_finalexp<kBlockCCMiller><<<gfm, kBlockCCMiller, 0, st>>>(mv, flag, d_out, n);
     else if (isg) k_g_finalexp<kBlockCCMiller><<<gfm, kBlockCCMiller, 0, st>>>(mv, flag, d_out, n);
     else k_d_finalexp<kBlockCC><<<gf, kBlockCC, 0, st>>>(mv, flag, d_out, n);
     LAUNCHED();
@@ -984,7 +1049,8 @@ static int run_slice(pbc_b200_pairing_s* p, int dev, const Job& job, unsigned ch
     int s = k & 1;
     cudaStream_t st = c.stream[s];
     size_t o1 = job.mode == kPP ? 0 : in1_elems(job, off) * p->g1_len;
-    CUDA_OK(cudaMemcpyAsync(c.d_in1[s], in1 + o1, in1_elems(job, m) * p->g1_len, cudaMemcpyHostToDevice, st));
+    if (!job.pp_in1)
+      CUDA_OK(cudaMemcpyAsync(c.d_in1[s], in1 + o1, in1_elems(job, m) * p->g1_len, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(c.d_in2[s], in2 + in2_elems(job, off) * p->g2_len, in2_elems(job, m) * p->g2_len,
                             cudaMemcpyHostToDevice, st));
     if (enqueue_pairings(p, job, c.d_out[s], c.d_in1[s], c.d_in2[s], m, c.ws[s], st)) return 1;
@@ -998,12 +1064,12 @@ static int run_slice(pbc_b200_pairing_s* p, int dev, const Job& job, unsigned ch
 // contiguous slices of the outputs, one host thread per device, results written at the slice offset
 static int run_host(pbc_b200_pairing_s* p, const Job& job, unsigned char* out, const unsigned char* in1,
                     const unsigned char* in2, size_t n) {
-  if (!p || (!out && n) || (!in1 && n) || (!in2 && n)) return fail("null argument");
+  if (!p || (!out && n) || (!in1 && n && !job.pp_in1) || (!in2 && n)) return fail("null argument");
   if (n == 0) return 0;
   std::lock_guard<std::mutex> lk(p->mu);
   int cur = 0;
   CUDA_OK(cudaGetDevice(&cur));
-  if (p->ndev <= 1) return run_slice(p, cur, job, out, in1, in2, n);
+  if (p->ndev <= 1 || job.pp_in1) return run_slice(p, cur, job, out, in1, in2, n);   // a pp handle lives on one device
   int nd = p->ndev;
   if ((int)p->ctx.size() < nd) p->ctx.resize(nd);   // sized here: the per-device threads must not resize it
   std::vector<int> rc(nd, 0);
@@ -1044,8 +1110,10 @@ static int run_device(pbc_b200_pairing_s* p, const Job& job, void* d_out, const 
   }
   if (p->profile && !c.ev[0])
     for (int i = 0; i < 4; i++) CUDA_OK(cudaEventCreate(&c.ev[i]));
-  return enqueue_pairings(p, job, (uint8_t*)d_out, (const uint8_t*)d_in1, (const uint8_t*)d_in2, n,
-                          c.ws_dev, (cudaStream_t)stream, p->profile ? c.ev : nullptr);
+  if (ws_acquire(c, (cudaStream_t)stream)) return 1;
+  if (enqueue_pairings(p, job, (uint8_t*)d_out, (const uint8_t*)d_in1, (const uint8_t*)d_in2, n,
+                       c.ws_dev, (cudaStream_t)stream, p->profile ? c.ev : nullptr)) return 1;
+  return ws_release(c, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1157,6 +1225,84 @@ int pbc_b200_pp_pairings_apply(pbc_b200_pairing_t* p, unsigned char* out, const 
 int pbc_b200_pp_pairings_apply_device(pbc_b200_pairing_t* p, void* d_out, const void* d_in1,
                                       const void* d_in2, size_t n, void* stream) {
   return run_device(p, Job{kPP, 1}, d_out, d_in1, d_in2, n, stream);
+}
+
+// ---- pairing_pp_t (include/pbc_pairing.h:54-89): preprocessing kept on the device ----
+struct pbc_b200_pp_s {
+  pbc_b200_pairing_s* p = nullptr;
+  int dev = 0;
+  uint8_t* d_in1 = nullptr;     // wire bytes of the fixed first argument
+  void* d_tab = nullptr;        // types a, a1: line-coefficient table
+};
+
+int pbc_b200_pp_init(pbc_b200_pairing_t* p, pbc_b200_pp_t** out, const unsigned char* in1) {
+  if (!p || !out || !in1) return fail("null argument");
+  *out = nullptr;
+  std::lock_guard<std::mutex> lk(p->mu);
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> dev_lock(g_dev_mu[dev & 63]);
+  if (ctx_prepare(p, dev)) return 1;
+  DevCtx& c = p->ctx[dev];
+  pbc_b200_pp_s* pp = new pbc_b200_pp_s();
+  pp->p = p;
+  pp->dev = dev;
+  cudaStream_t st = c.stream[0];
+  size_t tab_bytes = 0;
+  if (p->type == 'a') tab_bytes = (size_t)(3 * (p->a.exp2 + 1) * kNA + 4) * 4;
+  if (p->type == '1') tab_bytes = (p->a1_rows * kNA1 + 4) * 4;
+  cudaError_t e = cudaMalloc(&pp->d_in1, (size_t)p->g1_len);
+  if (e == cudaSuccess && tab_bytes) e = cudaMalloc(&pp->d_tab, tab_bytes);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pp->d_in1, in1, (size_t)p->g1_len, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && p->type == 'a') { k_a_pp_init<32><<<1, 32, kSmemAPPInit, st>>>(pp->d_in1, (uint32_t*)pp->d_tab); LAUNCHED(); }
+  if (e == cudaSuccess && p->type == '1') { k_a1_pp_init<32><<<1, 32, kSmemA1PPInit, st>>>(pp->d_in1, (uint32_t*)pp->d_tab, p->a1_rows); LAUNCHED(); }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cudaFree(pp->d_in1); cudaFree(pp->d_tab);
+    delete pp;
+    return fail("pp_init: %s", cudaGetErrorString(e));
+  }
+  *out = pp;
+  return 0;
+}
+
+static Job pp_job(const pbc_b200_pp_s* pp) {
+  Job j;
+  j.mode = kPP;
+  j.pp_tab = pp->d_tab;
+  j.pp_in1 = pp->d_in1;
+  return j;
+}
+
+int pbc_b200_pp_apply(pbc_b200_pp_t* pp, unsigned char* out, const unsigned char* in2, size_t n) {
+  if (!pp) return fail("null argument");
+  int cur = 0;
+  CUDA_OK(cudaGetDevice(&cur));
+  if (cur != pp->dev) CUDA_OK(cudaSetDevice(pp->dev));
+  int rc = run_host(pp->p, pp_job(pp), out, nullptr, in2, n);
+  if (cur != pp->dev) cudaSetDevice(cur);
+  return rc;
+}
+
+int pbc_b200_pp_apply_device(pbc_b200_pp_t* pp, void* d_out, const void* d_in2, size_t n, void* stream) {
+  if (!pp) return fail("null argument");
+  int cur = 0;
+  CUDA_OK(cudaGetDevice(&cur));
+  if (cur != pp->dev) return fail("pp_apply_device: the handle was initialised on device %d", pp->dev);
+  return run_device(pp->p, pp_job(pp), d_out, pp->d_in1, d_in2, n, stream);
+}
+
+void pbc_b200_pp_clear(pbc_b200_pp_t* pp) {
+  if (!pp) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  cudaSetDevice(pp->dev);
+  cudaDeviceSynchronize();
+  cudaFree(pp->d_in1);
+  cudaFree(pp->d_tab);
+  cudaSetDevice(cur);
+  delete pp;
 }
 
 int pbc_b200_set_stage_profiling(pbc_b200_pairing_t* p, int on) {
@@ -1347,12 +1493,16 @@ static int run_group(pbc_b200_pairing_s* p, int which, unsigned char* out, const
     CUDA_OK(cudaMalloc(&c.ws_dev, wsb + stage));
     c.cap_dev = wsb + stage;
   }
-  if (device)
-    return enqueue_group(p, which, (uint8_t*)out, (const uint8_t*)in, (const uint8_t*)k, n, c.ws_dev, (cudaStream_t)stream);
+  if (device) {
+    if (ws_acquire(c, (cudaStream_t)stream)) return 1;
+    if (enqueue_group(p, which, (uint8_t*)out, (const uint8_t*)in, (const uint8_t*)k, n, c.ws_dev, (cudaStream_t)stream)) return 1;
+    return ws_release(c, (cudaStream_t)stream);
+  }
   uint8_t* d_in = (uint8_t*)c.ws_dev + wsb;
   uint8_t* d_out = d_in + n * elen;
   uint8_t* d_k = d_out + n * elen;
   cudaStream_t st = c.stream[0];
+  if (ws_acquire(c, st)) return 1;           // a _device call of this handle may still be using the workspace
   CUDA_OK(cudaMemcpyAsync(d_in, in, n * elen, cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemcpyAsync(d_k, k, n * (size_t)p->zr_len, cudaMemcpyHostToDevice, st));
   if (enqueue_group(p, which, d_out, d_in, d_k, n, c.ws_dev, st)) return 1;
@@ -1416,6 +1566,7 @@ static int run_from_hash(pbc_b200_pairing_s* p, unsigned char* out, const unsign
     c.cap_dev = wsb + stage;
   }
   cudaStream_t st = device ? (cudaStream_t)stream : c.stream[0];
+  if (ws_acquire(c, st)) return 1;
   uint8_t* d_out = device ? (uint8_t*)out : (uint8_t*)c.ws_dev + wsb;
   const uint8_t* d_data = device ? (const uint8_t*)data : d_out + n * elen;
   if (!device) CUDA_OK(cudaMemcpyAsync((void*)d_data, data, n * len, cudaMemcpyHostToDevice, st));
@@ -1457,8 +1608,9 @@ static int run_from_hash(pbc_b200_pairing_s* p, unsigned char* out, const unsign
   if (!device) {
     CUDA_OK(cudaMemcpyAsync(out, d_out, n * elen, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
   }
-  return 0;
+  return ws_release(c, st);
 }
 
 extern "C" {
@@ -1494,6 +1646,7 @@ extern "C" int pbc_b200_g1_from_bytes_compressed(pbc_b200_pairing_t* p, unsigned
     c.cap_dev = need;
   }
   cudaStream_t st = c.stream[0];
+  if (ws_acquire(c, st)) return 1;
   uint8_t* d_out = (uint8_t*)c.ws_dev;               // element output first: keeps it 4-byte aligned
   uint8_t* d_in = d_out + n * elen;
   CUDA_OK(cudaMemcpyAsync(d_in, in, n * clen, cudaMemcpyHostToDevice, st));

@@ -69,7 +69,7 @@ __device__ __forceinline__ bool cc_on_curve(const Fq& x, const Fq& y) {
   fq_mul(t, t, x);
   fq_add(t, t, B);
   fq_sqr(u, y);
-  return fq_eq(t, u);
+  return fq_eq(t, u) && !fq_is_zero(y);    // a 2-torsion point (y = 0) has no tangent line: decoded as O
 }
 
 // T supplies:  struct Acc;  struct Ctx;

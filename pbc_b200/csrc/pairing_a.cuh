@@ -39,6 +39,9 @@ constexpr int kWA = 64;        // wire bytes per coordinate
 
 // Loads P and Q (wire format), converts to Montgomery form, validates y^2 = x^3 + x
 // (ecc/curve.c:57-76, :611-623: off-curve input becomes O).  Returns false for O.
+// The 2-torsion point (0, 0) -- on the curve, outside G1, the one affine point without a tangent
+// line -- is decoded as O as well (documented in include/pbc_b200.h; the reference inverts Z = 0
+// there and returns a by-product of that).
 template <class O>
 __device__ __forceinline__ bool a_load_point(int sx, int sy, int st0, int st1, const uint8_t* p) {
   uint32_t x[kNA];
@@ -53,7 +56,7 @@ __device__ __forceinline__ bool a_load_point(int sx, int sy, int st0, int st1, c
   O::add(st0, st0, st1);      // x^2 + 1
   O::mul(st0, st0, sx);       // x^3 + x
   O::sqr(st1, sy);
-  return O::eq(st0, st1);
+  return O::eq(st0, st1) && !O::is_zero(sy);
 }
 
 // The step in weight-(1,2) coordinates x = X/Z, y = Y/Z^2 (the doubling of Costello, Lange and
@@ -237,6 +240,156 @@ k_a_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4* 
   O::st_global(f, 0, n, idx, aF0);
   O::st_global(f, 1, n, idx, aF1);
   O::st_global(dprod, 0, n, idx, aT0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same Miller loop on NINE slots (round 2).  k_a_miller above keeps 14 slots = 112 KB per
+// 128-thread block: two blocks = 8 warps per SM, shared-memory bound (ncu: fmaheavy 76 % active,
+// top stall = fixed-latency wait).  Here
+//   * Q (used twice per step, as one operand of a multiplication) lives in a limb-major global array
+//     in Montgomery form and is read through Ops::mulg -- L2-resident, the latency is covered by the
+//     other warps;
+//   * the step is re-scheduled around slot lifetimes (below): V = (X, Y, Z), f and four temporaries;
+//   * the two Karatsuba sums of the f update never get a slot (Ops::mul2).
+// 9 x 64 B x 128 threads = 72 KB per block: THREE blocks = 12 warps per SM, three per scheduler.
+// Cost: 2 Y Z is a product instead of (Y + Z)^2 - B - C (+120 of 8 136 IMAD.WIDE per step); the
+// additive calls drop from 22 to 16 (+ one copy).
+//
+//   g = f^2:            g0 = (f0 + f1)(f0 - f1),  g1 = 2 f0 f1
+//   A = X^2, B = Y^2, C = Z^2;  T = A - C,  A' = A + C,  U = 2 A' + T = 3A + C
+//   Re l = U Z Qx + X T,   Im l = 2 Y Z Qy
+//   X' = T^2,  E = 2 A'^2 - X',  F = (T + Y)^2 - B - X',  Y' = E F,  Z' = 4 B
+//   f' = g (Re l + i Im l)
+// ---------------------------------------------------------------------------------------------
+enum A9Slot { nX, nY, nZ, nF0, nF1, nT0, nT1, nT2, nT3, kA9Slots };
+
+// qx, qy: this thread's Q coordinates in the global array (Montgomery form), vectors n apart
+template <class O>
+__device__ __forceinline__ void a_double_step_9(const uint4* qx, const uint4* qy, size_t n) {
+  O::template mul2<true>(nT0, nF0, nF1, nF0, nF1);   // g0                     (f0 slot is free from here)
+  O::mul(nF1, nF0, nF1);
+  O::dbl(nF1, nF1);                                  // g1
+  O::sqr(nT1, nX);                                   // A
+  O::sqr(nT2, nY);                                   // B
+  O::sqr(nT3, nZ);                                   // C
+  O::sub(nF0, nT1, nT3);                             // T = A - C
+  O::add(nT3, nT1, nT3);                             // A' = A + C
+  O::dbl(nT1, nT3);
+  O::add(nT1, nT1, nF0);                             // U = 3A + C
+  O::mul(nT1, nT1, nZ);
+  O::mulg(nT1, nT1, qx, n);                          // U Z Qx
+  O::mul(nX, nX, nF0);                               // X T
+  O::add(nT1, nT1, nX);                              // Re l                   (X slot is free)
+  O::sqr(nX, nF0);                                   // X' = T^2
+  O::sqr(nT3, nT3);
+  O::dbl(nT3, nT3);
+  O::sub(nT3, nT3, nX);                              // E = 2 A'^2 - X'
+  O::add(nF0, nF0, nY);
+  O::sqr(nF0, nF0);
+  O::sub(nF0, nF0, nT2);
+  O::sub(nF0, nF0, nX);                              // F = (T + Y)^2 - B - X'
+  O::mul(nT3, nT3, nF0);                             // Y' (kept in T3 until Y has had its last use)
+  O::mul(nF0, nY, nZ);
+  O::dbl(nF0, nF0);
+  O::mulg(nF0, nF0, qy, n);                          // Im l = 2 Y Z Qy
+  O::dbl(nZ, nT2, 2);                                // Z' = 4 B
+  O::template mul2<false>(nT2, nT0, nF1, nT1, nF0);  // (g0 + g1)(Re l + Im l)
+  O::mul(nT0, nT0, nT1);                             // g0 Re l
+  O::mul(nF1, nF1, nF0);                             // g1 Im l
+  O::sub(nF0, nT0, nF1);                             // f0'
+  O::sub(nT2, nT2, nT0);
+  O::sub(nF1, nT2, nF1);                             // f1'
+  O::copy(nY, nT3);
+}
+
+// f *= (l0 + i l1) with two temporaries (t0, t1); l0, l1 are preserved
+template <class O>
+__device__ __forceinline__ void a_fmul_2t(int f0, int f1, int l0, int l1, int t0, int t1) {
+  O::template mul2<false>(t0, f0, f1, l0, l1);
+  O::mul(f0, f0, l0);
+  O::mul(f1, f1, l1);
+  O::sub(t1, f0, f1);
+  O::sub(t0, t0, f0);
+  O::sub(f1, t0, f1);
+  O::copy(f0, t1);
+}
+
+// f, dprod, save as for k_a_miller; qm: [2][4][n] uint4 scratch (Montgomery-form Q)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_a_miller9(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4* __restrict__ f,
+            uint4* __restrict__ dprod, uint4* __restrict__ save, uint4* __restrict__ qm, size_t n) {
+  using O = Ops<kNA, true, BLOCK>;
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;                      // no block-wide barrier in this kernel
+  bool okP = a_load_point<O>(nX, nY, nT0, nT1, P + idx * (2 * kWA));
+  bool okQ = a_load_point<O>(nT2, nT3, nT0, nT1, Q + idx * (2 * kWA));
+  bool valid = okP && okQ;
+  O::st_global(qm, 0, n, idx, nT2);
+  O::st_global(qm, 1, n, idx, nT3);
+  const uint4* qx = qm + idx;
+  const uint4* qy = qm + 4 * n + idx;
+
+  O::set_const(nZ, c_fp.one);
+  O::set_const(nF0, c_fp.one);
+  uint32_t zero[kNA] = {0};
+  O::st(nF1, zero);
+
+  const int exp1 = c_a.exp1, exp2 = c_a.exp2;
+  for (int i = 0; i < exp2; i++) {
+    if (i == exp1) {
+      // V1 = +-V, f1 = f or conj(f) ~ 1/f   (ecc/a_param.c:1162-1169)
+      if (c_a.sign1 < 0) { O::neg(nT0, nY); O::neg(nT1, nF1); }
+      else               { O::copy(nT0, nY); O::copy(nT1, nF1); }
+      O::st_global(save, 0, n, idx, nX);
+      O::st_global(save, 1, n, idx, nT0);
+      O::st_global(save, 2, n, idx, nZ);
+      O::st_global(save, 3, n, idx, nF0);
+      O::st_global(save, 4, n, idx, nT1);
+    }
+    a_double_step_9<O>(qx, qy, n);
+  }
+
+  // f *= f1
+  O::ld_global(nT2, save, 3, n, idx);
+  O::ld_global(nT3, save, 4, n, idx);
+  a_fmul_2t<O>(nF0, nF1, nT2, nT3, nT0, nT1);
+  // chord through V = (X, Y, Z) and V1 = (X1, Y1, Z1) in weight-(1,2) coordinates, scaled by
+  // Z^2 Z1^2 (compute_abc_line :114-130):
+  //   a = Y Z1^2 - Y1 Z^2,  b = Z Z1 (X1 Z - X Z1),  c = X Z Y1 - Y X1 Z1
+  O::ld_global(nT0, save, 2, n, idx);          // Z1
+  O::ld_global(nT1, save, 0, n, idx);          // X1
+  O::mul(nT2, nT1, nZ);                         // X1 Z
+  O::mul(nT3, nX, nT0);                         // X Z1
+  O::sub(nT2, nT2, nT3);
+  O::mul(nT2, nT2, nZ);
+  O::mul(nT2, nT2, nT0);                        // b
+  O::mul(nT3, nX, nZ);                          // X Z               (last use of X)
+  O::ld_global(nX, save, 1, n, idx);           // Y1
+  O::mul(nT3, nT3, nX);                         // X Z Y1
+  O::mul(nT1, nT1, nT0);                        // X1 Z1
+  O::mul(nT1, nT1, nY);                         // Y X1 Z1
+  O::sub(nT3, nT3, nT1);                        // c
+  O::sqr(nT0, nT0);                             // Z1^2
+  O::mul(nT0, nT0, nY);                         // Y Z1^2
+  O::sqr(nT1, nZ);                              // Z^2
+  O::mul(nT1, nT1, nX);                         // Y1 Z^2
+  O::sub(nT0, nT0, nT1);                        // a
+  O::mulg(nT0, nT0, qx, n);
+  O::sub(nT3, nT3, nT0);                        // Re l = c - a Qx
+  O::mulg(nT2, nT2, qy, n);                     // Im l = b Qy
+  a_fmul_2t<O>(nF0, nF1, nT3, nT2, nT0, nT1);
+
+  // D = (f0^2 + f1^2) f0 f1;  invalid inputs publish D = 0 (-> identity)
+  O::sqr(nT0, nF0);
+  O::sqr(nT1, nF1);
+  O::add(nT0, nT0, nT1);
+  O::mul(nT1, nF0, nF1);
+  O::mul(nT0, nT0, nT1);
+  if (!valid) O::st(nT0, zero);
+  O::st_global(f, 0, n, idx, nF0);
+  O::st_global(f, 1, n, idx, nF1);
+  O::st_global(dprod, 0, n, idx, nT0);
 }
 
 // ---------------------------------------------------------------------------------------------

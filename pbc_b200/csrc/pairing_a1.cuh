@@ -104,7 +104,7 @@ __device__ __noinline__ bool a1_load_point(int sx, int sy, int st0, int st1, con
   O::add(st0, st0, st1);      // x^2 + 1
   O::mul(st0, st0, sx);       // x^3 + x
   O::sqr(st1, sy);
-  return O::eq(st0, st1);
+  return O::eq(st0, st1) && !O::is_zero(sy);    // (0, 0), the 2-torsion point, decodes as O (see pairing_a.cuh)
 }
 
 // D = N(f) f0 f1 (the one quantity the final exponentiation needs inverted); 0 marks "output 1"

@@ -52,6 +52,9 @@ struct FConsts {
   uint32_t tau[5][2][kNS];             // tau^j,  j = 1..5  (wire -> internal, test hook)
   uint32_t tau_inv[5][2][kNS];         // tau^-j, j = 1..5  (internal -> wire)
   uint32_t qsq[2 * kNS];               // q^2 as a plain double-width integer (lazy reduction offset)
+  uint32_t qsqm[3][2 * kNS];           // q^2, 2 q^2, 3 q^2: starting values of the double-width accumulators
+  uint32_t slots_ok;                   // internal basis in use and 3 q < 2^160: the slot-machine kernels apply
+  uint32_t pad3[3];
 };
 __constant__ FConsts c_f;
 

@@ -67,6 +67,45 @@ struct Ops {
     fp_sqr<N, FULL>(x, x);
     st(d, x);
   }
+  // d = (a + a2) * (b + b2)   (SUBB: (a + a2) * (b - b2)): the cross term of a Karatsuba product or
+  // the real part of a square in F_q[i], without a slot for either sum
+  template <bool SUBB>
+  static __device__ __noinline__ void mul2(int d, int a, int a2, int b, int b2) {
+    uint32_t x[N], y[N];
+    {
+      uint32_t z[N];
+      ld(y, b); ld(z, b2);
+      if (SUBB) fp_sub<N>(y, y, z); else fp_add<N, FULL>(y, y, z);
+      ld(x, a); ld(z, a2);
+      fp_add<N, FULL>(x, x, z);
+    }
+    fp_mul<N, FULL>(x, x, y);
+    st(d, x);
+  }
+  // d = a * g, the second operand read from a limb-major global array (g already points at this
+  // thread's first vector; consecutive vectors are n apart): a value used once or twice per loop
+  // iteration lives in L2 instead of a shared-memory slot.  The global loads are issued first.
+  static __device__ __noinline__ void mulg(int d, int a, const void* g, size_t n) {
+    uint32_t x[N], y[N];
+    if constexpr (kVecWords == 4) {
+      const uint4* b = reinterpret_cast<const uint4*>(g);
+#pragma unroll
+      for (int v = 0; v < kVecs; v++) {
+        uint4 q = b[v * n];
+        y[4 * v] = q.x; y[4 * v + 1] = q.y; y[4 * v + 2] = q.z; y[4 * v + 3] = q.w;
+      }
+    } else {
+      const uint2* b = reinterpret_cast<const uint2*>(g);
+#pragma unroll
+      for (int v = 0; v < kVecs; v++) {
+        uint2 q = b[v * n];
+        y[2 * v] = q.x; y[2 * v + 1] = q.y;
+      }
+    }
+    ld(x, a);
+    fp_mul<N, FULL>(x, x, y);
+    st(d, x);
+  }
   // d = a*b - c
   static __device__ __noinline__ void mulsub(int d, int a, int b, int c) {
     uint32_t x[N], y[N];

@@ -90,9 +90,19 @@ class Pairing:
             raise PairingError(last_error())
 
     # -- element_prod_pairing -----------------------------------------------------------------
+    @staticmethod
+    def _need(buf, nbytes, what):
+        """length check for bytes-like host buffers (addresses and tensors are the caller's business)"""
+        if isinstance(buf, (bytes, bytearray, memoryview)) and len(buf) < nbytes:
+            raise ValueError("%s: buffer of %d bytes, %d needed" % (what, len(buf), nbytes))
+
     def prod_apply(self, in1: bytes, in2: bytes, k: int, n_out=None) -> bytes:
+        if k < 1:
+            raise ValueError("prod_apply: k must be positive")
         if n_out is None:
             n_out = len(in1) // (self.g1_len * k)
+        self._need(in1, n_out * k * self.g1_len, "prod_apply in1")
+        self._need(in2, n_out * k * self.g2_len, "prod_apply in2")
         out = C.create_string_buffer(max(1, n_out * self.gt_len))
         if lib.pbc_b200_prod_pairings_apply(self._h, C.addressof(out), _addr(in1), _addr(in2), k, n_out):
             raise PairingError(last_error())
@@ -110,6 +120,8 @@ class Pairing:
     def pp_apply(self, in1: bytes, in2: bytes, n=None) -> bytes:
         if n is None:
             n = len(in2) // self.g2_len
+        self._need(in1, self.g1_len, "pp_apply in1")
+        self._need(in2, n * self.g2_len, "pp_apply in2")
         out = C.create_string_buffer(max(1, n * self.gt_len))
         if lib.pbc_b200_pp_pairings_apply(self._h, C.addressof(out), _addr(in1), _addr(in2), n):
             raise PairingError(last_error())
@@ -123,10 +135,17 @@ class Pairing:
         if lib.pbc_b200_pp_pairings_apply_device(self._h, d_out, d_in1, d_in2, n, stream):
             raise PairingError(last_error())
 
+    def pp_init(self, in1: bytes) -> "PairingPP":
+        """pairing_pp_init: preprocess one first argument; the table stays on the GPU until clear()"""
+        self._need(in1, self.g1_len, "pp_init in1")
+        return PairingPP(self, in1)
+
     # -- element_pow_zn on G1 / GT (include/pbc_field.h:262-275) ------------------------------------
     def g1_pow_zn(self, points: bytes, scalars: bytes, n=None) -> bytes:
         if n is None:
             n = len(points) // self.g1_len
+        self._need(points, n * self.g1_len, "g1_pow_zn points")
+        self._need(scalars, n * self.zr_len, "g1_pow_zn scalars")
         out = C.create_string_buffer(max(1, n * self.g1_len))
         if lib.pbc_b200_g1_pow_zn(self._h, C.addressof(out), _addr(points), _addr(scalars), n):
             raise PairingError(last_error())
@@ -136,6 +155,7 @@ class Pairing:
         """element_from_hash on G1 for n hashes of `length` bytes each, back to back"""
         if n is None:
             n = len(data) // length
+        self._need(data, n * length, "g1_from_hash data")
         out = C.create_string_buffer(max(1, n * self.g1_len))
         if lib.pbc_b200_g1_from_hash(self._h, C.addressof(out), _addr(data), length, n):
             raise PairingError(last_error())
@@ -157,6 +177,7 @@ class Pairing:
         clen = self.g1_len // 2 + 1
         if n is None:
             n = len(data) // clen
+        self._need(data, n * clen, "g1_decompress data")
         out = C.create_string_buffer(max(1, n * self.g1_len))
         if lib.pbc_b200_g1_from_bytes_compressed(self._h, C.addressof(out), _addr(data), n):
             raise PairingError(last_error())
@@ -165,6 +186,8 @@ class Pairing:
     def g2_pow_zn(self, points: bytes, scalars: bytes, n=None) -> bytes:
         if n is None:
             n = len(points) // self.g2_len
+        self._need(points, n * self.g2_len, "g2_pow_zn points")
+        self._need(scalars, n * self.zr_len, "g2_pow_zn scalars")
         out = C.create_string_buffer(max(1, n * self.g2_len))
         if lib.pbc_b200_g2_pow_zn(self._h, C.addressof(out), _addr(points), _addr(scalars), n):
             raise PairingError(last_error())
@@ -173,6 +196,8 @@ class Pairing:
     def gt_pow_zn(self, elems: bytes, scalars: bytes, n=None) -> bytes:
         if n is None:
             n = len(elems) // self.gt_len
+        self._need(elems, n * self.gt_len, "gt_pow_zn elems")
+        self._need(scalars, n * self.zr_len, "gt_pow_zn scalars")
         out = C.create_string_buffer(max(1, n * self.gt_len))
         if lib.pbc_b200_gt_pow_zn(self._h, C.addressof(out), _addr(elems), _addr(scalars), n):
             raise PairingError(last_error())
@@ -232,6 +257,46 @@ class Pairing:
         if ms < 0:
             raise PairingError(last_error())
         return ms
+
+
+class PairingPP:
+    """pairing_pp_t (include/pbc_pairing.h:54-89): init once, apply many times, clear"""
+
+    def __init__(self, pairing: Pairing, in1: bytes):
+        self.pairing = pairing
+        self._h = C.c_void_p()
+        if lib.pbc_b200_pp_init(pairing.handle, C.byref(self._h), _addr(in1)):
+            self._h = C.c_void_p()
+            raise PairingError(last_error())
+
+    def apply(self, in2: bytes, n=None) -> bytes:
+        pr = self.pairing
+        if n is None:
+            n = len(in2) // pr.g2_len
+        pr._need(in2, n * pr.g2_len, "pp apply in2")
+        out = C.create_string_buffer(max(1, n * pr.gt_len))
+        if lib.pbc_b200_pp_apply(self._h, C.addressof(out), _addr(in2), n):
+            raise PairingError(last_error())
+        return out.raw[:n * pr.gt_len]
+
+    def apply_into(self, out, in2, n: int):
+        if lib.pbc_b200_pp_apply(self._h, _addr(out), _addr(in2), n):
+            raise PairingError(last_error())
+
+    def apply_device(self, d_out, d_in2, n, stream=0):
+        if lib.pbc_b200_pp_apply_device(self._h, d_out, d_in2, n, stream):
+            raise PairingError(last_error())
+
+    def clear(self):
+        if getattr(self, "_h", None):
+            lib.pbc_b200_pp_clear(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.clear()
+        except Exception:
+            pass
 
 
 def pairing_init_set_str(param_text) -> Pairing:

@@ -25,6 +25,7 @@
  * There is no CPU fallback: if the GPU call fails the shim reports through pbc_die (the
  * reference's fatal-error convention, misc/utils.c:70-77).
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -41,13 +42,20 @@ struct attach_s {
   int g1_len, g2_len, gt_len;
 };
 static struct attach_s g_attached[MAX_ATTACHED];
+/* the table is shared by every pairing_t of the process: attach, detach and look-up take this lock
+ * (the reference itself is used from one thread per pairing_t; different pairings may
+ * live on different threads) */
+static pthread_mutex_t g_attach_mu = PTHREAD_MUTEX_INITIALIZER;
 
 static struct attach_s *find_attach(pairing_ptr p) {
   int i;
-  for (i = 0; i < MAX_ATTACHED; i++)
-    if (g_attached[i].pairing == p) return &g_attached[i];
-  pbc_die("pbc_b200: pairing %p is not attached to a GPU handle", (void *)p);
-  return NULL;
+  struct attach_s *a = NULL;
+  pthread_mutex_lock(&g_attach_mu);
+  for (i = 0; i < MAX_ATTACHED && !a; i++)
+    if (g_attached[i].pairing == p) a = &g_attached[i];
+  pthread_mutex_unlock(&g_attach_mu);
+  if (!a) pbc_die("pbc_b200: pairing %p is not attached to a GPU handle", (void *)p);
+  return a;
 }
 
 static void check(int rc, const char *what) {
@@ -81,28 +89,35 @@ static void b200_prod_pairings(element_ptr out, element_t in1[], element_t in2[]
   pbc_free(b1);
 }
 
-/* pairing_pp_init / apply / clear (include/pbc_pairing.h:54-89): p->data keeps the wire bytes of
- * the fixed first argument; the line-coefficient table lives on the GPU for the duration of a call */
+/* pairing_pp_init / apply / clear (include/pbc_pairing.h:54-89): p->data is the engine's
+ * pbc_b200_pp_t -- the preprocessing (types a, a1: the line-coefficient table) is computed once here
+ * and stays in device memory until pairing_pp_clear, as the reference keeps its table in p->data
+ * (ecc/a_param.c:149-220) */
 static void b200_pp_init(pairing_pp_t p, element_ptr in1, pairing_ptr pairing) {
   struct attach_s *a = find_attach(pairing);
-  p->data = pbc_malloc(a->g1_len);
-  element_to_bytes(p->data, in1);
+  unsigned char buf[1024];
+  pbc_b200_pp_t *pp = NULL;
+  element_to_bytes(buf, in1);
+  check(pbc_b200_pp_init(a->h, &pp, buf), "pairing_pp_init");
+  p->data = pp;
 }
 static void b200_pp_apply(element_ptr out, element_ptr in2, pairing_pp_t p) {
   struct attach_s *a = find_attach(p->pairing);
   unsigned char buf[1024];
   unsigned char *b2 = buf, *bo = b2 + a->g2_len;
   element_to_bytes(b2, in2);
-  check(pbc_b200_pp_pairings_apply(a->h, bo, p->data, b2, 1), "pairing_pp_apply");
+  check(pbc_b200_pp_apply((pbc_b200_pp_t *)p->data, bo, b2, 1), "pairing_pp_apply");
   element_from_bytes(out, bo);
 }
-static void b200_pp_clear(pairing_pp_t p) { pbc_free(p->data); }
+static void b200_pp_clear(pairing_pp_t p) { pbc_b200_pp_clear((pbc_b200_pp_t *)p->data); }
 
 static void b200_clear(pairing_ptr pairing) {
   struct attach_s *a = find_attach(pairing);
   void (*orig)(struct pairing_s *) = a->orig_clear;
   pbc_b200_pairing_clear(a->h);
+  pthread_mutex_lock(&g_attach_mu);
   memset(a, 0, sizeof *a);
+  pthread_mutex_unlock(&g_attach_mu);
   orig(pairing);
 }
 
@@ -110,27 +125,34 @@ static void b200_clear(pairing_ptr pairing) {
  * reference's init convention); on failure the pairing is left as the reference set it up. */
 int pbc_b200_attach(pairing_t pairing, const char *param, size_t len) {
   int i;
-  struct attach_s *a = NULL;
-  for (i = 0; i < MAX_ATTACHED && !a; i++)
-    if (!g_attached[i].pairing) a = &g_attached[i];
-  if (!a) { pbc_error("pbc_b200: too many attached pairings"); return 1; }
+  struct attach_s *a = NULL, t;
+  memset(&t, 0, sizeof t);
   if (!len) len = strlen(param);
-  if (pbc_b200_pairing_init_set_buf(&a->h, param, len)) {
+  if (pbc_b200_pairing_init_set_buf(&t.h, param, len)) {
     pbc_error("pbc_b200: %s", pbc_b200_last_error());
     return 1;
   }
-  a->g1_len = pbc_b200_pairing_length_in_bytes_G1(a->h);
-  a->g2_len = pbc_b200_pairing_length_in_bytes_G2(a->h);
-  a->gt_len = pbc_b200_pairing_length_in_bytes_GT(a->h);
-  if (a->g1_len != pairing_length_in_bytes_G1(pairing) || a->g2_len != pairing_length_in_bytes_G2(pairing) ||
-      a->gt_len != pairing_length_in_bytes_GT(pairing) || a->g1_len + a->g2_len + a->gt_len > 1024) {
-    pbc_b200_pairing_clear(a->h);
-    memset(a, 0, sizeof *a);
+  t.g1_len = pbc_b200_pairing_length_in_bytes_G1(t.h);
+  t.g2_len = pbc_b200_pairing_length_in_bytes_G2(t.h);
+  t.gt_len = pbc_b200_pairing_length_in_bytes_GT(t.h);
+  if (t.g1_len != pairing_length_in_bytes_G1(pairing) || t.g2_len != pairing_length_in_bytes_G2(pairing) ||
+      t.gt_len != pairing_length_in_bytes_GT(pairing) || t.g1_len + t.g2_len + t.gt_len > 1024) {
+    pbc_b200_pairing_clear(t.h);
     pbc_error("pbc_b200: element sizes disagree with the reference");
     return 1;
   }
-  a->pairing = pairing;
-  a->orig_clear = pairing->clear_func;
+  t.pairing = pairing;
+  t.orig_clear = pairing->clear_func;
+  pthread_mutex_lock(&g_attach_mu);
+  for (i = 0; i < MAX_ATTACHED && !a; i++)
+    if (!g_attached[i].pairing) a = &g_attached[i];
+  if (a) *a = t;
+  pthread_mutex_unlock(&g_attach_mu);
+  if (!a) {
+    pbc_b200_pairing_clear(t.h);
+    pbc_error("pbc_b200: too many attached pairings");
+    return 1;
+  }
   pairing->map = b200_map;
   pairing->prod_pairings = b200_prod_pairings;
   pairing->pp_init = b200_pp_init;

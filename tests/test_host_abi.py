@@ -49,6 +49,51 @@ def test_init_failure_cases_match_reference(built):
         built.Pairing(PARAMS["a"].replace("exp2 159", "exp2 15x9").replace("r 7307", "r 8307"))
 
 
+def test_parameter_ranges_this_build_cannot_represent_are_rejected(built):
+    """a group order wider than the 160-bit scalar registers, or a modulus whose wire width
+    (ceil(bits / 8), arith/montfp.c:577) is not the one the kernels are compiled for, must fail at
+    init instead of producing a non-reference byte format"""
+    from pbc_b200.params import PARAMS
+    from pbc_b200 import synth
+    A = synth.parse_param(PARAMS["a"])
+    # r' = r * 2^40 (201 bits) with h' = h / 2^40 keeps r h = q + 1 when 2^40 | h; a.param's h is
+    # divisible by 4 only, so craft the text directly: the check on r comes before r h == q + 1
+    big_r = PARAMS["a"].replace("r %d" % A["r"], "r %d" % (A["r"] << 41))
+    with pytest.raises(built.PairingError, match="group order"):
+        built.Pairing(big_r)
+    small_q = PARAMS["a"].replace("q %d" % A["q"], "q %d" % (A["q"] >> 16))
+    with pytest.raises(built.PairingError, match="505..512"):
+        built.Pairing(small_q)
+    with pytest.raises(built.PairingError, match="exp1/exp2"):
+        built.Pairing(PARAMS["a"].replace("exp2 159", "exp2 100000"))
+    for name in ("f", "d159"):
+        T = synth.parse_param(PARAMS[name])
+        with pytest.raises(built.PairingError, match="153..159"):
+            built.Pairing(PARAMS[name].replace("q %d" % T["q"], "q %d" % (T["q"] >> 8)))
+    # scalars travel with the width the kernels stride by
+    for name in ("a", "f", "d159", "g149"):
+        p = built.Pairing(PARAMS[name])
+        r = synth.parse_param(PARAMS[name])["r"]
+        assert p.zr_len == (r.bit_length() + 7) // 8
+
+
+def test_python_mirror_checks_buffer_lengths(built):
+    from pbc_b200.params import PARAMS
+    p = built.Pairing(PARAMS["a"])
+    with pytest.raises(ValueError):
+        p.prod_apply(b"\0" * 128, b"\0" * 128, 0, 1)
+    with pytest.raises(ValueError):
+        p.prod_apply(b"\0" * 128, b"\0" * 256, 2, 1)
+    with pytest.raises(ValueError):
+        p.pp_apply(b"\0" * 127, b"\0" * 128, 1)
+    with pytest.raises(ValueError):
+        p.g1_pow_zn(b"\0" * 256, b"\0" * 20, 2)
+    with pytest.raises(ValueError):
+        p.gt_pow_zn(b"\0" * 128, b"\0" * 19, 1)
+    with pytest.raises(ValueError):
+        p.g1_from_hash(b"abc", 2, 2)
+
+
 def test_param_text_tolerates_comments_and_whitespace(built):
     from pbc_b200.params import PARAMS
     text = "# leading comment\n\n" + PARAMS["a"].replace("\n", "   # trailing\n\t")
