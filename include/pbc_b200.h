@@ -136,6 +136,23 @@ int pbc_b200_g1_pow_zn_device(pbc_b200_pairing_t *p, void *d_out, const void *d_
 int pbc_b200_gt_pow_zn_device(pbc_b200_pairing_t *p, void *d_out, const void *d_in, const void *d_k,
                               size_t n, void *stream);
 
+/* The GT operations next to the pairing, batched, host buffers:
+ *   gt_mul:  out[i] = a[i] * b[i]      element_mul on GT (ecc/pairing.c:199-201 -> the F_q^k product:
+ *            fi_mul arith/fieldquadratic.c:425-457 for types a / a1, polymod_mul arith/poly.c:932-1143 over
+ *            fq_mul for f, the quadratic extensions of d / g)
+ *   gt_cmp:  flags[i] = 1 if a[i] != b[i], else 0      element_cmp (include/pbc_field.h:334-339)
+ *   is_almost_coddh (include/pbc_pairing.h:240-243 -> generic_is_almost_coddh ecc/pairing.c:15-33 for
+ *            types a, a1, f; cc_is_almost_coddh ecc/d_param.c:739-784, ecc/g_param.c:560):
+ *            flags[i] = 1 if e(a[i], d[i]) == e(b[i], c[i]) or e(a[i], d[i]) * e(b[i], c[i]) == 1, else 0;
+ *            a, b in G1 and c, d in G2 (wire format).  Two batched pairings, one GT product, one compare. */
+int pbc_b200_gt_mul(pbc_b200_pairing_t *p, unsigned char *out, const unsigned char *a,
+                    const unsigned char *b, size_t n);
+int pbc_b200_gt_cmp(pbc_b200_pairing_t *p, unsigned char *flags, const unsigned char *a,
+                    const unsigned char *b, size_t n);
+int pbc_b200_is_almost_coddh(pbc_b200_pairing_t *p, unsigned char *flags, const unsigned char *a,
+                             const unsigned char *b, const unsigned char *c, const unsigned char *d,
+                             size_t n);
+
 /* Batched element_from_hash on G1 (include/pbc_field.h:202-212 -> curve_from_hash,
  * ecc/curve.c:455-482 with pbc_mpz_from_hash, arith/field.c:643-668): out[i] = the G1 element the
  * reference derives from the `len` bytes at data + i*len -- x from the hash, x <- x^2 + 1 until

@@ -46,6 +46,9 @@ lib.pbc_b200_pairing_length_in_bytes_Zr.argtypes = [_P]
 for _n in ("g1_pow_zn", "g2_pow_zn", "gt_pow_zn"):
     getattr(lib, "pbc_b200_" + _n).argtypes = [_P, _P, _P, _P, C.c_size_t]
     getattr(lib, "pbc_b200_" + _n + "_device").argtypes = [_P, _P, _P, _P, C.c_size_t, _P]
+lib.pbc_b200_gt_mul.argtypes = [_P, _P, _P, _P, C.c_size_t]
+lib.pbc_b200_gt_cmp.argtypes = [_P, _P, _P, _P, C.c_size_t]
+lib.pbc_b200_is_almost_coddh.argtypes = [_P, _P, _P, _P, _P, _P, C.c_size_t]
 lib.pbc_b200_g1_from_hash.argtypes = [_P, _P, _P, C.c_size_t, C.c_size_t]
 lib.pbc_b200_g1_from_hash_device.argtypes = [_P, _P, _P, C.c_size_t, C.c_size_t, _P]
 lib.pbc_b200_pairing_length_in_bytes_compressed_G1.argtypes = [_P]

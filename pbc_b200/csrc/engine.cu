@@ -175,6 +175,8 @@ struct Job {
   const uint8_t* pp_in1 = nullptr;
 };
 
+static size_t cc_table_bytes(const pbc_b200_pairing_s* p);
+
 // workspace bytes for n_out outputs of `job`
 static size_t ws_bytes(const pbc_b200_pairing_s* p, const Job& job, size_t n_out) {
   if (p->type == '1') {
@@ -197,9 +199,27 @@ static size_t ws_bytes(const pbc_b200_pairing_s* p, const Job& job, size_t n_out
   size_t bytes = n_in * (W + 1) * 4;
   if (p->type == 'f') bytes += n_in * (size_t)kFGWords * 4;   // Q, P of the slot-machine Miller kernel
   if (p->type == 'f') bytes += n_out * (size_t)kFStashWords * 4;   // parked F_q^12 values of the slot-machine final exponentiation
+  if (job.mode == kPP) bytes += cc_table_bytes(p);             // line table of the fixed first argument
   if (job.mode == kProd) bytes += n_out * (W + 1) * 4;
   return bytes;
 }
+// lines of the Miller walk of types f, d, g: one tangent per loop position, one chord per non-zero digit
+// strictly between the top digit and digit 0 (miller_cc_walk)
+static size_t cc_table_rows(const pbc_b200_pairing_s* p) {
+  BigUInt r;
+  for (int i = kNS; i-- > 0;) r = r.shl(32) + BigUInt((uint64_t)p->cc.r[i]);
+#if PBC_CC_NAF
+  std::vector<int8_t> dg = naf_digits(r);
+  size_t rows = dg.size() - 1;
+  for (size_t m = 1; m + 1 < dg.size(); m++) rows += dg[m] ? 1 : 0;
+#else
+  size_t rows = r.bits() - 1;
+  for (size_t m = 1; m + 1 < r.bits(); m++) rows += r.bit(m) ? 1 : 0;
+#endif
+  return rows;
+}
+static size_t cc_table_bytes(const pbc_b200_pairing_s* p) { return (cc_table_rows(p) * 3 * kNS + 4) * 4; }
+
 static size_t in1_elems(const Job& job, size_t n_out) {
   return job.mode == kProd ? n_out * job.k : (job.mode == kPP ? 1 : n_out);
 }
@@ -714,9 +734,15 @@ static int init_type_g(pbc_b200_pairing_s* p, const std::map<std::string, std::s
 // ------------------------------------------------------------------------------------------
 // device contexts
 // ------------------------------------------------------------------------------------------
+// opt in to `bytes` of dynamic shared memory per block AND ask for the largest shared-memory carve-out:
+// the slot kernels are sized so that 2 or 3 blocks fill the 228 KB of an SM; with the default
+// preference the driver may configure a smaller carve-out that holds fewer blocks than the kernel was
+// designed for (round 2: the nine-slot type A kernel ran two blocks per SM instead of three)
 template <class K>
 static cudaError_t allow_smem(K kernel, size_t bytes) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 }
 
 static constexpr size_t kSmemAMiller = (size_t)kASlots * 64 * kBlockMiller;
@@ -775,6 +801,7 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
       CUDA_OK(allow_smem(k_a_g1_mul<kBlockMiller>, (size_t)kGSlots * 64 * kBlockMiller));
       CUDA_OK(allow_smem(k_a_g1_finish<kBlockFinal>, (size_t)4 * 64 * kBlockFinal));
       CUDA_OK(allow_smem(k_a_gt_pow<kBlockMiller>, (size_t)7 * 64 * kBlockMiller));
+      CUDA_OK(allow_smem(k_a_gt_mul<kBlockMiller>, (size_t)7 * 64 * kBlockMiller));
       CUDA_OK(allow_smem(k_a_g1_from_hash<kBlockMiller>, (size_t)kGSlots * 64 * kBlockMiller));
       CUDA_OK(allow_smem(k_a_g1_decompress<kBlockMiller>, (size_t)5 * 64 * kBlockMiller));
     }
@@ -792,6 +819,7 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
       CUDA_OK(allow_smem(k_a1_g1_from_hash<kBlockA1G>, kSmemA1G));
       CUDA_OK(allow_smem(k_a1_g1_finish<kBlockA1G>, (size_t)4 * kSlotA1 * kBlockA1G));
       CUDA_OK(allow_smem(k_a1_gt_pow<kBlockA1G>, (size_t)7 * kSlotA1 * kBlockA1G));
+      CUDA_OK(allow_smem(k_a1_gt_mul<kBlockA1G>, (size_t)7 * kSlotA1 * kBlockA1G));
       CUDA_OK(allow_smem(k_a1_g1_decompress<kBlockA1G>, (size_t)5 * kSlotA1 * kBlockA1G));
     }
     c.ready = true;
@@ -983,12 +1011,26 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
     if (job.mode == kPP && job.pp_in1) d_in1 = job.pp_in1;
     unsigned gm = (unsigned)((m + kBlockCCMiller - 1) / kBlockCCMiller);
     STAGE(0);
+    // fixed first argument: the line table, from the pp handle or built here at the end of the workspace
+    const uint32_t* tab = nullptr;
+    size_t rows = 0;
+    if (job.mode == kPP) {
+      rows = cc_table_rows(p);
+      if (job.pp_tab) tab = (const uint32_t*)job.pp_tab;
+      else {
+        uint32_t* t = (uint32_t*)((uint8_t*)ws + ws_bytes(p, job, n) - cc_table_bytes(p));
+        if (isg) k_cc_pp_init<kWG><<<1, 32, 0, st>>>(d_in1, t, rows);
+        else k_cc_pp_init<kWS><<<1, 32, 0, st>>>(d_in1, t, rows);
+        LAUNCHED();
+        tab = t;
+      }
+    }
     if (isf && PBC_F_SLOTS && p->f.slots_ok) {
       uint32_t* gq = mv + (W + 1) * m + (job.mode == kProd ? (W + 1) * n : 0);   // after the Miller values and flags
-      k_f_miller_s<kBlockFS><<<(unsigned)((m + kBlockFS - 1) / kBlockFS), kBlockFS, kSmemFMillerS, st>>>(d_in1, d_in2, mv, flag, gq, m, stride1);
-    } else if (isf) k_f_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1);
-    else if (isg) k_g_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1);
-    else k_d_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1);
+      k_f_miller_s<kBlockFS><<<(unsigned)((m + kBlockFS - 1) / kBlockFS), kBlockFS, kSmemFMillerS, st>>>(d_in1, d_in2, mv, flag, gq, m, stride1, tab, rows);
+    } else if (isf) k_f_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1, tab, rows);
+    else if (isg) k_g_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1, tab, rows);
+    else k_d_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1, tab, rows);
     LAUNCHED();
     STAGE(1);
     if (job.mode == kProd) {
@@ -1251,11 +1293,18 @@ int pbc_b200_pp_init(pbc_b200_pairing_t* p, pbc_b200_pp_t** out, const unsigned 
   size_t tab_bytes = 0;
   if (p->type == 'a') tab_bytes = (size_t)(3 * (p->a.exp2 + 1) * kNA + 4) * 4;
   if (p->type == '1') tab_bytes = (p->a1_rows * kNA1 + 4) * 4;
+  const bool cc = p->type == 'f' || p->type == 'd' || p->type == 'g';
+  if (cc) tab_bytes = cc_table_bytes(p);
   cudaError_t e = cudaMalloc(&pp->d_in1, (size_t)p->g1_len);
   if (e == cudaSuccess && tab_bytes) e = cudaMalloc(&pp->d_tab, tab_bytes);
   if (e == cudaSuccess) e = cudaMemcpyAsync(pp->d_in1, in1, (size_t)p->g1_len, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess && p->type == 'a') { k_a_pp_init<32><<<1, 32, kSmemAPPInit, st>>>(pp->d_in1, (uint32_t*)pp->d_tab); LAUNCHED(); }
   if (e == cudaSuccess && p->type == '1') { k_a1_pp_init<32><<<1, 32, kSmemA1PPInit, st>>>(pp->d_in1, (uint32_t*)pp->d_tab, p->a1_rows); LAUNCHED(); }
+  if (e == cudaSuccess && cc) {
+    if (p->type == 'g') k_cc_pp_init<kWG><<<1, 32, 0, st>>>(pp->d_in1, (uint32_t*)pp->d_tab, cc_table_rows(p));
+    else k_cc_pp_init<kWS><<<1, 32, 0, st>>>(pp->d_in1, (uint32_t*)pp->d_tab, cc_table_rows(p));
+    LAUNCHED();
+  }
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -1669,6 +1718,112 @@ extern "C" int pbc_b200_g1_from_bytes_compressed(pbc_b200_pairing_t* p, unsigned
 }
 
 // ------------------------------------------------------------------------------------------
+// GT operations next to the pairing: batched element_mul, element_cmp and
+// is_almost_coddh.  Host buffers; device staging is allocated per call.
+// ------------------------------------------------------------------------------------------
+namespace pbcb200 {
+__global__ void k_bytes_cmp(uint8_t* flags, const uint8_t* a, const uint8_t* b, size_t len, size_t n);
+__global__ void k_coddh_flags(uint8_t* flags, const uint8_t* t0, const uint8_t* t1, const uint8_t* t2, size_t len, size_t wb, size_t n);
+}
+static int enqueue_gt_mul(pbc_b200_pairing_s* p, uint8_t* d_out, const uint8_t* d_a, const uint8_t* d_b, size_t n,
+                          cudaStream_t st) {
+  if (p->type == 'a') {
+    unsigned g = (unsigned)((n + kBlockMiller - 1) / kBlockMiller);
+    k_a_gt_mul<kBlockMiller><<<g, kBlockMiller, (size_t)7 * 64 * kBlockMiller, st>>>(d_a, d_b, d_out, n);
+  } else if (p->type == '1') {
+    unsigned g = (unsigned)((n + kBlockA1G - 1) / kBlockA1G);
+    k_a1_gt_mul<kBlockA1G><<<g, kBlockA1G, (size_t)7 * kSlotA1 * kBlockA1G, st>>>(d_a, d_b, d_out, n);
+  } else {
+    unsigned g = (unsigned)((n + 63) / 64);
+    if (p->type == 'f') k_f_tower_op<<<g, 64, 0, st>>>(0, d_out, d_a, d_b, n);
+    else if (p->type == 'g') k_g_tower_op<<<g, 64, 0, st>>>(0, d_out, d_a, d_b, n);
+    else k_d_tower_op<<<g, 64, 0, st>>>(0, d_out, d_a, d_b, n);
+  }
+  LAUNCHED();
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pbc_b200_gt_mul(pbc_b200_pairing_t* p, unsigned char* out, const unsigned char* a,
+                               const unsigned char* b, size_t n) {
+  if (!p || (n && (!out || !a || !b))) return fail("null argument");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(p->mu);
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> dev_lock(g_dev_mu[dev & 63]);
+  if (ctx_prepare(p, dev)) return 1;
+  cudaStream_t st = p->ctx[dev].stream[0];
+  size_t len = (size_t)p->gt_len;
+  DevBuf da, db, dout;
+  CUDA_OK(da.alloc(n * len)); CUDA_OK(db.alloc(n * len)); CUDA_OK(dout.alloc(n * len));
+  CUDA_OK(cudaMemcpyAsync(da.p, a, n * len, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(db.p, b, n * len, cudaMemcpyHostToDevice, st));
+  if (enqueue_gt_mul(p, dout.as<uint8_t>(), da.as<uint8_t>(), db.as<uint8_t>(), n, st)) return 1;
+  CUDA_OK(cudaMemcpyAsync(out, dout.p, n * len, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int pbc_b200_gt_cmp(pbc_b200_pairing_t* p, unsigned char* flags, const unsigned char* a,
+                               const unsigned char* b, size_t n) {
+  if (!p || (n && (!flags || !a || !b))) return fail("null argument");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(p->mu);
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> dev_lock(g_dev_mu[dev & 63]);
+  if (ctx_prepare(p, dev)) return 1;
+  cudaStream_t st = p->ctx[dev].stream[0];
+  size_t len = (size_t)p->gt_len;
+  DevBuf da, db, df;
+  CUDA_OK(da.alloc(n * len)); CUDA_OK(db.alloc(n * len)); CUDA_OK(df.alloc(n));
+  CUDA_OK(cudaMemcpyAsync(da.p, a, n * len, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(db.p, b, n * len, cudaMemcpyHostToDevice, st));
+  k_bytes_cmp<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(df.as<uint8_t>(), da.as<uint8_t>(), db.as<uint8_t>(), len, n);
+  LAUNCHED();
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(flags, df.p, n, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int pbc_b200_is_almost_coddh(pbc_b200_pairing_t* p, unsigned char* flags, const unsigned char* a,
+                                        const unsigned char* b, const unsigned char* c, const unsigned char* d,
+                                        size_t n) {
+  if (!p || (n && (!flags || !a || !b || !c || !d))) return fail("null argument");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(p->mu);
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> dev_lock(g_dev_mu[dev & 63]);
+  if (ctx_prepare(p, dev)) return 1;
+  cudaStream_t st = p->ctx[dev].stream[0];
+  const size_t l1 = (size_t)p->g1_len, l2 = (size_t)p->g2_len, lt = (size_t)p->gt_len;
+  Job job;
+  DevBuf da, db, dc, dd, t0, t1, t2, df, ws;
+  CUDA_OK(da.alloc(n * l1)); CUDA_OK(db.alloc(n * l1)); CUDA_OK(dc.alloc(n * l2)); CUDA_OK(dd.alloc(n * l2));
+  CUDA_OK(t0.alloc(n * lt)); CUDA_OK(t1.alloc(n * lt)); CUDA_OK(t2.alloc(n * lt)); CUDA_OK(df.alloc(n));
+  CUDA_OK(ws.alloc(ws_bytes(p, job, n)));
+  CUDA_OK(cudaMemcpyAsync(da.p, a, n * l1, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(db.p, b, n * l1, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(dc.p, c, n * l2, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(dd.p, d, n * l2, cudaMemcpyHostToDevice, st));
+  // t0 = e(a, d), t1 = e(b, c)
+  if (enqueue_pairings(p, job, t0.as<uint8_t>(), da.as<uint8_t>(), dd.as<uint8_t>(), n, ws.p, st)) return 1;
+  if (enqueue_pairings(p, job, t1.as<uint8_t>(), db.as<uint8_t>(), dc.as<uint8_t>(), n, ws.p, st)) return 1;
+  if (enqueue_gt_mul(p, t2.as<uint8_t>(), t0.as<uint8_t>(), t1.as<uint8_t>(), n, st)) return 1;
+  size_t wb = p->type == '1' ? (size_t)p->gt_len / 2 : (p->type == 'a' ? (size_t)kWA : (p->type == 'g' ? (size_t)kWG : (size_t)kWS));
+  k_coddh_flags<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(df.as<uint8_t>(), t0.as<uint8_t>(), t1.as<uint8_t>(),
+                                                            t2.as<uint8_t>(), lt, wb, n);
+  LAUNCHED();
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(flags, df.p, n, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // F_p differential-test hook
 // ------------------------------------------------------------------------------------------
 namespace pbcb200 {
@@ -1719,6 +1874,29 @@ __global__ void k_fq_op(int op, uint8_t* __restrict__ out, const uint8_t* __rest
     case 7: fq_mul(x, x, y); fq_sub(x, x, y); break;
   }
   fq_to_wire_w<W>(out + idx * W, x);
+}
+
+// element_cmp on wire bytes (canonical residues: equal elements <=> equal bytes): flags[i] = 1 if a[i] != b[i]
+__global__ void k_bytes_cmp(uint8_t* __restrict__ flags, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                            size_t len, size_t n) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  uint32_t diff = 0;
+  for (size_t k = 0; k < len; k++) diff |= (uint32_t)(a[idx * len + k] ^ b[idx * len + k]);
+  flags[idx] = diff ? 1 : 0;
+}
+// is_almost_coddh (ecc/pairing.c:15-33, ecc/d_param.c:739-784): 1 if t0 == t1 or t0 t1 == 1; t2 = t0 t1.
+// The GT identity on the wire: the first coordinate is 1 (wb bytes, big-endian), every other one 0.
+__global__ void k_coddh_flags(uint8_t* __restrict__ flags, const uint8_t* __restrict__ t0, const uint8_t* __restrict__ t1,
+                              const uint8_t* __restrict__ t2, size_t len, size_t wb, size_t n) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  uint32_t diff = 0, notone = 0;
+  for (size_t k = 0; k < len; k++) {
+    diff |= (uint32_t)(t0[idx * len + k] ^ t1[idx * len + k]);
+    notone |= (uint32_t)(t2[idx * len + k] ^ (k == wb - 1 ? 1u : 0u));
+  }
+  flags[idx] = (!diff || !notone) ? 1 : 0;
 }
 
 // dependent chain of five-limb Montgomery multiplications (mode 0) / squarings (mode 1)

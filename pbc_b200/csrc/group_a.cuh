@@ -353,4 +353,30 @@ k_a_gt_pow(const uint8_t* __restrict__ G, const uint8_t* __restrict__ K, uint8_t
   }
 }
 
+// out[i] = a[i] * b[i] in F_q^2: element_mul on GT (ecc/pairing.c:199-201 -> fi_mul, arith/fieldquadratic.c:425-457)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_a_gt_mul(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B, uint8_t* __restrict__ out, size_t n) {
+  using O = Ops<kNA, true, BLOCK>;
+  enum { sA0, sA1, sB0, sB1, sT0, sT1, sT2 };
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  uint32_t x[kNA], one[kNA] = {1};
+#pragma unroll 1
+  for (int c = 0; c < 4; c++) {
+    const uint8_t* src = (c < 2 ? A : B) + idx * (2 * kWA) + (c & 1) * kWA;
+    limbs_from_be<kNA, kWA>(x, src);
+    mont_mul<kNA, true>(x, x, c_fp.r2);
+    O::st(sA0 + c, x);
+  }
+  a_fmul<O>(sA0, sA1, sB0, sB1, sT0, sT1, sT2);
+  uint8_t* o = out + idx * (2 * kWA);
+#pragma unroll 1
+  for (int c = 0; c < 2; c++) {
+    O::ld(x, sA0 + c);
+    mont_mul<kNA, true>(x, x, one);
+    limbs_to_be<kNA, kWA>(o + c * kWA, x);
+  }
+}
+
 }  // namespace pbcb200

@@ -276,4 +276,33 @@ k_a1_g1_decompress(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, si
   a1_limbs_to_be(out + idx * 2 * (size_t)wb + wb, y, wb);
 }
 
+// out[i] = a[i] * b[i] in F_p^2: element_mul on GT of type a1
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_a1_gt_mul(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B, uint8_t* __restrict__ out, size_t n) {
+  using O = Ops<kNA1, false, BLOCK>;
+  enum { sA0, sA1, sB0, sB1, sT0, sT1, sT2 };
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  const int wb = (int)c_a1.wb;
+  uint32_t x[kNA1], one[kNA1] = {1};
+  O::set_const(sT0, c_fp.r2);
+#pragma unroll 1
+  for (int c = 0; c < 4; c++) {
+    a1_limbs_from_be(x, (c < 2 ? A : B) + idx * 2 * (size_t)wb + (size_t)(c & 1) * wb, wb);
+    O::st(sA0 + c, x);
+    O::mul(sA0 + c, sT0, sA0 + c);          // into Montgomery form (R^2 as the full operand, see a1_load_point)
+  }
+  a_fmul<O>(sA0, sA1, sB0, sB1, sT0, sT1, sT2);
+  O::st(sT0, one);
+  O::mul(sA0, sA0, sT0);
+  O::mul(sA1, sA1, sT0);
+  uint8_t* o = out + idx * 2 * (size_t)wb;
+#pragma unroll 1
+  for (int c = 0; c < 2; c++) {
+    O::ld(x, sA0 + c);
+    a1_limbs_to_be(o + c * wb, x, wb);
+  }
+}
+
 }  // namespace pbcb200

@@ -87,9 +87,11 @@ __device__ __forceinline__ void mc_sub(Fq& r, const Fq& a, const Fq& b) {
   if (PBC_CC_BODY_CALLS) r = fq_sub_call(a, b); else fq_sub(r, a, b);
 }
 
-template <class T>
-__device__ __forceinline__ void miller_cc(typename T::Acc* v, const Fq& xP, const Fq& yP,
-                                          const typename T::Ctx* ctx) {
+// The walk over the digits of r, generic in what happens to each line: `sink.line(a, b, c)` receives
+// the coefficients of every tangent and chord in loop order, `sink.sqr()` marks the squaring between
+// iterations.  Two sinks: the Miller accumulator (below) and the fixed-argument table (pairing_pp_init).
+template <class Sink>
+__device__ __forceinline__ void miller_cc_walk(Sink& sink, const Fq& xP, const Fq& yP) {
   Fq X = xP, Y = yP, Z, a, b, c, M, Y2, Z2, t, u;
   fq_one(Z);
 #if PBC_CC_NAF
@@ -100,7 +102,7 @@ __device__ __forceinline__ void miller_cc(typename T::Acc* v, const Fq& xP, cons
   int m = (int)c_cc.rbits - 2;
 #endif
   for (;;) {
-    if (PBC_CC_LOCKSTEP) __syncthreads();
+    if (PBC_CC_LOCKSTEP && Sink::kBarriers) __syncthreads();
     // ---- tangent at V ----
     fq_sqr(Z2, Z);
     fq_sqr(t, X);
@@ -121,7 +123,7 @@ __device__ __forceinline__ void miller_cc(typename T::Acc* v, const Fq& xP, cons
     fq_mul(c, M, X);
     mc_sub(c, c, Y2);
     mc_sub(c, c, Y2);                      // c = M X - 2 Y^2
-    T::mul_line(v, &a, &b, &c, ctx);
+    sink.line(a, b, c);
     if (m == 0) break;
     // ---- V = 2 V ----
     fq_mul(t, X, Y2);
@@ -160,8 +162,8 @@ __device__ __forceinline__ void miller_cc(typename T::Acc* v, const Fq& xP, cons
       fq_mul(t, t, X);
       fq_mul(u, xP, Y);
       mc_sub(c, t, u);                     // c = yP Z X - xP Y
-      if (PBC_CC_LOCKSTEP >= 2) __syncthreads();
-      T::mul_line(v, &a, &b, &c, ctx);
+      if (PBC_CC_LOCKSTEP >= 2 && Sink::kBarriers) __syncthreads();
+      sink.line(a, b, c);
       fq_sqr(t, H);                        // H^2
       fq_mul(u, t, H);                     // H^3
       fq_mul(t, t, X);                     // X H^2
@@ -176,7 +178,90 @@ __device__ __forceinline__ void miller_cc(typename T::Acc* v, const Fq& xP, cons
       Z = b;
     }
     m--;
-    if (PBC_CC_LOCKSTEP >= 2) __syncthreads();
+    if (PBC_CC_LOCKSTEP >= 2 && Sink::kBarriers) __syncthreads();
+    sink.sqr();
+  }
+}
+
+template <class T>
+struct MillerSink {
+  static constexpr bool kBarriers = true;
+  typename T::Acc* v;
+  const typename T::Ctx* ctx;
+  __device__ __forceinline__ void line(Fq& a, Fq& b, Fq& c) { T::mul_line(v, &a, &b, &c, ctx); }
+  __device__ __forceinline__ void sqr() { T::sqr(v); }
+};
+template <class T>
+__device__ __forceinline__ void miller_cc(typename T::Acc* v, const Fq& xP, const Fq& yP,
+                                          const typename T::Ctx* ctx) {
+  MillerSink<T> sink{v, ctx};
+  miller_cc_walk(sink, xP, yP);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fixed first argument (pairing_pp_init / pairing_pp_apply; d_pairing_pp_init ecc/d_param.c:794-966
+// stores the coefficients of every tangent and chord of the walk over P; the reference's generic
+// fall-back, ecc/pairing.c:48-72, stores only P).  Here for every type on this loop (f, d, g):
+//   tab[(3 row + {0, 1, 2}) * kNS ..] = a, b, c of line `row` in loop order (Montgomery form, each
+//   line scaled by some element of F_q^*, as in the plain loop);  tab[3 rows kNS] = 1 if P decoded
+//   to a finite point of the curve.
+// The apply loop does no point arithmetic at all.
+// ---------------------------------------------------------------------------------------------
+struct TableSink {
+  static constexpr bool kBarriers = false;
+  uint32_t* tab;
+  size_t row;
+  __device__ __forceinline__ void line(Fq& a, Fq& b, Fq& c) {
+#pragma unroll
+    for (int k = 0; k < kNS; k++) {
+      tab[(3 * row + 0) * kNS + k] = a.v[k];
+      tab[(3 * row + 1) * kNS + k] = b.v[k];
+      tab[(3 * row + 2) * kNS + k] = c.v[k];
+    }
+    row++;
+  }
+  __device__ __forceinline__ void sqr() {}
+};
+
+template <int WB>
+__global__ void k_cc_pp_init(const uint8_t* __restrict__ P, uint32_t* __restrict__ tab, size_t rows) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Fq xP, yP;
+  fq_from_wire_w<WB>(xP, P);
+  fq_from_wire_w<WB>(yP, P + WB);
+  bool ok = cc_on_curve(xP, yP);
+  TableSink sink{tab, 0};
+  miller_cc_walk(sink, xP, yP);
+  tab[3 * rows * kNS] = (ok && sink.row == rows) ? 1u : 0u;
+}
+
+// v <- Miller value from the table (the same sequence of line products and squarings as miller_cc)
+template <class T>
+__device__ __forceinline__ void miller_cc_tab(typename T::Acc* v, const uint32_t* __restrict__ tab,
+                                              const typename T::Ctx* ctx) {
+  Fq a, b, c;
+  size_t row = 0;
+#if PBC_CC_NAF
+  int m = (int)c_ccnaf.len - 2;
+#else
+  int m = (int)c_cc.rbits - 2;
+#endif
+  for (;;) {
+    if (PBC_CC_LOCKSTEP) __syncthreads();
+    fq_set(a, tab + (3 * row + 0) * kNS); fq_set(b, tab + (3 * row + 1) * kNS); fq_set(c, tab + (3 * row + 2) * kNS);
+    row++;
+    T::mul_line(v, &a, &b, &c, ctx);
+    if (m == 0) break;
+#if PBC_CC_NAF
+    if ((c_ccnaf.nz[m >> 5] >> (m & 31)) & 1u) {
+#else
+    if ((c_cc.r[m >> 5] >> (m & 31)) & 1u) {
+#endif
+      fq_set(a, tab + (3 * row + 0) * kNS); fq_set(b, tab + (3 * row + 1) * kNS); fq_set(c, tab + (3 * row + 2) * kNS);
+      row++;
+      T::mul_line(v, &a, &b, &c, ctx);
+    }
+    m--;
     T::sqr(v);
   }
 }

@@ -298,18 +298,24 @@ __device__ __forceinline__ void f6d_ld_global(F6D& v, const uint32_t* g, size_t 
 }
 
 // P: 40 bytes each (stride1 = 0 shares one P), Q: n x 120 bytes (x: 3 coefficients, y: 3).
+// tab != nullptr: the line coefficients of the (one) first argument come from the table (k_cc_pp_init).
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (PBC_CC_MINBLOCKS * 128) / BLOCK)
 k_d_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_t* __restrict__ mv,
-           uint32_t* __restrict__ flag, size_t n, size_t stride1) {
+           uint32_t* __restrict__ flag, size_t n, size_t stride1, const uint32_t* __restrict__ tab, size_t rows) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   const bool live = idx < n;      // every thread runs the loop (block-wide barrier inside)
   if (!live) idx = 0;
   Fq xP, yP;
-  const uint8_t* p = P + idx * stride1;
-  fq_from_wire(xP, p);
-  fq_from_wire(yP, p + kWS);
-  bool ok = cc_on_curve(xP, yP);
+  bool ok;
+  if (tab) {
+    ok = tab[3 * rows * kNS] != 0;
+  } else {
+    const uint8_t* p = P + idx * stride1;
+    fq_from_wire(xP, p);
+    fq_from_wire(yP, p + kWS);
+    ok = cc_on_curve(xP, yP);
+  }
   DTower::Ctx ctx;
   F3 t, u;
   F6D v;
@@ -338,7 +344,8 @@ k_d_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_
   fq_set(k, c_d.nqrinv2);
   f3_scale(ctx.Qy, ctx.Qy, k);
   f6d_one(v);
-  miller_cc<DTower>(&v, xP, yP, &ctx);   // off-curve inputs run too (total arithmetic) and are flagged
+  if (tab) miller_cc_tab<DTower>(&v, tab, &ctx);
+  else miller_cc<DTower>(&v, xP, yP, &ctx);   // off-curve inputs run too (total arithmetic) and are flagged
   if (!live) return;
   if (!ok) f6d_one(v);
   f6d_st_global(mv, n, idx, v);

@@ -454,15 +454,20 @@ __device__ __noinline__ void f12_to_internal(F12& v) {
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (PBC_CC_MINBLOCKS * 128) / BLOCK)
 k_f_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_t* __restrict__ mv,
-           uint32_t* __restrict__ flag, size_t n, size_t stride1) {
+           uint32_t* __restrict__ flag, size_t n, size_t stride1, const uint32_t* __restrict__ tab, size_t rows) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   const bool live = idx < n;      // every thread runs the loop (block-wide barrier inside)
   if (!live) idx = 0;
   Fq xP, yP, yP2;
-  const uint8_t* p = P + idx * stride1;
-  fq_from_wire(xP, p);
-  fq_from_wire(yP, p + kWS);
-  bool ok = cc_on_curve(xP, yP);
+  bool ok;
+  if (tab) {
+    ok = tab[3 * rows * kNS] != 0;             // fixed first argument: lines from the table (k_cc_pp_init)
+  } else {
+    const uint8_t* p = P + idx * stride1;
+    fq_from_wire(xP, p);
+    fq_from_wire(yP, p + kWS);
+    ok = cc_on_curve(xP, yP);
+  }
   FTower::Ctx ctx;
   F2 t, u;
   F12 v;
@@ -486,7 +491,8 @@ k_f_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_
   f2_mul(&ctx.Qx, &ctx.Qx, f2_const(c_f.kx));
   f2_mul(&ctx.Qy, &ctx.Qy, f2_const(c_f.ky));
   f12_one(v);
-  miller_cc<FTower>(&v, xP, yP, &ctx);   // off-curve inputs run too (total arithmetic) and are flagged
+  if (tab) miller_cc_tab<FTower>(&v, tab, &ctx);
+  else miller_cc<FTower>(&v, xP, yP, &ctx);   // off-curve inputs run too (total arithmetic) and are flagged
   if (!live) return;
   if (!ok) f12_one(v);
   f12_st_global(mv, n, idx, v);
@@ -645,7 +651,8 @@ __global__ void __launch_bounds__(BLOCK, (PBC_CC_MINBLOCKS * 128) / BLOCK)
 k_f_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
              uint8_t* __restrict__ out, size_t n) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (idx >= n) return;
+  const bool live = idx < n;             // padding threads of the last block run too: f12_pow_u has block-wide barriers
+  if (!live) idx = 0;
   F12 f, acc;
   const bool ok = flag[idx] != 0;
   // every thread runs the exponentiation (block-wide barriers inside f12_pow_u); flagged-off
@@ -653,6 +660,7 @@ k_f_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
   f12_ld_global(f, mv, n, idx);
   if (!ok) f12_one(f);
   f12_final_exp(acc, f);
+  if (!live) return;                     // after the last barrier
   f12_to_reference(acc);
   if (!ok) f12_one(acc);
   uint8_t* o = out + idx * (12 * kWS);
@@ -684,7 +692,8 @@ __device__ __forceinline__ void f12_to_wire(uint8_t* p, const F12& v) {
 __global__ void k_f_tower_op(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a,
                              const uint8_t* __restrict__ b, size_t n) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
+  const bool live = idx < n;             // op 3 reaches the barriers of f12_pow_u: no early exit
+  if (!live) idx = 0;
   F12 x, y, r;
   f12_from_wire(x, a + idx * (12 * kWS));
   f12_from_wire(y, b + idx * (12 * kWS));
@@ -698,6 +707,7 @@ __global__ void k_f_tower_op(int op, uint8_t* __restrict__ out, const uint8_t* _
     case 5: r = x; f12_cyc_sqr(&r); break;
     default: r = x; f12_mul_line(&r, &F12C(y, 0).a, &F12C(y, 3), &F12C(y, 4)); break;
   }
+  if (!live) return;
   f12_to_reference(r);
   f12_to_wire(out + idx * (12 * kWS), r);
 }

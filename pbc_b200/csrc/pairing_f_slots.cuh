@@ -161,6 +161,13 @@ struct FS {
     if (neg) fq_neg(x, x);
     st(d, x);
   }
+  // slot <- kNS consecutive words (the same address for every thread: a table row)
+  static __device__ __forceinline__ void qldc(int d, const uint32_t* c) {
+    Fq x;
+#pragma unroll
+    for (int k = 0; k < kNS; k++) x.v[k] = c[k];
+    st(d, x);
+  }
   // (d, d+1) <- (global F_q^2 element at e, e+1) * slot a
   static __device__ __noinline__ void f2scale_g(int d, const uint32_t* g, int e, size_t n, int a) {
     Fq x, y0, y1;
@@ -382,7 +389,8 @@ struct FS {
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_t* __restrict__ mv,
-             uint32_t* __restrict__ flag, uint32_t* __restrict__ gq, size_t n, size_t stride1) {
+             uint32_t* __restrict__ flag, uint32_t* __restrict__ gq, size_t n, size_t stride1,
+             const uint32_t* __restrict__ tab, size_t rows) {
   using S = FS<BLOCK>;
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (idx >= n) return;                    // no block-wide barrier in this kernel
@@ -390,10 +398,15 @@ k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint3
   {
     // decode, validate, move to the basis in use (as k_f_miller)
     Fq xP, yP, sg;
-    const uint8_t* p = P + idx * stride1;
-    fq_from_wire(xP, p);
-    fq_from_wire(yP, p + kWS);
-    ok = cc_on_curve(xP, yP);
+    if (tab) {
+      ok = tab[3 * rows * kNS] != 0;           // fixed first argument: lines from the table (k_cc_pp_init)
+      fq_zero(xP); fq_zero(yP);
+    } else {
+      const uint8_t* p = P + idx * stride1;
+      fq_from_wire(xP, p);
+      fq_from_wire(yP, p + kWS);
+      ok = cc_on_curve(xP, yP);
+    }
     F2 Qx, Qy, t, u;
     const uint8_t* q = Q + idx * (4 * kWS);
     fq_from_wire(Qx.a, q);
@@ -423,12 +436,21 @@ k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint3
   }
   const uint32_t* g = gq + idx;
   int V = fsV, T = fsT;
+  size_t row = 0;
 #if PBC_CC_NAF
   int m = (int)c_ccnaf.len - 2;
 #else
   int m = (int)c_cc.rbits - 2;
 #endif
   for (;;) {
+    if (tab) {
+      // ---- fixed first argument: (a, b, c) of the next line from the table ----
+      S::qldc(T + 4, tab + (3 * row + 0) * kNS); S::f2scale_g(fsL4, g, 0, n, T + 4);
+      S::qldc(T + 4, tab + (3 * row + 1) * kNS); S::f2scale_g(fsL3, g, 2, n, T + 4);
+      S::qldc(fsC, tab + (3 * row + 2) * kNS);
+      S::f2mulxi(fsXL3, fsL3); S::f2mulxi(fsXL4, fsL4);
+      row++;
+    } else {
     // ---- tangent at V (a = -M Z^2, b = 2 Y Z^3, c = M X - 2 Y^2; the curve has A = 0), V <- 2V ----
     S::qsqr(T, fsZ);                                   // Z^2
     S::qsqr(T + 5, fsX);
@@ -448,6 +470,7 @@ k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint3
       S::qsqr(T + 2, T + 2); S::qdbl(T + 2, T + 2, 3);   // 8 Y^4
       S::qsub(T + 5, T + 5, fsX); S::qmul(fsY, T + 1, T + 5); S::qsub(fsY, fsY, T + 2);   // Y'
     }
+    }
     S::line_mul(T, V);
     { int s = V; V = T; T = s; }
     if (m == 0) break;
@@ -458,6 +481,14 @@ k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint3
     if ((c_cc.r[m >> 5] >> (m & 31)) & 1u) {
       const bool minus = false;
 #endif
+      if (tab) {
+        S::qldc(T + 4, tab + (3 * row + 0) * kNS); S::f2scale_g(fsL4, g, 0, n, T + 4);
+        S::qldc(T + 4, tab + (3 * row + 1) * kNS); S::f2scale_g(fsL3, g, 2, n, T + 4);
+        S::qldc(fsC, tab + (3 * row + 2) * kNS);
+        S::f2mulxi(fsXL3, fsL3); S::f2mulxi(fsXL4, fsL4);
+        row++;
+      } else {
+      (void)minus;
       // ---- chord through V and +-P (a = Y - yS Z^3, b = (xP Z^2 - X) Z, c = yS Z X - xP Y), V <- V +- P ----
       S::qldg(T + 6, g, 4, n, false);                    // xP
       S::qldg(T + 7, g, 5, n, minus);                    // yS
@@ -482,6 +513,7 @@ k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint3
       S::qsub(T, T, fsX); S::qmul(T, T, T + 3);
       S::qmul(T + 1, T + 1, fsY);
       S::qsub(fsY, T, T + 1);                            // Y3
+      }
       S::line_mul(T, V);
       { int s = V; V = T; T = s; }
     }

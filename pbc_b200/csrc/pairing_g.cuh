@@ -280,15 +280,20 @@ __device__ __forceinline__ void f10_to_wire(uint8_t* p, const F10& v) {
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (PBC_CC_MINBLOCKS * 128) / BLOCK)
 k_g_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_t* __restrict__ mv,
-           uint32_t* __restrict__ flag, size_t n, size_t stride1) {
+           uint32_t* __restrict__ flag, size_t n, size_t stride1, const uint32_t* __restrict__ tab, size_t rows) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   const bool live = idx < n;      // every thread runs the loop (block-wide barrier inside)
   if (!live) idx = 0;
   Fq xP, yP, k;
-  const uint8_t* p = P + idx * stride1;
-  fq_from_wire_b<kWG>(xP, p);
-  fq_from_wire_b<kWG>(yP, p + kWG);
-  bool ok = cc_on_curve(xP, yP);
+  bool ok;
+  if (tab) {
+    ok = tab[3 * rows * kNS] != 0;             // fixed first argument: lines from the table (k_cc_pp_init)
+  } else {
+    const uint8_t* p = P + idx * stride1;
+    fq_from_wire_b<kWG>(xP, p);
+    fq_from_wire_b<kWG>(yP, p + kWG);
+    ok = cc_on_curve(xP, yP);
+  }
   GTower::Ctx ctx;
   F5 t, u;
   F10 v;
@@ -313,7 +318,8 @@ k_g_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_
   fq_set(k, c_g.nqrinv2);
   f5_scale(ctx.Qy, ctx.Qy, k);
   f10_one(v);
-  miller_cc<GTower>(&v, xP, yP, &ctx);   // off-curve inputs run too (total arithmetic) and are flagged
+  if (tab) miller_cc_tab<GTower>(&v, tab, &ctx);
+  else miller_cc<GTower>(&v, xP, yP, &ctx);   // off-curve inputs run too (total arithmetic) and are flagged
   if (!live) return;
   if (!ok) f10_one(v);
   f10_st_global(mv, n, idx, v);
@@ -395,7 +401,8 @@ __global__ void __launch_bounds__(BLOCK, (PBC_CC_MINBLOCKS * 128) / BLOCK)
 k_g_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
              uint8_t* __restrict__ out, size_t n) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (idx >= n) return;
+  const bool live = idx < n;             // the ladder may hold block-wide barriers (PBC_G_FINAL_LOCKSTEP): no early exit
+  if (!live) idx = 0;
   F10 f;
   F5 out0, out1;
   const bool ok = flag[idx] != 0;
@@ -403,6 +410,7 @@ k_g_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
   f10_ld_global(f, mv, n, idx);
   if (!ok) f10_one(f);
   f10_final_exp(out0, out1, f);
+  if (!live) return;
   if (!ok) {
     f5_zero(out0);
     f5_zero(out1);
@@ -421,7 +429,8 @@ k_g_finalexp(const uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag,
 __global__ void k_g_tower_op(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a,
                              const uint8_t* __restrict__ b, size_t n) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
+  const bool live = idx < n;
+  if (!live) idx = 0;
   F10 x, y, r;
   f10_from_wire(x, a + idx * (10 * kWG));
   f10_from_wire(y, b + idx * (10 * kWG));
@@ -433,6 +442,7 @@ __global__ void k_g_tower_op(int op, uint8_t* __restrict__ out, const uint8_t* _
     case 5: f5_mul(&r.a, &x.a, &y.a); f5_zero(r.b); break;
     default: f5_inv(&r.a, &x.a); f5_zero(r.b); break;
   }
+  if (!live) return;
   f10_to_wire(out + idx * (10 * kWG), r);
 }
 

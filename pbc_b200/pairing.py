@@ -203,6 +203,41 @@ class Pairing:
             raise PairingError(last_error())
         return out.raw[:n * self.gt_len]
 
+    # -- element_mul / element_cmp on GT, is_almost_coddh (include/pbc_pairing.h:240-243) -------------
+    def gt_mul(self, a: bytes, b: bytes, n=None) -> bytes:
+        if n is None:
+            n = len(a) // self.gt_len
+        self._need(a, n * self.gt_len, "gt_mul a")
+        self._need(b, n * self.gt_len, "gt_mul b")
+        out = C.create_string_buffer(max(1, n * self.gt_len))
+        if lib.pbc_b200_gt_mul(self._h, C.addressof(out), _addr(a), _addr(b), n):
+            raise PairingError(last_error())
+        return out.raw[:n * self.gt_len]
+
+    def gt_cmp(self, a: bytes, b: bytes, n=None) -> bytes:
+        """one byte per element: 0 if equal (element_cmp returns 0), 1 otherwise"""
+        if n is None:
+            n = len(a) // self.gt_len
+        self._need(a, n * self.gt_len, "gt_cmp a")
+        self._need(b, n * self.gt_len, "gt_cmp b")
+        out = C.create_string_buffer(max(1, n))
+        if lib.pbc_b200_gt_cmp(self._h, C.addressof(out), _addr(a), _addr(b), n):
+            raise PairingError(last_error())
+        return out.raw[:n]
+
+    def is_almost_coddh(self, a: bytes, b: bytes, c: bytes, d: bytes, n=None) -> bytes:
+        """one byte per tuple: 1 if e(a, d) = e(b, c)^(+-1)"""
+        if n is None:
+            n = len(a) // self.g1_len
+        self._need(a, n * self.g1_len, "is_almost_coddh a")
+        self._need(b, n * self.g1_len, "is_almost_coddh b")
+        self._need(c, n * self.g2_len, "is_almost_coddh c")
+        self._need(d, n * self.g2_len, "is_almost_coddh d")
+        out = C.create_string_buffer(max(1, n))
+        if lib.pbc_b200_is_almost_coddh(self._h, C.addressof(out), _addr(a), _addr(b), _addr(c), _addr(d), n):
+            raise PairingError(last_error())
+        return out.raw[:n]
+
     def g1_pow_zn_device(self, d_out, d_in, d_k, n, stream=0):
         if lib.pbc_b200_g1_pow_zn_device(self._h, d_out, d_in, d_k, n, stream):
             raise PairingError(last_error())

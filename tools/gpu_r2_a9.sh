@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_type_a.py tests/test_gpu_type_fd.py tests/test_gpu_shim.py -m gpu -q -x 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_type_a.py tests/test_gpu_type_fd.py tests/test_gpu_shim.py tests/test_gpu_edge_cases.py -m gpu -q -x 2>&1 | tail -2
 timeout 600 python bench.py --steps 5 --warmup 3 --configs f,prod16 > gpurun_out/r2_bench_a9.json 2> gpurun_out/r2_bench_a9.err; echo "bench rc=$?"; tail -3 gpurun_out/r2_bench_a9.err
 python - <<'PY'
 import json
