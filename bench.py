@@ -48,16 +48,17 @@ SEED = 20260922
 # 2(2t)^2 + 2t of them: 528 for t = 8 (type a), 78 for t = 3 (types f, d)  -- SURVEY.md 8(d).
 # ref_mulmods = reference-algorithm mulmods per output (SURVEY 8d probes); ref_main = the part the
 # first kernel (Miller loop) stands for.  exec_unit_ops_main = what OUR first kernel executes
-# (type A, weight-(1,2) Miller loop: 1616 multiplications of 528 units + 1121 squarings of 408).
+# (type A, nine-slot weight-(1,2) Miller loop: 11 M + 6 S per step, 159 steps, + 26 M + 8 S around the loop:
+# 1775 multiplications of 528 units + 962 squarings of 408).
 WORKLOADS = {
     "a": dict(param="a", mode="single", k=1, n=1 << 20, unit=528, ref_mulmods=4394, ref_main=4394 - 719,
-              exec_unit_ops_main=1616 * 528 + 1121 * 408, cpu_rate=1100.0, port_rate=110.0,
+              exec_unit_ops_main=1775 * 528 + 962 * 408, cpu_rate=1100.0, port_rate=110.0,
               name="type A (param/a.param) element_pairing, batch 2^20 (P,Q) pairs per GPU, 512-bit F_q",
-              dtype="u32 limbs (16 x 32-bit = 512-bit F_q, exact integer)", kernels=("k_a_miller", "k_batch_invert", "k_a_finalexp")),
+              dtype="u32 limbs (16 x 32-bit = 512-bit F_q, exact integer)", kernels=("k_a_miller9", "k_batch_invert", "k_a_finalexp")),
     "f": dict(param="f", mode="single", k=1, n=1 << 20, unit=78, ref_mulmods=98183, ref_main=None,
-              exec_unit_ops_main=None, exec_unit_ops_all=824465, cpu_rate=70.0, port_rate=3.0,
+              exec_unit_ops_main=None, exec_unit_ops_all=852815, cpu_rate=70.0, port_rate=3.0,
               name="type F (param/f.param, BN k=12) element_pairing, batch 2^20 pairs per GPU, 158-bit F_q",
-              dtype="u32 limbs (5 x 32-bit = 160-bit F_q, exact integer)", kernels=("k_f_miller", "-", "k_f_finalexp")),
+              dtype="u32 limbs (5 x 32-bit = 160-bit F_q, exact integer)", kernels=("k_f_miller_s", "-", "k_f_finalexp_s")),
     "d": dict(param="d159", mode="single", k=1, n=1 << 18, unit=78, ref_mulmods=23039, ref_main=None,
               exec_unit_ops_main=None, exec_unit_ops_all=812590, cpu_rate=350.0, port_rate=10.0,
               name="type D (param/d159.param, MNT k=6) element_pairing, batch 2^18 pairs per GPU, 159-bit F_q",
@@ -67,10 +68,10 @@ WORKLOADS = {
               name="type G (param/g149.param, Freeman k=10) element_pairing, batch 2^18 pairs per GPU, 149-bit F_q",
               dtype="u32 limbs (5 x 32-bit = 160-bit F_q, exact integer)", kernels=("k_g_miller", "-", "k_g_finalexp")),
     "prod16": dict(param="a", mode="prod", k=16, n=1 << 16, unit=528, ref_mulmods=41536, ref_main=41536 - 719,
-                   exec_unit_ops_main=16 * (1616 * 528 + 1121 * 408), cpu_rate=130.0, port_rate=8.0,
+                   exec_unit_ops_main=16 * (1775 * 528 + 962 * 408), cpu_rate=130.0, port_rate=8.0,
                    name="type A element_prod_pairing n=16, 2^16 outputs (2^20 Miller loops) over all GPUs",
                    dtype="u32 limbs (16 x 32-bit = 512-bit F_q, exact integer)",
-                   kernels=("k_a_miller+k_a_prod", "k_batch_invert", "k_a_finalexp")),
+                   kernels=("k_a_miller9+k_a_prod", "k_batch_invert", "k_a_finalexp")),
     "pp": dict(param="a", mode="pp", k=1, n=1 << 20, unit=528, ref_mulmods=1838 + 719, ref_main=1838,
                exec_unit_ops_main=(160 * 7 + 5) * 528 + 4 * 408, cpu_rate=400.0, port_rate=110.0,
                name="type A pairing_pp_init + pairing_pp_apply: one fixed first argument, 2^20 second arguments per GPU",
@@ -619,7 +620,7 @@ def run_config(G, wname, args, Ph, Qh, n, idx, cpu_out, cpu, steps, warmup, per_
             roof["reference_equivalent_is"] = ("the reference algorithm's mulmod count x %d unit ops per mulmod over the same "
                                                "time: above frac because these kernels execute fewer multiplications" % unit)
         assert frac <= 1.05, "roofline.frac %.3f > 1: the executed-work count or the peak is wrong" % frac
-        ws_per = 576 * k if w["param"] == "a" else {"f": 61 * 4, "d159": 31 * 4, "g149": 51 * 4, "a1": 6 * 136}[w["param"]]
+        ws_per = 704 * k if w["param"] == "a" else {"f": (61 + 30 + 240) * 4, "d159": 31 * 4, "g149": 51 * 4, "a1": 6 * 136}[w["param"]]
         rec = {
             "value": value, "unit": unit_name, "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
             "scaling": "weak" if (single and args.scaling == "weak") else "strong",
