@@ -76,7 +76,7 @@ WORKLOADS = {
                exec_unit_ops_main=(160 * 7 + 5) * 528 + 4 * 408, cpu_rate=400.0, port_rate=110.0,
                name="type A pairing_pp_init + pairing_pp_apply: one fixed first argument, 2^20 second arguments per GPU",
                dtype="u32 limbs (16 x 32-bit = 512-bit F_q, exact integer)",
-               kernels=("k_a_pp_init+k_a_pp_apply", "k_batch_invert", "k_a_finalexp")),
+               kernels=("k_a_pp_apply", "k_batch_invert", "k_a_finalexp")),
 }
 def _a1_exec_ops():
     """unit ops k_a1_miller executes per pairing: 13 M + 6 S per bit of n, 16 M + 3 S per chord;
@@ -485,9 +485,13 @@ def run_config(G, wname, args, Ph, Qh, n, idx, cpu_out, cpu, steps, warmup, per_
     dP, dQ = Pp.to(dev), Qp.to(dev)
     dO = torch.empty(n * gt, dtype=torch.uint8, device=dev)
 
+    # fixed first argument: pairing_pp_init once, outside the timed region, as benchmark/benchmark.c:79-84
+    # does; the handle keeps the line table on the device (pbc_b200_pp_init)
+    pph = pr.pp_init(Ph[:g1].tobytes()) if w["mode"] == "pp" else None
+
     def step():
         if w["mode"] == "pp":
-            pr.pp_apply_device(dO.data_ptr(), dP.data_ptr(), dQ.data_ptr(), n, st.cuda_stream)
+            pph.apply_device(dO.data_ptr(), dQ.data_ptr(), n, st.cuda_stream)
         elif single:
             pr.apply_device(dO.data_ptr(), dP.data_ptr(), dQ.data_ptr(), n, st.cuda_stream)
         else:
@@ -495,7 +499,7 @@ def run_config(G, wname, args, Ph, Qh, n, idx, cpu_out, cpu, steps, warmup, per_
 
     def host_step():
         if w["mode"] == "pp":
-            pr.pp_apply_into(Op, Pp, Qp, n)
+            pph.apply_into(Op, Qp, n)
         elif single:
             pr.apply_into(Op, Pp, Qp, n)
         else:
@@ -646,6 +650,8 @@ def run_config(G, wname, args, Ph, Qh, n, idx, cpu_out, cpu, steps, warmup, per_
                         "ranks_checked": int(tot[3]), "against": "oracle/_ref (unmodified reference), seeded random index sample per rank + whole e2e buffer vs device buffer"}
                        if tot[3] > 0 else None),
         }
+    if pph is not None:
+        pph.clear()
     pr.clear()
     del dP, dQ, dO, Pp, Qp, Op
     torch.cuda.empty_cache()

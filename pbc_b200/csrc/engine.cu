@@ -758,7 +758,12 @@ static constexpr size_t kSmemAMiller9 = (size_t)kA9Slots * 64 * kBlockMiller;
 #define PBC_F_SLOTS 1
 #endif
 static constexpr int kBlockFS = 128;
-static constexpr size_t kSmemFMillerS = (size_t)kFSlots * kNS * 4 * kBlockFS;
+// threads per block of the slot-machine Miller kernel: 128 -> two blocks (8 warps) per SM, 96 -> three blocks (9 warps)
+#ifndef PBC_FS_MILLER_BLOCK
+#define PBC_FS_MILLER_BLOCK 128
+#endif
+static constexpr int kBlockFSM = PBC_FS_MILLER_BLOCK;
+static constexpr size_t kSmemFMillerS = (size_t)kFSlots * kNS * 4 * kBlockFSM;
 static constexpr size_t kSmemFFinalS = (size_t)kFFinalSlots * kNS * 4 * kBlockFS;
 static constexpr size_t kSmemAFinal = (size_t)kAFSlots * 64 * kBlockFinal;
 static constexpr size_t kSmemInv16 = (size_t)5 * 64 * kBlockInv;
@@ -805,7 +810,7 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
       CUDA_OK(allow_smem(k_a_g1_from_hash<kBlockMiller>, (size_t)kGSlots * 64 * kBlockMiller));
       CUDA_OK(allow_smem(k_a_g1_decompress<kBlockMiller>, (size_t)5 * 64 * kBlockMiller));
     }
-    if (p->type == 'f') CUDA_OK(allow_smem(k_f_miller_s<kBlockFS>, kSmemFMillerS));
+    if (p->type == 'f') CUDA_OK(allow_smem(k_f_miller_s<kBlockFSM>, kSmemFMillerS));
     if (p->type == 'f') CUDA_OK(allow_smem(k_f_finalexp_s<kBlockFS>, kSmemFFinalS));
     if (p->type == '1') {
       CUDA_OK(allow_smem(k_a1_miller<kBlockA1>, kSmemA1Miller));
@@ -1027,7 +1032,7 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
     }
     if (isf && PBC_F_SLOTS && p->f.slots_ok) {
       uint32_t* gq = mv + (W + 1) * m + (job.mode == kProd ? (W + 1) * n : 0);   // after the Miller values and flags
-      k_f_miller_s<kBlockFS><<<(unsigned)((m + kBlockFS - 1) / kBlockFS), kBlockFS, kSmemFMillerS, st>>>(d_in1, d_in2, mv, flag, gq, m, stride1, tab, rows);
+      k_f_miller_s<kBlockFSM><<<(unsigned)((m + kBlockFSM - 1) / kBlockFSM), kBlockFSM, kSmemFMillerS, st>>>(d_in1, d_in2, mv, flag, gq, m, stride1, tab, rows);
     } else if (isf) k_f_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1, tab, rows);
     else if (isg) k_g_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1, tab, rows);
     else k_d_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1, tab, rows);

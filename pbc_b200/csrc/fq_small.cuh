@@ -169,6 +169,124 @@ __device__ __forceinline__ void fqw_sub(FqW& r, const FqW& a, const FqW& b) {
 #pragma unroll
   for (int k = 1; k < 2 * kNS; k++) PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(r.v[k]) : "r"(a.v[k]), "r"(b.v[k]));
 }
+// ---- inline double-width product and reduction (the slot-machine kernels, pairing_f_slots.cuh) ----
+// t = a b (25 products), operand scanning on two accumulators.  The product a_j b_i is a 64-bit value
+// at word column c = i + j; products on EVEN columns are accumulated in E (pairs (E[c], E[c+1])),
+// products on ODD columns in O, so that within one row (one b_i) each accumulator sees a run of
+// ADJACENT pairs: one IMAD.WIDE.U32 per product with the carry handed from pair to pair in the
+// carry flag, no per-product carry word.  The pair two columns above a row's run has not been touched
+// by earlier rows (row i' reaches column i' + 4 at most), so either the run's top pair is fresh and
+// cannot overflow, or one addc into the fresh word above it absorbs the carry.  t = E + O at the end.
+// The column-wise form this replaces (fq_mulw_call in fq_small.cuh) compiles to ~95 instructions per
+// product of two elements -- IMAD.WIDE + IADD3.X per product plus SEL / IMAD.MOV / IMAD.X to move
+// carries and re-align register pairs at every column (ncu, round 2: IMAD.WIDE was 21 % of the type F
+// instruction stream and a third of the multiplier pipe's busy time went to those moves); this one to ~40.
+#ifndef PBC_FQW_OS
+#define PBC_FQW_OS 1
+#endif
+#define PBC_MADW_FIRST(lo, hi, x, y) PBC_ASM("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(x), "r"(y))
+#define PBC_MADW_NEXT(lo, hi, x, y) PBC_ASM("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(x), "r"(y))
+#define PBC_MULW_PAIR(lo, hi, x, y) PBC_ASM("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(x), "r"(y))
+#define PBC_CARRY_TO(w) PBC_ASM("addc.u32 %0, 0, 0;" : "=r"(w))
+__device__ __forceinline__ void fqw_mul(FqW& t, const Fq& a, const Fq& b) {
+  static_assert(kNS == 5, "the row schedule below is written out for five limbs");
+#if PBC_FQW_OS
+  uint32_t E[10], O[10];
+  const uint32_t* x = a.v;
+  const uint32_t* y = b.v;
+  // row 0: every pair is fresh
+  PBC_MULW_PAIR(E[0], E[1], x[0], y[0]);
+  PBC_MULW_PAIR(E[2], E[3], x[2], y[0]);
+  PBC_MULW_PAIR(E[4], E[5], x[4], y[0]);
+  PBC_MULW_PAIR(O[1], O[2], x[1], y[0]);
+  PBC_MULW_PAIR(O[3], O[4], x[3], y[0]);
+  // row 1: E columns 2, 4 (+ carry into the fresh E[6]); O columns 1, 3, 5 (top pair fresh)
+  O[5] = 0; O[6] = 0;
+  PBC_MADW_FIRST(E[2], E[3], x[1], y[1]);
+  PBC_MADW_NEXT(E[4], E[5], x[3], y[1]);
+  PBC_CARRY_TO(E[6]);
+  PBC_MADW_FIRST(O[1], O[2], x[0], y[1]);
+  PBC_MADW_NEXT(O[3], O[4], x[2], y[1]);
+  PBC_MADW_NEXT(O[5], O[6], x[4], y[1]);
+  // row 2: E columns 2, 4, 6 (E[6] holds one carry bit, E[7] fresh: no overflow); O columns 3, 5 (+ carry into O[7])
+  E[7] = 0;
+  PBC_MADW_FIRST(E[2], E[3], x[0], y[2]);
+  PBC_MADW_NEXT(E[4], E[5], x[2], y[2]);
+  PBC_MADW_NEXT(E[6], E[7], x[4], y[2]);
+  PBC_MADW_FIRST(O[3], O[4], x[1], y[2]);
+  PBC_MADW_NEXT(O[5], O[6], x[3], y[2]);
+  PBC_CARRY_TO(O[7]);
+  // row 3: E columns 4, 6 (+ carry into E[8]); O columns 3, 5, 7 (O[8] fresh)
+  O[8] = 0;
+  PBC_MADW_FIRST(E[4], E[5], x[1], y[3]);
+  PBC_MADW_NEXT(E[6], E[7], x[3], y[3]);
+  PBC_CARRY_TO(E[8]);
+  PBC_MADW_FIRST(O[3], O[4], x[0], y[3]);
+  PBC_MADW_NEXT(O[5], O[6], x[2], y[3]);
+  PBC_MADW_NEXT(O[7], O[8], x[4], y[3]);
+  // row 4: E columns 4, 6, 8 (E[9] fresh); O columns 5, 7 (+ carry into O[9])
+  E[9] = 0;
+  PBC_MADW_FIRST(E[4], E[5], x[0], y[4]);
+  PBC_MADW_NEXT(E[6], E[7], x[2], y[4]);
+  PBC_MADW_NEXT(E[8], E[9], x[4], y[4]);
+  PBC_MADW_FIRST(O[5], O[6], x[1], y[4]);
+  PBC_MADW_NEXT(O[7], O[8], x[3], y[4]);
+  PBC_CARRY_TO(O[9]);
+  // t = E + O   (O[0] does not exist; the sum is below 2^320: no carry out of word 9)
+  t.v[0] = E[0];
+  PBC_ASM("add.cc.u32 %0, %1, %2;" : "=r"(t.v[1]) : "r"(E[1]), "r"(O[1]));
+#pragma unroll
+  for (int k = 2; k < 9; k++) PBC_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(t.v[k]) : "r"(E[k]), "r"(O[k]));
+  PBC_ASM("addc.u32 %0, %1, %2;" : "=r"(t.v[9]) : "r"(E[9]), "r"(O[9]));
+#else
+  uint32_t u0 = 0, u1 = 0, u2 = 0;
+#pragma unroll
+  for (int i = 0; i < 2 * kNS - 1; i++) {
+#pragma unroll
+    for (int j = (i < kNS ? 0 : i - kNS + 1); j <= (i < kNS ? i : kNS - 1); j++) PBC_MAC3(u0, u1, u2, a.v[j], b.v[i - j]);
+    t.v[i] = u0;
+    u0 = u1; u1 = u2; u2 = 0;
+  }
+  t.v[2 * kNS - 1] = u0;
+#endif
+}
+// Montgomery reduction of t < 2 q R to the canonical residue (two conditional subtractions)
+__device__ __forceinline__ void fqw_redc2(Fq& r, const FqW& t) {
+  uint32_t m[kNS], o[kNS];
+  uint32_t v0 = 0, v1 = 0, v2 = 0;
+#pragma unroll
+  for (int i = 0; i < kNS; i++) {
+#pragma unroll
+    for (int j = 0; j < i; j++) PBC_MAC3(v0, v1, v2, m[j], c_fp.p[i - j]);
+    PBC_ASM("add.cc.u32 %0, %0, %3; addc.cc.u32 %1, %1, 0; addc.u32 %2, %2, 0;" : "+r"(v0), "+r"(v1), "+r"(v2) : "r"(t.v[i]));
+    m[i] = v0 * c_fp.np0;
+    PBC_MAC3(v0, v1, v2, m[i], c_fp.p[0]);
+    v0 = v1; v1 = v2; v2 = 0;
+  }
+#pragma unroll
+  for (int i = kNS; i < 2 * kNS; i++) {
+#pragma unroll
+    for (int j = i - kNS + 1; j < kNS; j++) PBC_MAC3(v0, v1, v2, m[j], c_fp.p[i - j]);
+    PBC_ASM("add.cc.u32 %0, %0, %3; addc.cc.u32 %1, %1, 0; addc.u32 %2, %2, 0;" : "+r"(v0), "+r"(v1), "+r"(v2) : "r"(t.v[i]));
+    o[i - kNS] = v0;
+    v0 = v1; v1 = v2; v2 = 0;
+  }
+  // value = o + v0 2^160 < 3 q: subtract q while it is >= q
+  uint32_t d[kNS], borrow;
+  PBC_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(d[0]) : "r"(o[0]), "r"(c_fp.p[0]));
+#pragma unroll
+  for (int k = 1; k < kNS; k++) PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(d[k]) : "r"(o[k]), "r"(c_fp.p[k]));
+  PBC_ASM("subc.u32 %0, 0, 0;" : "=r"(borrow));
+  bool use_d = v0 != 0 || borrow == 0;
+#pragma unroll
+  for (int k = 0; k < kNS; k++) o[k] = use_d ? d[k] : o[k];
+  PBC_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(d[0]) : "r"(o[0]), "r"(c_fp.p[0]));
+#pragma unroll
+  for (int k = 1; k < kNS; k++) PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(d[k]) : "r"(o[k]), "r"(c_fp.p[k]));
+  PBC_ASM("subc.u32 %0, 0, 0;" : "=r"(borrow));
+#pragma unroll
+  for (int k = 0; k < kNS; k++) r.v[k] = borrow == 0 ? d[k] : o[k];
+}
 // a + b without reduction (the caller knows the sum fits the limbs)
 __device__ __forceinline__ void fq_add_nr(Fq& r, const Fq& a, const Fq& b) {
   PBC_ASM("add.cc.u32 %0, %1, %2;" : "=r"(r.v[0]) : "r"(a.v[0]), "r"(b.v[0]));

@@ -262,12 +262,16 @@ k_a_miller(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4* 
 //   f' = g (Re l + i Im l)
 // ---------------------------------------------------------------------------------------------
 enum A9Slot { nX, nY, nZ, nF0, nF1, nT0, nT1, nT2, nT3, kA9Slots };
+// PBC_A_LOCKSTEP = 1: block-wide barrier at the top of every Miller iteration (A/B experiment)
+#ifndef PBC_A_LOCKSTEP
+#define PBC_A_LOCKSTEP 1
+#endif
 
 // qx, qy: this thread's Q coordinates in the global array (Montgomery form), vectors n apart
 template <class O>
 __device__ __forceinline__ void a_double_step_9(const uint4* qx, const uint4* qy, size_t n) {
   O::template mul2<true>(nT0, nF0, nF1, nF0, nF1);   // g0                     (f0 slot is free from here)
-  O::mul(nF1, nF0, nF1);
+  O::mulp(nF1, nF0, nF1);
   O::dbl(nF1, nF1);                                  // g1
   O::sqr(nT1, nX);                                   // A
   O::sqr(nT2, nY);                                   // B
@@ -276,9 +280,9 @@ __device__ __forceinline__ void a_double_step_9(const uint4* qx, const uint4* qy
   O::add(nT3, nT1, nT3);                             // A' = A + C
   O::dbl(nT1, nT3);
   O::add(nT1, nT1, nF0);                             // U = 3A + C
-  O::mul(nT1, nT1, nZ);
+  O::mulp(nT1, nT1, nZ);
   O::mulg(nT1, nT1, qx, n);                          // U Z Qx
-  O::mul(nX, nX, nF0);                               // X T
+  O::mulp(nX, nX, nF0);                               // X T
   O::add(nT1, nT1, nX);                              // Re l                   (X slot is free)
   O::sqr(nX, nF0);                                   // X' = T^2
   O::sqr(nT3, nT3);
@@ -288,14 +292,14 @@ __device__ __forceinline__ void a_double_step_9(const uint4* qx, const uint4* qy
   O::sqr(nF0, nF0);
   O::sub(nF0, nF0, nT2);
   O::sub(nF0, nF0, nX);                              // F = (T + Y)^2 - B - X'
-  O::mul(nT3, nT3, nF0);                             // Y' (kept in T3 until Y has had its last use)
-  O::mul(nF0, nY, nZ);
+  O::mulp(nT3, nT3, nF0);                             // Y' (kept in T3 until Y has had its last use)
+  O::mulp(nF0, nY, nZ);
   O::dbl(nF0, nF0);
   O::mulg(nF0, nF0, qy, n);                          // Im l = 2 Y Z Qy
   O::dbl(nZ, nT2, 2);                                // Z' = 4 B
   O::template mul2<false>(nT2, nT0, nF1, nT1, nF0);  // (g0 + g1)(Re l + Im l)
-  O::mul(nT0, nT0, nT1);                             // g0 Re l
-  O::mul(nF1, nF1, nF0);                             // g1 Im l
+  O::mulp(nT0, nT0, nT1);                             // g0 Re l
+  O::mulp(nF1, nF1, nF0);                             // g1 Im l
   O::sub(nF0, nT0, nF1);                             // f0'
   O::sub(nT2, nT2, nT0);
   O::sub(nF1, nT2, nF1);                             // f1'
@@ -306,8 +310,8 @@ __device__ __forceinline__ void a_double_step_9(const uint4* qx, const uint4* qy
 template <class O>
 __device__ __forceinline__ void a_fmul_2t(int f0, int f1, int l0, int l1, int t0, int t1) {
   O::template mul2<false>(t0, f0, f1, l0, l1);
-  O::mul(f0, f0, l0);
-  O::mul(f1, f1, l1);
+  O::mulp(f0, f0, l0);
+  O::mulp(f1, f1, l1);
   O::sub(t1, f0, f1);
   O::sub(t0, t0, f0);
   O::sub(f1, t0, f1);
@@ -321,12 +325,20 @@ k_a_miller9(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4*
             uint4* __restrict__ dprod, uint4* __restrict__ save, uint4* __restrict__ qm, size_t n) {
   using O = Ops<kNA, true, BLOCK>;
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+#if PBC_A_LOCKSTEP
+  const bool live = idx < n;                 // every thread runs the loop: block-wide barrier inside
+  if (!live) idx = 0;
+#else
   if (idx >= n) return;                      // no block-wide barrier in this kernel
+  const bool live = true;
+#endif
   bool okP = a_load_point<O>(nX, nY, nT0, nT1, P + idx * (2 * kWA));
   bool okQ = a_load_point<O>(nT2, nT3, nT0, nT1, Q + idx * (2 * kWA));
   bool valid = okP && okQ;
-  O::st_global(qm, 0, n, idx, nT2);
-  O::st_global(qm, 1, n, idx, nT3);
+  if (live) {
+    O::st_global(qm, 0, n, idx, nT2);
+    O::st_global(qm, 1, n, idx, nT3);
+  }
   const uint4* qx = qm + idx;
   const uint4* qy = qm + 4 * n + idx;
 
@@ -337,7 +349,10 @@ k_a_miller9(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4*
 
   const int exp1 = c_a.exp1, exp2 = c_a.exp2;
   for (int i = 0; i < exp2; i++) {
-    if (i == exp1) {
+#if PBC_A_LOCKSTEP
+    __syncthreads();                         // the loop is uniform: keep the block's warps in the same routine (instruction cache)
+#endif
+    if (i == exp1 && live) {
       // V1 = +-V, f1 = f or conj(f) ~ 1/f   (ecc/a_param.c:1162-1169)
       if (c_a.sign1 < 0) { O::neg(nT0, nY); O::neg(nT1, nF1); }
       else               { O::copy(nT0, nY); O::copy(nT1, nF1); }
@@ -349,6 +364,7 @@ k_a_miller9(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4*
     }
     a_double_step_9<O>(qx, qy, n);
   }
+  if (!live) return;
 
   // f *= f1
   O::ld_global(nT2, save, 3, n, idx);
@@ -359,21 +375,21 @@ k_a_miller9(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4*
   //   a = Y Z1^2 - Y1 Z^2,  b = Z Z1 (X1 Z - X Z1),  c = X Z Y1 - Y X1 Z1
   O::ld_global(nT0, save, 2, n, idx);          // Z1
   O::ld_global(nT1, save, 0, n, idx);          // X1
-  O::mul(nT2, nT1, nZ);                         // X1 Z
-  O::mul(nT3, nX, nT0);                         // X Z1
+  O::mulp(nT2, nT1, nZ);                         // X1 Z
+  O::mulp(nT3, nX, nT0);                         // X Z1
   O::sub(nT2, nT2, nT3);
-  O::mul(nT2, nT2, nZ);
-  O::mul(nT2, nT2, nT0);                        // b
-  O::mul(nT3, nX, nZ);                          // X Z               (last use of X)
+  O::mulp(nT2, nT2, nZ);
+  O::mulp(nT2, nT2, nT0);                        // b
+  O::mulp(nT3, nX, nZ);                          // X Z               (last use of X)
   O::ld_global(nX, save, 1, n, idx);           // Y1
-  O::mul(nT3, nT3, nX);                         // X Z Y1
-  O::mul(nT1, nT1, nT0);                        // X1 Z1
-  O::mul(nT1, nT1, nY);                         // Y X1 Z1
+  O::mulp(nT3, nT3, nX);                         // X Z Y1
+  O::mulp(nT1, nT1, nT0);                        // X1 Z1
+  O::mulp(nT1, nT1, nY);                         // Y X1 Z1
   O::sub(nT3, nT3, nT1);                        // c
   O::sqr(nT0, nT0);                             // Z1^2
-  O::mul(nT0, nT0, nY);                         // Y Z1^2
+  O::mulp(nT0, nT0, nY);                         // Y Z1^2
   O::sqr(nT1, nZ);                              // Z^2
-  O::mul(nT1, nT1, nX);                         // Y1 Z^2
+  O::mulp(nT1, nT1, nX);                         // Y1 Z^2
   O::sub(nT0, nT0, nT1);                        // a
   O::mulg(nT0, nT0, qx, n);
   O::sub(nT3, nT3, nT0);                        // Re l = c - a Qx
@@ -384,8 +400,8 @@ k_a_miller9(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4*
   O::sqr(nT0, nF0);
   O::sqr(nT1, nF1);
   O::add(nT0, nT0, nT1);
-  O::mul(nT1, nF0, nF1);
-  O::mul(nT0, nT0, nT1);
+  O::mulp(nT1, nF0, nF1);
+  O::mulp(nT0, nT0, nT1);
   if (!valid) O::st(nT0, zero);
   O::st_global(f, 0, n, idx, nF0);
   O::st_global(f, 1, n, idx, nF1);

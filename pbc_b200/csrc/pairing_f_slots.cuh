@@ -25,7 +25,11 @@
 
 namespace pbcb200 {
 
-constexpr int kFSlots = 36;            // F_q slots per thread
+// Slots per thread: 36 = 720 B, two 128-thread blocks (8 warps) per SM, about 210 registers per thread.
+// A 29-slot version (V = (X, Y, Z) and xi L3, xi L4 parked in the global scratch: three blocks = 12 warps
+// per SM, registers capped at 168) was measured 36 % SLOWER (profiles/r2_variants_f29.jsonl): the cap
+// spills inside the product routines.  These kernels want registers more than they want warps.
+constexpr int kFSlots = 36;
 enum FSlotMap {
   fsV = 0,                             // 12: Miller value (coefficient j at 2 * f12_pos(j))
   fsT = 12,                            // 12: scratch / the other copy (roles alternate)
@@ -33,58 +37,11 @@ enum FSlotMap {
   fsC = 27,                            // line: c + L3 x^3 + L4 x^4
   fsL3 = 28, fsL4 = 30, fsXL3 = 32, fsXL4 = 34,
 };
-constexpr int kFGWords = 6 * kNS;      // global scratch per pairing: Qx (2), Qy (2), xP, yP
+// global scratch per pairing, F_q elements: Qx (0, 1), Qy (2, 3), xP (4), yP (5)
+enum FGlobalMap { fgQx = 0, fgQy = 2, fgPx = 4, fgPy = 5 };
+constexpr int kFGWords = 6 * kNS;
 
-// ---- register-level pieces (inline; the slot routines below are the out-of-line units) ----
-// t = a b, schoolbook by columns (25 products)
-__device__ __forceinline__ void fqw_mul(FqW& t, const Fq& a, const Fq& b) {
-  uint32_t u0 = 0, u1 = 0, u2 = 0;
-#pragma unroll
-  for (int i = 0; i < 2 * kNS - 1; i++) {
-#pragma unroll
-    for (int j = (i < kNS ? 0 : i - kNS + 1); j <= (i < kNS ? i : kNS - 1); j++) PBC_MAC3(u0, u1, u2, a.v[j], b.v[i - j]);
-    t.v[i] = u0;
-    u0 = u1; u1 = u2; u2 = 0;
-  }
-  t.v[2 * kNS - 1] = u0;
-}
-// Montgomery reduction of t < 2 q R to the canonical residue (two conditional subtractions)
-__device__ __forceinline__ void fqw_redc2(Fq& r, const FqW& t) {
-  uint32_t m[kNS], o[kNS];
-  uint32_t v0 = 0, v1 = 0, v2 = 0;
-#pragma unroll
-  for (int i = 0; i < kNS; i++) {
-#pragma unroll
-    for (int j = 0; j < i; j++) PBC_MAC3(v0, v1, v2, m[j], c_fp.p[i - j]);
-    PBC_ASM("add.cc.u32 %0, %0, %3; addc.cc.u32 %1, %1, 0; addc.u32 %2, %2, 0;" : "+r"(v0), "+r"(v1), "+r"(v2) : "r"(t.v[i]));
-    m[i] = v0 * c_fp.np0;
-    PBC_MAC3(v0, v1, v2, m[i], c_fp.p[0]);
-    v0 = v1; v1 = v2; v2 = 0;
-  }
-#pragma unroll
-  for (int i = kNS; i < 2 * kNS; i++) {
-#pragma unroll
-    for (int j = i - kNS + 1; j < kNS; j++) PBC_MAC3(v0, v1, v2, m[j], c_fp.p[i - j]);
-    PBC_ASM("add.cc.u32 %0, %0, %3; addc.cc.u32 %1, %1, 0; addc.u32 %2, %2, 0;" : "+r"(v0), "+r"(v1), "+r"(v2) : "r"(t.v[i]));
-    o[i - kNS] = v0;
-    v0 = v1; v1 = v2; v2 = 0;
-  }
-  // value = o + v0 2^160 < 3 q: subtract q while it is >= q
-  uint32_t d[kNS], borrow;
-  PBC_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(d[0]) : "r"(o[0]), "r"(c_fp.p[0]));
-#pragma unroll
-  for (int k = 1; k < kNS; k++) PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(d[k]) : "r"(o[k]), "r"(c_fp.p[k]));
-  PBC_ASM("subc.u32 %0, 0, 0;" : "=r"(borrow));
-  bool use_d = v0 != 0 || borrow == 0;
-#pragma unroll
-  for (int k = 0; k < kNS; k++) o[k] = use_d ? d[k] : o[k];
-  PBC_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(d[0]) : "r"(o[0]), "r"(c_fp.p[0]));
-#pragma unroll
-  for (int k = 1; k < kNS; k++) PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(d[k]) : "r"(o[k]), "r"(c_fp.p[k]));
-  PBC_ASM("subc.u32 %0, 0, 0;" : "=r"(borrow));
-#pragma unroll
-  for (int k = 0; k < kNS; k++) r.v[k] = borrow == 0 ? d[k] : o[k];
-}
+// ---- register-level pieces (fqw_mul, fqw_redc2: fq_small.cuh) ----
 // (re, im) += x y for F_q^2 operands in the internal basis (i^2 = -1), double width, unreduced:
 //   re += x0 y0 - x1 y1,  im += (x0 + x1)(y0 + y1) - x0 y0 - x1 y1.
 // The caller starts re at (number of terms) * q^2 so that it never goes negative.
@@ -114,6 +71,38 @@ __device__ __forceinline__ void f2r_mul_xi(Fq& x0, Fq& x1) {
   fq_small_combo(t, a, b1, b2, b4);      // a x1
   fq_sub(x0, p, q2);
   fq_add(x1, s2, t);
+}
+
+// (o0 + o1 i) = (x0 + x1 i)^2 = (x0 + x1)(x0 - x1) + 2 x0 x1 i, in registers
+__device__ __forceinline__ void f2r_sqr(Fq& o0, Fq& o1, const Fq& x0, const Fq& x1) {
+  Fq s, t;
+  fq_add_nr(s, x0, x1);                    // below 2q < 2^160: fine as a multiplier operand
+  fq_sub(t, x0, x1);
+  mont_mul_ps<kNS, false>(s.v, s.v, t.v);
+  mont_mul_ps<kNS, false>(t.v, x0.v, x1.v);
+  fq_dbl(o1, t);
+  o0 = s;
+}
+// (r0, r1) = (a + b s)^2 in F_q^4 = F_q^2[s]/(s^2 - xi): r0 = a^2 + xi b^2, r1 = (a + b)^2 - a^2 - b^2
+__device__ __forceinline__ void f4r_sqr(Fq& r00, Fq& r01, Fq& r10, Fq& r11, const Fq& a0, const Fq& a1,
+                                        const Fq& b0, const Fq& b1) {
+  Fq sb0, sb1, t0, t1;
+  f2r_sqr(r00, r01, a0, a1);               // a^2
+  f2r_sqr(sb0, sb1, b0, b1);               // b^2
+  fq_add(t0, a0, b0); fq_add(t1, a1, b1);
+  f2r_sqr(r10, r11, t0, t1);               // (a + b)^2
+  fq_sub(r10, r10, r00); fq_sub(r11, r11, r01);
+  fq_sub(r10, r10, sb0); fq_sub(r11, r11, sb1);
+  f2r_mul_xi(sb0, sb1);
+  fq_add(r00, r00, sb0); fq_add(r01, r01, sb1);
+}
+// c <- 3 r + 2 c (PLUS) or 3 r - 2 c, one F_q coordinate
+template <bool PLUS>
+__device__ __forceinline__ void gs_combine(Fq& c, const Fq& r) {
+  Fq t;
+  if (PLUS) fq_add(t, r, c); else fq_sub(t, r, c);
+  fq_dbl(t, t);
+  fq_add(c, r, t);
 }
 
 // ---- the slot machine ----
@@ -273,11 +262,11 @@ struct FS {
 #pragma unroll 1
     for (int k = 0; k < 6; k++) {
       const int i3 = k >= 3 ? k - 3 : k + 3, i4 = k >= 4 ? k - 4 : k + 2;
-      const int m3 = k >= 3 ? fsL3 : fsXL3, m4 = k >= 4 ? fsL4 : fsXL4;
       FqW re, im, t;
 #pragma unroll
       for (int w = 0; w < 2 * kNS; w++) { re.v[w] = c_f.qsqm[1][w]; im.v[w] = 0; }
       Fq x0, x1, y0, y1;
+      const int m3 = k >= 3 ? fsL3 : fsXL3, m4 = k >= 4 ? fsL4 : fsXL4;
       ld(x0, m3); ld(x1, m3 + 1);
       ld(y0, v + 2 * f12_pos(i3)); ld(y1, v + 2 * f12_pos(i3) + 1);
       f2w_mac(re, im, x0, x1, y0, y1);
@@ -333,19 +322,38 @@ struct FS {
     f2sub(r1, r1, e);
     f2addxi(r0, r0, e);
   }
-  // v <- v^2 for v in the cyclotomic subgroup (Granger-Scott, see f12_cyc_sqr); t: 12 slots, e: 2 slots
-  static __device__ __forceinline__ void f12cycsqr(int v, int t, int e) {
-    // coefficient j lives at v + 2 f12_pos(j): c0 -> 0, c1 -> 6, c2 -> 2, c3 -> 8, c4 -> 4, c5 -> 10
-    f4sqr(t, t + 2, v, v + 8, e);              // A from (c0, c3)
-    f4sqr(t + 4, t + 6, v + 6, v + 4, e);      // B from (c1, c4)
-    f4sqr(t + 8, t + 10, v + 2, v + 10, e);    // C from (c2, c5)
-    f2gs<false>(v, t, v);                      // c0' = 3 A0 - 2 c0
-    f2gs<true>(v + 8, t + 2, v + 8);           // c3' = 3 A1 + 2 c3
-    f2gs<false>(v + 2, t + 4, v + 2);          // c2' = 3 B0 - 2 c2
-    f2gs<true>(v + 10, t + 6, v + 10);         // c5' = 3 B1 + 2 c5
-    f2mulxi(t + 10, t + 10);
-    f2gs<true>(v + 6, t + 10, v + 6);          // c1' = 3 xi C1 + 2 c1
-    f2gs<false>(v + 4, t + 8, v + 4);          // c4' = 3 C0 - 2 c4
+  // v <- v^2 for v in the cyclotomic subgroup (Granger-Scott, see f12_cyc_sqr), in place, two fused
+  // routines working in registers (the first version made 28 calls of F_q^2 routines per squaring and
+  // ran at 0.3 of the multiplier peak: 5.5 instructions per product).  Coefficient j lives at
+  // v + 2 f12_pos(j): c0 -> 0, c1 -> 6, c2 -> 2, c3 -> 8, c4 -> 4, c5 -> 10.
+  //   A = (c0 + c3 s)^2:  c0' = 3 A0 - 2 c0,  c3' = 3 A1 + 2 c3
+  static __device__ __noinline__ void cyc_pair_a(int v) {
+    Fq a0, a1, b0, b1, r00, r01, r10, r11;
+    ld(a0, v); ld(a1, v + 1); ld(b0, v + 8); ld(b1, v + 9);
+    f4r_sqr(r00, r01, r10, r11, a0, a1, b0, b1);
+    gs_combine<false>(a0, r00); gs_combine<false>(a1, r01);
+    gs_combine<true>(b0, r10); gs_combine<true>(b1, r11);
+    st(v, a0); st(v + 1, a1); st(v + 8, b0); st(v + 9, b1);
+  }
+  //   B = (c1 + c4 s)^2, C = (c2 + c5 s)^2:  c2' = 3 B0 - 2 c2, c5' = 3 B1 + 2 c5, c1' = 3 xi C1 + 2 c1, c4' = 3 C0 - 2 c4
+  static __device__ __noinline__ void cyc_pair_bc(int v) {
+    Fq c10, c11, c40, c41, c20, c21, c50, c51;
+    Fq B00, B01, B10, B11, C00, C01, C10, C11;
+    ld(c10, v + 6); ld(c11, v + 7); ld(c40, v + 4); ld(c41, v + 5);
+    f4r_sqr(B00, B01, B10, B11, c10, c11, c40, c41);
+    ld(c20, v + 2); ld(c21, v + 3); ld(c50, v + 10); ld(c51, v + 11);
+    f4r_sqr(C00, C01, C10, C11, c20, c21, c50, c51);
+    gs_combine<false>(c20, B00); gs_combine<false>(c21, B01);
+    gs_combine<true>(c50, B10); gs_combine<true>(c51, B11);
+    f2r_mul_xi(C10, C11);
+    gs_combine<true>(c10, C10); gs_combine<true>(c11, C11);
+    gs_combine<false>(c40, C00); gs_combine<false>(c41, C01);
+    st(v + 2, c20); st(v + 3, c21); st(v + 10, c50); st(v + 11, c51);
+    st(v + 6, c10); st(v + 7, c11); st(v + 4, c40); st(v + 5, c41);
+  }
+  static __device__ __forceinline__ void f12cycsqr(int v, int, int) {
+    cyc_pair_a(v);
+    cyc_pair_bc(v);
   }
   // v <- v^(q^k), k = 1, 2, 3 (f12_frob)
   static __device__ __noinline__ void f12frob(int v, int k) {
@@ -425,11 +433,10 @@ k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint3
     f2_mul(&Qy, &Qy, f2_const(c_f.ky));
     fq_st_global(gq, 0, n, idx, Qx.a); fq_st_global(gq, 1, n, idx, Qx.b);
     fq_st_global(gq, 2, n, idx, Qy.a); fq_st_global(gq, 3, n, idx, Qy.b);
-    fq_st_global(gq, 4, n, idx, xP); fq_st_global(gq, 5, n, idx, yP);
-    S::st(fsX, xP); S::st(fsY, yP);
+    fq_st_global(gq, fgPx, n, idx, xP); fq_st_global(gq, fgPy, n, idx, yP);
     Fq one, zero;
     fq_one(one); fq_zero(zero);
-    S::st(fsZ, one);
+    S::st(fsX, xP); S::st(fsY, yP); S::st(fsZ, one);
     S::st(fsV, one);
 #pragma unroll 1
     for (int s = 1; s < 12; s++) S::st(fsV + s, zero);

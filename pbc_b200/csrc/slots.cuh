@@ -67,45 +67,55 @@ struct Ops {
     fp_sqr<N, FULL>(x, x);
     st(d, x);
   }
-  // d = (a + a2) * (b + b2)   (SUBB: (a + a2) * (b - b2)): the cross term of a Karatsuba product or
-  // the real part of a square in F_q[i], without a slot for either sum
-  template <bool SUBB>
-  static __device__ __noinline__ void mul2(int d, int a, int a2, int b, int b2) {
+  // ---- ONE multiplier routine for the kernels that need operand variants (k_a_miller9) ----
+  // d = x * y with  x = a [+ a2],  y = b [+ b2 | - b2]  or  y = the element at g (limb-major global
+  // array, vectors n apart: a value used once or twice per loop iteration lives in L2 instead of a
+  // slot).  All branches are warp-uniform.  One copy of the 528-product body instead of one per
+  // variant: with 12 warps per SM the four separate copies (mul, mul2<+>, mul2<->, mulg: 3 200
+  // instructions, 51 KB) made instruction fetch the second largest stall (ncu, round 2).
+  static constexpr uint32_t MX_ADD_A = 1u, MX_ADD_B = 2u, MX_SUB_B = 4u, MX_GLOBAL_B = 8u;
+  static __device__ __noinline__ void mulx(int d, int a, int b, uint32_t mode, int a2, int b2, const void* g, size_t n) {
     uint32_t x[N], y[N];
-    {
+    if (mode & MX_GLOBAL_B) {
+      if constexpr (kVecWords == 4) {
+        const uint4* p = reinterpret_cast<const uint4*>(g);
+#pragma unroll
+        for (int v = 0; v < kVecs; v++) {
+          uint4 q = p[v * n];
+          y[4 * v] = q.x; y[4 * v + 1] = q.y; y[4 * v + 2] = q.z; y[4 * v + 3] = q.w;
+        }
+      } else {
+        const uint2* p = reinterpret_cast<const uint2*>(g);
+#pragma unroll
+        for (int v = 0; v < kVecs; v++) {
+          uint2 q = p[v * n];
+          y[2 * v] = q.x; y[2 * v + 1] = q.y;
+        }
+      }
+    } else {
+      ld(y, b);
+    }
+    if (mode & (MX_ADD_B | MX_SUB_B)) {
+      ld(x, b2);
+      if (mode & MX_ADD_B) fp_add<N, FULL>(y, y, x); else fp_sub<N>(y, y, x);
+    }
+    ld(x, a);
+    if (mode & MX_ADD_A) {
       uint32_t z[N];
-      ld(y, b); ld(z, b2);
-      if (SUBB) fp_sub<N>(y, y, z); else fp_add<N, FULL>(y, y, z);
-      ld(x, a); ld(z, a2);
+      ld(z, a2);
       fp_add<N, FULL>(x, x, z);
     }
     fp_mul<N, FULL>(x, x, y);
     st(d, x);
   }
-  // d = a * g, the second operand read from a limb-major global array (g already points at this
-  // thread's first vector; consecutive vectors are n apart): a value used once or twice per loop
-  // iteration lives in L2 instead of a shared-memory slot.  The global loads are issued first.
-  static __device__ __noinline__ void mulg(int d, int a, const void* g, size_t n) {
-    uint32_t x[N], y[N];
-    if constexpr (kVecWords == 4) {
-      const uint4* b = reinterpret_cast<const uint4*>(g);
-#pragma unroll
-      for (int v = 0; v < kVecs; v++) {
-        uint4 q = b[v * n];
-        y[4 * v] = q.x; y[4 * v + 1] = q.y; y[4 * v + 2] = q.z; y[4 * v + 3] = q.w;
-      }
-    } else {
-      const uint2* b = reinterpret_cast<const uint2*>(g);
-#pragma unroll
-      for (int v = 0; v < kVecs; v++) {
-        uint2 q = b[v * n];
-        y[2 * v] = q.x; y[2 * v + 1] = q.y;
-      }
-    }
-    ld(x, a);
-    fp_mul<N, FULL>(x, x, y);
-    st(d, x);
+  template <bool SUBB>
+  static __device__ __forceinline__ void mul2(int d, int a, int a2, int b, int b2) {
+    mulx(d, a, b, MX_ADD_A | (SUBB ? MX_SUB_B : MX_ADD_B), a2, b2, nullptr, 0);
   }
+  static __device__ __forceinline__ void mulg(int d, int a, const void* g, size_t n) {
+    mulx(d, a, 0, MX_GLOBAL_B, 0, 0, g, n);
+  }
+  static __device__ __forceinline__ void mulp(int d, int a, int b) { mulx(d, a, b, 0, 0, 0, nullptr, 0); }
   // d = a*b - c
   static __device__ __noinline__ void mulsub(int d, int a, int b, int c) {
     uint32_t x[N], y[N];

@@ -7,6 +7,7 @@
 //   mul_os  mont_mul<N,FULL>(a, b)        mul_ps  mont_mul_ps<N,FULL>(a, b)     sqr_ps  mont_sqr_ps<N,FULL>(a)
 //   add sub neg halve                      fp_add / fp_sub / fp_neg / fp_halve
 //   fq_mul  fq_redc_call(fq_mulw_call(a, b))                       (N = kNS only)
+//   fq_mul_os / fq_mac_os  the same through the inline operand-scanning product fqw_mul and fqw_redc2
 //   fq_mac  fq_redc2_call(a b + c d)  fq_msb  fq_redc2_call(a b + (q R - c d))... see the test
 #include HOST_FP_HEADER
 
@@ -70,8 +71,11 @@ int main() {
         Fq A, B, C, D;
         from_hex(a, A.v, kNS); from_hex(b, B.v, kNS); from_hex(c, C.v, kNS); from_hex(d, D.v, kNS);
         Fq R;
+        if (op == "fq_wmul") { FqW t; fqw_mul(t, A, B); std::cout << to_hex(t.v, 2 * kNS) << "\n"; continue; }
         if (op == "fq_mul") R = fq_redc_call(fq_mulw_call(A, B));
         else if (op == "fq_mac") { FqW s, t = fq_mulw_call(A, B), u = fq_mulw_call(C, D); fqw_add(s, t, u); R = fq_redc2_call(s); }
+        else if (op == "fq_mul_os") { FqW t; fqw_mul(t, A, B); fqw_redc2(R, t); }
+        else if (op == "fq_mac_os") { FqW s, t, u; fqw_mul(t, A, B); fqw_mul(u, C, D); fqw_add(s, t, u); fqw_redc2(R, s); }
         else if (op == "fq_mulcall") R = fq_mul_call(A, B);
         else if (op == "fq_sqrcall") R = fq_sqr_call(A);
         else { std::cout << "?" << "\n"; continue; }

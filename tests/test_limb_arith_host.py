@@ -105,11 +105,33 @@ def test_lazy_double_width_reduction(harness):
         Rinv = pow(R, -1, p)
         for a, b in _operands(p, 5, rnd, 40):
             c, d = rnd.randrange(p), rnd.randrange(p)
-            reqs += [(N, 0, "fq_mul", p, a, b, 0, 0), (N, 0, "fq_mulcall", p, a, b, 0, 0), (N, 0, "fq_sqrcall", p, a, 0, 0, 0)]
-            want += [a * b * Rinv % p, a * b * Rinv % p, a * a * Rinv % p]
+            reqs += [(N, 0, "fq_mul", p, a, b, 0, 0), (N, 0, "fq_mulcall", p, a, b, 0, 0), (N, 0, "fq_sqrcall", p, a, 0, 0, 0),
+                     (N, 0, "fq_mul_os", p, a, b, 0, 0)]
+            want += [a * b * Rinv % p, a * b * Rinv % p, a * a * Rinv % p, a * b * Rinv % p]
             if a * b + c * d < 2 * p * R:                # fq_redc2_call's contract
-                reqs.append((N, 0, "fq_mac", p, a, b, c, d))
-                want.append((a * b + c * d) * Rinv % p)
+                reqs += [(N, 0, "fq_mac", p, a, b, c, d), (N, 0, "fq_mac_os", p, a, b, c, d)]
+                want += [(a * b + c * d) * Rinv % p] * 2
+        # the operand-scanning product on unreduced operands (sums of two residues, below 2^160) and on
+        # all-ones limbs: every carry path of the even / odd accumulators
+        ones = (1 << 160) - 1
+        for a, b in [(ones, ones), (ones, 1), (ones - (1 << 32), ones), ((1 << 159) + 1, ones), (2 * p - 2, 2 * p - 1)]:
+            if a * b < 2 * p * R:
+                reqs.append((N, 0, "fq_mul_os", p, a, b, 0, 0))
+                want.append(a * b * Rinv % p)
     got = _run(harness, reqs)
     bad = [(r[2], hex(r[3])) for r, g, w in zip(reqs, got, want) if g != w]
+    assert not bad, bad[:5]
+
+
+def test_operand_scanning_wide_product_is_exact(harness):
+    """fqw_mul (fq_small.cuh): the 320-bit product on the even / odd accumulators against Python's a * b,
+    on the operands that drive every carry path: all-ones limbs, single set bits, alternating limbs"""
+    rnd = random.Random(23)
+    ones = (1 << 160) - 1
+    edge = [0, 1, ones, ones - 1, 1 << 159, (1 << 159) - 1, int("ffffffff00000000" * 3, 16) & ones,
+            int("00000000ffffffff" * 3, 16) & ones, 0xffffffff, 0xffffffff << 128, (1 << 32), (1 << 64) - 1]
+    pairs = [(a, b) for a in edge for b in edge] + [(rnd.getrandbits(160), rnd.getrandbits(160)) for _ in range(300)]
+    p = (1 << 158) | 0x1234567 | 1                      # unused by fqw_mul, the harness wants one
+    got = _run(harness, [(5, 0, "fq_wmul", p, a, b, 0, 0) for a, b in pairs])
+    bad = [(hex(a), hex(b)) for (a, b), g in zip(pairs, got) if g != a * b]
     assert not bad, bad[:5]
