@@ -478,7 +478,8 @@ def run_config(G, wname, args, Ph, Qh, n, idx, cpu_out, cpu, steps, warmup, per_
     g1, g2, gt = WIRE[w["param"]]
     unit_name = "pairings/s" if single else "outputs/s"
     world, dev, st = G.world, G.dev, G.st
-    pr = Pairing(PARAMS[w["param"]])
+    # PBC_B200_PARAM_EXTRA: extra "b200_*" test switches for A/B runs (e.g. "b200_prod_share 4"); never set by the driver
+    pr = Pairing(PARAMS[w["param"]] + "\n" + os.environ.get("PBC_B200_PARAM_EXTRA", "") + "\n")
     Pp = torch.from_numpy(Ph.copy()).pin_memory()
     Qp = torch.from_numpy(Qh.copy()).pin_memory()
     Op = torch.empty(n * gt, dtype=torch.uint8).pin_memory()

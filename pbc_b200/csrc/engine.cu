@@ -37,6 +37,13 @@ __global__ void k_fqmul_chain(uint32_t* __restrict__ out, const uint32_t* __rest
 }
 using namespace pbcb200;
 
+// type a, element_prod_pairing: pairs of one product handled by one thread with a shared Miller
+// accumulator (k_a_miller9_shared); 1 = one thread per pair (k_a_miller9).  Overridable per handle with the
+// parameter key "b200_prod_share".
+#ifndef PBC_A_PROD_SHARE
+#define PBC_A_PROD_SHARE 2
+#endif
+
 // ------------------------------------------------------------------------------------------
 // errors (misc/utils.c:79-101 pbc_error -> here a thread-local message)
 // ------------------------------------------------------------------------------------------
@@ -93,6 +100,7 @@ static std::map<std::string, std::string> parse_param_text(const char* s, size_t
 struct DevCtx {
   int dev = -1;
   bool ready = false;
+  int sms = 148;               // multiprocessors of this device
   cudaStream_t stream[2] = {nullptr, nullptr};
   // host-API staging, per stream
   uint8_t* d_in1[2] = {nullptr, nullptr};
@@ -140,6 +148,8 @@ struct pbc_b200_pairing_s {
   bool profile = false;        // record CUDA events between the kernels of the device-API path
   bool force_reference_basis = false;   // test switches, from "b200_*" keys of the parameter text
   bool force_generic_final_exp = false;
+  int prod_share = PBC_A_PROD_SHARE;   // type a products: pairs per thread sharing one Miller accumulator ("b200_prod_share")
+  bool prod_share_forced = false;      // set through the parameter key: use it whatever the batch size (tests, A/B runs)
   std::vector<DevCtx> ctx;     // indexed by device ordinal
   std::map<std::string, std::vector<BigUInt>> derived;   // canonical values of the derived constants (tests)
   std::mutex mu;
@@ -147,6 +157,7 @@ struct pbc_b200_pairing_s {
 };
 
 static std::atomic<uint64_t> g_next_id{1};
+
 static std::mutex g_const_mu;
 static std::map<int, uint64_t> g_const_owner;   // device -> handle id whose constants are resident
 // The curve constants live in __constant__ memory, one set per device at a time.  Blocking (host
@@ -190,7 +201,8 @@ static size_t ws_bytes(const pbc_b200_pairing_s* p, const Job& job, size_t n_out
     const size_t fq = 64;
     // f [2], dprod, prefix, save [5] (V1, f1), qm [2] (Montgomery-form Q of the nine-slot Miller kernel)
     if (job.mode == kSingle) return n_out * (2 + 1 + 1 + 5 + 2) * fq;
-    if (job.mode == kProd) return n_out * job.k * (2 + 1 + 5 + 2) * fq + n_out * (2 + 1 + 1) * fq;
+    // products: + vj [3] per pair (V of the pairs that share an accumulator, k_a_miller9_shared)
+    if (job.mode == kProd) return n_out * job.k * (2 + 1 + 5 + 2 + 3) * fq + n_out * (2 + 1 + 1) * fq;
     return n_out * (2 + 1 + 1) * fq + (size_t)(3 * (p->a.exp2 + 1) * kNA + 4) * 4;
   }
   // types f, d: Miller values [W][n] words + one flag word each; products add the reduced arrays
@@ -793,10 +805,12 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
   CUDA_OK(cudaSetDevice(dev));
   if (!c.ready) {
     c.dev = dev;
+    CUDA_OK(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
     for (int s = 0; s < 2; s++) CUDA_OK(cudaStreamCreateWithFlags(&c.stream[s], cudaStreamNonBlocking));
     if (p->type == 'a') {
       CUDA_OK(allow_smem(k_a_miller<kBlockMiller>, kSmemAMiller));
       CUDA_OK(allow_smem(k_a_miller9<kBlockMiller>, kSmemAMiller9));
+      CUDA_OK(allow_smem(k_a_miller9_shared<kBlockMiller>, kSmemAMiller9));
       CUDA_OK(allow_smem(k_a_finalexp<kBlockFinal>, kSmemAFinal));
       CUDA_OK(allow_smem(k_batch_invert<kNA, true, kBlockInv>, kSmemInv16));
       CUDA_OK(allow_smem(k_fpmul_slots<kNA, true, 128, 0>, 2 * 64 * 128));
@@ -972,15 +986,35 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
       uint4* di = fi + 8 * m;                    // [4][m]
       uint4* save = di + 4 * m;                  // [5][4][m]
       uint4* qm = save + 20 * m;                 // [2][4][m]
-      f = qm + 8 * m;                            // [2][4][n]
+      uint4* vj = qm + 8 * m;                    // [3][4][m]
+      f = vj + 12 * m;                           // [2][4][n]
       dprod = f + 8 * n;
       prefix = dprod + 4 * n;
-      unsigned gm = (unsigned)((m + kBlockMiller - 1) / kBlockMiller);
-      if (PBC_A_SLOTS9) k_a_miller9<kBlockMiller><<<gm, kBlockMiller, kSmemAMiller9, st>>>(d_in1, d_in2, fi, di, save, qm, m);
-      else k_a_miller<kBlockMiller><<<gm, kBlockMiller, kSmemAMiller, st>>>(d_in1, d_in2, fi, di, save, m);
+      // pairs per thread sharing one accumulator: the largest divisor of k not above the handle's setting
+      // that still leaves four waves of threads (sharing divides the thread count; measured on 2^16
+      // outputs of 16 pairs, profiles/r2_prod_share.jsonl: M = 2 +3.6 %, M = 4 +2.8 %, M = 8 -16 %)
+      size_t share = 1;
+      if (PBC_A_SLOTS9) {
+        int dev_now = 0;
+        cudaGetDevice(&dev_now);
+        const size_t wave = (size_t)((int)p->ctx.size() > dev_now ? p->ctx[dev_now].sms : 148) * 3 * kBlockMiller;
+        for (size_t c = (size_t)p->prod_share; c > 1; c--)
+          if (job.k % c == 0 && (m / c >= 4 * wave || p->prod_share_forced)) { share = c; break; }
+      }
+      size_t kk = job.k, mm = m;                 // pairs per output / Miller values that reach k_a_prod
+      if (share > 1) {
+        mm = m / share;
+        kk = job.k / share;
+        unsigned gs = (unsigned)((mm + kBlockMiller - 1) / kBlockMiller);
+        k_a_miller9_shared<kBlockMiller><<<gs, kBlockMiller, kSmemAMiller9, st>>>(d_in1, d_in2, fi, di, save, qm, vj, mm, share);
+      } else {
+        unsigned gm = (unsigned)((m + kBlockMiller - 1) / kBlockMiller);
+        if (PBC_A_SLOTS9) k_a_miller9<kBlockMiller><<<gm, kBlockMiller, kSmemAMiller9, st>>>(d_in1, d_in2, fi, di, save, qm, m);
+        else k_a_miller<kBlockMiller><<<gm, kBlockMiller, kSmemAMiller, st>>>(d_in1, d_in2, fi, di, save, m);
+      }
       LAUNCHED();
       unsigned gp = (unsigned)((n + kBlockProd - 1) / kBlockProd);
-      k_a_prod<kBlockProd><<<gp, kBlockProd, kSmemAProd, st>>>(fi, di, f, dprod, job.k, n, m);
+      k_a_prod<kBlockProd><<<gp, kBlockProd, kSmemAProd, st>>>(fi, di, f, dprod, kk, n, mm);
       LAUNCHED();
     } else {
       f = (uint4*)ws;
@@ -1183,6 +1217,10 @@ int pbc_b200_pairing_init_set_buf(pbc_b200_pairing_t** out, const char* param, s
   // test switches (ignored by the reference parser, which only looks up the keys it needs)
   p->force_reference_basis = tab.count("b200_reference_basis") && tab["b200_reference_basis"] != "0";
   p->force_generic_final_exp = tab.count("b200_generic_final_exp") && tab["b200_generic_final_exp"] != "0";
+  if (tab.count("b200_prod_share")) {
+    int m = atoi(tab["b200_prod_share"].c_str());
+    if (m >= 1 && m <= 64) { p->prod_share = m; p->prod_share_forced = true; }
+  }
   if (it->second == "a") rc = init_type_a(p, tab);
   else if (it->second == "a1") rc = init_type_a1(p, tab);
   else if (it->second == "f") rc = init_type_f(p, tab);

@@ -267,12 +267,10 @@ enum A9Slot { nX, nY, nZ, nF0, nF1, nT0, nT1, nT2, nT3, kA9Slots };
 #define PBC_A_LOCKSTEP 1
 #endif
 
-// qx, qy: this thread's Q coordinates in the global array (Montgomery form), vectors n apart
+// qx, qy: this thread's Q coordinates in the global array (Montgomery form), vectors n apart.
+// a_step_9_line: on entry g = (nT0, nF1) and the f0 slot is free; on exit f' = g l in (nF0, nF1), V doubled.
 template <class O>
-__device__ __forceinline__ void a_double_step_9(const uint4* qx, const uint4* qy, size_t n) {
-  O::template mul2<true>(nT0, nF0, nF1, nF0, nF1);   // g0                     (f0 slot is free from here)
-  O::mulp(nF1, nF0, nF1);
-  O::dbl(nF1, nF1);                                  // g1
+__device__ __forceinline__ void a_step_9_line(const uint4* qx, const uint4* qy, size_t n) {
   O::sqr(nT1, nX);                                   // A
   O::sqr(nT2, nY);                                   // B
   O::sqr(nT3, nZ);                                   // C
@@ -282,7 +280,7 @@ __device__ __forceinline__ void a_double_step_9(const uint4* qx, const uint4* qy
   O::add(nT1, nT1, nF0);                             // U = 3A + C
   O::mulp(nT1, nT1, nZ);
   O::mulg(nT1, nT1, qx, n);                          // U Z Qx
-  O::mulp(nX, nX, nF0);                               // X T
+  O::mulp(nX, nX, nF0);                              // X T
   O::add(nT1, nT1, nX);                              // Re l                   (X slot is free)
   O::sqr(nX, nF0);                                   // X' = T^2
   O::sqr(nT3, nT3);
@@ -292,18 +290,30 @@ __device__ __forceinline__ void a_double_step_9(const uint4* qx, const uint4* qy
   O::sqr(nF0, nF0);
   O::sub(nF0, nF0, nT2);
   O::sub(nF0, nF0, nX);                              // F = (T + Y)^2 - B - X'
-  O::mulp(nT3, nT3, nF0);                             // Y' (kept in T3 until Y has had its last use)
+  O::mulp(nT3, nT3, nF0);                            // Y' (kept in T3 until Y has had its last use)
   O::mulp(nF0, nY, nZ);
   O::dbl(nF0, nF0);
   O::mulg(nF0, nF0, qy, n);                          // Im l = 2 Y Z Qy
   O::dbl(nZ, nT2, 2);                                // Z' = 4 B
   O::template mul2<false>(nT2, nT0, nF1, nT1, nF0);  // (g0 + g1)(Re l + Im l)
-  O::mulp(nT0, nT0, nT1);                             // g0 Re l
-  O::mulp(nF1, nF1, nF0);                             // g1 Im l
+  O::mulp(nT0, nT0, nT1);                            // g0 Re l
+  O::mulp(nF1, nF1, nF0);                            // g1 Im l
   O::sub(nF0, nT0, nF1);                             // f0'
   O::sub(nT2, nT2, nT0);
   O::sub(nF1, nT2, nF1);                             // f1'
   O::copy(nY, nT3);
+}
+// g = f^2 into (nT0, nF1): g0 = (f0 + f1)(f0 - f1), g1 = 2 f0 f1   (the f0 slot is free afterwards)
+template <class O>
+__device__ __forceinline__ void a_step_9_square() {
+  O::template mul2<true>(nT0, nF0, nF1, nF0, nF1);
+  O::mulp(nF1, nF0, nF1);
+  O::dbl(nF1, nF1);
+}
+template <class O>
+__device__ __forceinline__ void a_double_step_9(const uint4* qx, const uint4* qy, size_t n) {
+  a_step_9_square<O>();
+  a_step_9_line<O>(qx, qy, n);
 }
 
 // f *= (l0 + i l1) with two temporaries (t0, t1); l0, l1 are preserved
@@ -316,6 +326,36 @@ __device__ __forceinline__ void a_fmul_2t(int f0, int f1, int l0, int l1, int t0
   O::sub(t0, t0, f0);
   O::sub(f1, t0, f1);
   O::copy(f0, t1);
+}
+
+// f *= the chord through V = (nX, nY, nZ) and the saved V1 = (X1, Y1, Z1) of pair `idx`, evaluated at
+// phi(Q); V is consumed.  Weight-(1,2) coordinates, scaled by Z^2 Z1^2 (compute_abc_line :114-130).
+template <class O>
+__device__ __forceinline__ void a_chord_9(const uint4* save, const uint4* qx, const uint4* qy, size_t n, size_t idx) {
+  //   a = Y Z1^2 - Y1 Z^2,  b = Z Z1 (X1 Z - X Z1),  c = X Z Y1 - Y X1 Z1
+  O::ld_global(nT0, save, 2, n, idx);          // Z1
+  O::ld_global(nT1, save, 0, n, idx);          // X1
+  O::mulp(nT2, nT1, nZ);                         // X1 Z
+  O::mulp(nT3, nX, nT0);                         // X Z1
+  O::sub(nT2, nT2, nT3);
+  O::mulp(nT2, nT2, nZ);
+  O::mulp(nT2, nT2, nT0);                        // b
+  O::mulp(nT3, nX, nZ);                          // X Z               (last use of X)
+  O::ld_global(nX, save, 1, n, idx);           // Y1
+  O::mulp(nT3, nT3, nX);                         // X Z Y1
+  O::mulp(nT1, nT1, nT0);                        // X1 Z1
+  O::mulp(nT1, nT1, nY);                         // Y X1 Z1
+  O::sub(nT3, nT3, nT1);                        // c
+  O::sqr(nT0, nT0);                             // Z1^2
+  O::mulp(nT0, nT0, nY);                         // Y Z1^2
+  O::sqr(nT1, nZ);                              // Z^2
+  O::mulp(nT1, nT1, nX);                         // Y1 Z^2
+  O::sub(nT0, nT0, nT1);                        // a
+  O::mulg(nT0, nT0, qx, n);
+  O::sub(nT3, nT3, nT0);                        // Re l = c - a Qx
+  O::mulg(nT2, nT2, qy, n);                     // Im l = b Qy
+  a_fmul_2t<O>(nF0, nF1, nT3, nT2, nT0, nT1);
+
 }
 
 // f, dprod, save as for k_a_miller; qm: [2][4][n] uint4 scratch (Montgomery-form Q)
@@ -370,31 +410,7 @@ k_a_miller9(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4*
   O::ld_global(nT2, save, 3, n, idx);
   O::ld_global(nT3, save, 4, n, idx);
   a_fmul_2t<O>(nF0, nF1, nT2, nT3, nT0, nT1);
-  // chord through V = (X, Y, Z) and V1 = (X1, Y1, Z1) in weight-(1,2) coordinates, scaled by
-  // Z^2 Z1^2 (compute_abc_line :114-130):
-  //   a = Y Z1^2 - Y1 Z^2,  b = Z Z1 (X1 Z - X Z1),  c = X Z Y1 - Y X1 Z1
-  O::ld_global(nT0, save, 2, n, idx);          // Z1
-  O::ld_global(nT1, save, 0, n, idx);          // X1
-  O::mulp(nT2, nT1, nZ);                         // X1 Z
-  O::mulp(nT3, nX, nT0);                         // X Z1
-  O::sub(nT2, nT2, nT3);
-  O::mulp(nT2, nT2, nZ);
-  O::mulp(nT2, nT2, nT0);                        // b
-  O::mulp(nT3, nX, nZ);                          // X Z               (last use of X)
-  O::ld_global(nX, save, 1, n, idx);           // Y1
-  O::mulp(nT3, nT3, nX);                         // X Z Y1
-  O::mulp(nT1, nT1, nT0);                        // X1 Z1
-  O::mulp(nT1, nT1, nY);                         // Y X1 Z1
-  O::sub(nT3, nT3, nT1);                        // c
-  O::sqr(nT0, nT0);                             // Z1^2
-  O::mulp(nT0, nT0, nY);                         // Y Z1^2
-  O::sqr(nT1, nZ);                              // Z^2
-  O::mulp(nT1, nT1, nX);                         // Y1 Z^2
-  O::sub(nT0, nT0, nT1);                        // a
-  O::mulg(nT0, nT0, qx, n);
-  O::sub(nT3, nT3, nT0);                        // Re l = c - a Qx
-  O::mulg(nT2, nT2, qy, n);                     // Im l = b Qy
-  a_fmul_2t<O>(nF0, nF1, nT3, nT2, nT0, nT1);
+  a_chord_9<O>(save, qx, qy, n, idx);
 
   // D = (f0^2 + f1^2) f0 f1;  invalid inputs publish D = 0 (-> identity)
   O::sqr(nT0, nF0);
@@ -406,6 +422,106 @@ k_a_miller9(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4*
   O::st_global(f, 0, n, idx, nF0);
   O::st_global(f, 1, n, idx, nF1);
   O::st_global(dprod, 0, n, idx, nT0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared Miller accumulator (a_pairings_affine, ecc/a_param.c:1283-1383: ONE f for the n pairs of a
+// product, f <- f^2 once per step, then f <- f l_j for every pair).  One thread owns M consecutive pairs
+// of one product: per step it squares f once and runs the line / doubling part of the nine-slot step
+// for each pair in turn, the pair's V = (X, Y, Z) parked in a limb-major global array between its turns.
+// 2 + 15 M multiplications per step instead of 17 M.  The thread count drops by M, so M stays small
+// (the host picks it; M = 1 is k_a_miller9): with 2^16 outputs of 16 pairs a wave of 56 832 threads is
+// already 5 % of the batch at M = 1.
+//   f, dprod: [..][n_thr] (one partial Miller value per thread);  save, qm, vj: per pair, n_pairs = n_thr M
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_a_miller9_shared(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint4* __restrict__ f,
+                   uint4* __restrict__ dprod, uint4* __restrict__ save, uint4* __restrict__ qm,
+                   uint4* __restrict__ vj, size_t n_thr, size_t M) {
+  using O = Ops<kNA, true, BLOCK>;
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+#if PBC_A_LOCKSTEP
+  const bool live = idx < n_thr;
+  if (!live) idx = 0;
+#else
+  if (idx >= n_thr) return;
+  const bool live = true;
+#endif
+  const size_t np = n_thr * M, p0 = idx * M;
+  bool valid = true;
+  for (size_t j = 0; j < M; j++) {
+    const size_t pr = p0 + j;
+    bool okP = a_load_point<O>(nX, nY, nT0, nT1, P + pr * (2 * kWA));
+    bool okQ = a_load_point<O>(nT2, nT3, nT0, nT1, Q + pr * (2 * kWA));
+    valid = valid && okP && okQ;
+    O::set_const(nZ, c_fp.one);
+    if (live) {
+      O::st_global(qm, 0, np, pr, nT2);
+      O::st_global(qm, 1, np, pr, nT3);
+      O::st_global(vj, 0, np, pr, nX);
+      O::st_global(vj, 1, np, pr, nY);
+      O::st_global(vj, 2, np, pr, nZ);
+    }
+  }
+  O::set_const(nF0, c_fp.one);
+  uint32_t zero[kNA] = {0};
+  O::st(nF1, zero);
+
+  const int exp1 = c_a.exp1, exp2 = c_a.exp2;
+  for (int i = 0; i < exp2; i++) {
+#if PBC_A_LOCKSTEP
+    __syncthreads();
+#endif
+    if (i == exp1 && live) {
+      // f1 = f or conj(f) ~ 1/f, once per thread (kept with the thread's first pair)
+      if (c_a.sign1 < 0) O::neg(nT1, nF1); else O::copy(nT1, nF1);
+      O::st_global(save, 3, np, p0, nF0);
+      O::st_global(save, 4, np, p0, nT1);
+    }
+    a_step_9_square<O>();
+    for (size_t j = 0; j < M; j++) {
+      const size_t pr = p0 + j;
+      if (j) O::copy(nT0, nF0);               // the running product where the step expects g0
+      O::ld_global(nX, vj, 0, np, pr);
+      O::ld_global(nY, vj, 1, np, pr);
+      O::ld_global(nZ, vj, 2, np, pr);
+      if (i == exp1 && live) {
+        // V1 = +-V of this pair   (ecc/a_param.c:1162-1169)
+        if (c_a.sign1 < 0) O::neg(nF0, nY); else O::copy(nF0, nY);
+        O::st_global(save, 0, np, pr, nX);
+        O::st_global(save, 1, np, pr, nF0);
+        O::st_global(save, 2, np, pr, nZ);
+      }
+      a_step_9_line<O>(qm + pr, qm + 4 * np + pr, np);
+      if (live) {
+        O::st_global(vj, 0, np, pr, nX);
+        O::st_global(vj, 1, np, pr, nY);
+        O::st_global(vj, 2, np, pr, nZ);
+      }
+    }
+  }
+  if (!live) return;
+
+  O::ld_global(nT2, save, 3, np, p0);
+  O::ld_global(nT3, save, 4, np, p0);
+  a_fmul_2t<O>(nF0, nF1, nT2, nT3, nT0, nT1);          // f *= f1
+  for (size_t j = 0; j < M; j++) {
+    const size_t pr = p0 + j;
+    O::ld_global(nX, vj, 0, np, pr);
+    O::ld_global(nY, vj, 1, np, pr);
+    O::ld_global(nZ, vj, 2, np, pr);
+    a_chord_9<O>(save, qm + pr, qm + 4 * np + pr, np, pr);
+  }
+  O::sqr(nT0, nF0);
+  O::sqr(nT1, nF1);
+  O::add(nT0, nT0, nT1);
+  O::mulp(nT1, nF0, nF1);
+  O::mulp(nT0, nT0, nT1);
+  if (!valid) O::st(nT0, zero);
+  O::st_global(f, 0, n_thr, idx, nF0);
+  O::st_global(f, 1, n_thr, idx, nF1);
+  O::st_global(dprod, 0, n_thr, idx, nT0);
 }
 
 // ---------------------------------------------------------------------------------------------

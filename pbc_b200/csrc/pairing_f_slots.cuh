@@ -29,6 +29,12 @@ namespace pbcb200 {
 // A 29-slot version (V = (X, Y, Z) and xi L3, xi L4 parked in the global scratch: three blocks = 12 warps
 // per SM, registers capped at 168) was measured 36 % SLOWER (profiles/r2_variants_f29.jsonl): the cap
 // spills inside the product routines.  These kernels want registers more than they want warps.
+// PBC_FS_LOCKSTEP = 1: block-wide barrier at the top of every Miller iteration and of every step of the
+// powers by u, so that the warps of a block fetch the same routines (ncu, round 2: k_f_finalexp_s spent 0.94
+// warp-cycles per issue waiting for instructions).  Every thread of a block then has to run the loops.
+#ifndef PBC_FS_LOCKSTEP
+#define PBC_FS_LOCKSTEP 1
+#endif
 constexpr int kFSlots = 36;
 enum FSlotMap {
   fsV = 0,                             // 12: Miller value (coefficient j at 2 * f12_pos(j))
@@ -372,7 +378,8 @@ struct FS {
 #pragma unroll 1
     for (int s = 0; s < 12; s++) qldg(d + s, g, s, n, false);
   }
-  static __device__ __noinline__ void f12stg(uint32_t* g, size_t n, int a) {
+  static __device__ __noinline__ void f12stg(uint32_t* g, size_t n, int a, bool live = true) {
+    if (!live) return;                       // padding threads share index 0 with a real thread: they never write
 #pragma unroll 1
     for (int s = 0; s < 12; s++) {
       Fq x;
@@ -385,6 +392,7 @@ struct FS {
   static __device__ __noinline__ void f12powu(int r0, int r1, int t, int e) {
     f12copy(r0, r1);
     for (int j = (int)c_f.u_bits - 2; j >= 0; j--) {
+      if (PBC_FS_LOCKSTEP) __syncthreads();
       f12cycsqr(r0, t, e);
       if ((c_f.u_abs[j >> 5] >> (j & 31)) & 1u) f12mul(r0, r1, t);
     }
@@ -401,7 +409,9 @@ k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint3
              const uint32_t* __restrict__ tab, size_t rows) {
   using S = FS<BLOCK>;
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (idx >= n) return;                    // no block-wide barrier in this kernel
+  const bool live = idx < n;               // padding threads of the last block run too (block-wide barriers below)
+  if (!PBC_FS_LOCKSTEP && !live) return;
+  if (!live) idx = 0;
   bool ok;
   {
     // decode, validate, move to the basis in use (as k_f_miller)
@@ -450,6 +460,7 @@ k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint3
   int m = (int)c_cc.rbits - 2;
 #endif
   for (;;) {
+    if (PBC_FS_LOCKSTEP) __syncthreads();
     if (tab) {
       // ---- fixed first argument: (a, b, c) of the next line from the table ----
       S::qldc(T + 4, tab + (3 * row + 0) * kNS); S::f2scale_g(fsL4, g, 0, n, T + 4);
@@ -527,6 +538,7 @@ k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint3
     m--;
     S::f12sqr(V, T);
   }
+  if (!live) return;
   // publish (flagged-off inputs: the identity)
   Fq x;
 #pragma unroll 1
@@ -557,7 +569,9 @@ k_f_finalexp_s(uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag, uin
   using S = FS<BLOCK>;
   enum { R0 = 0, R1 = 12, T = 24, E = 36 };
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (idx >= n) return;
+  const bool live = idx < n;               // padding threads run the powers by u too (block-wide barriers inside)
+  if (!PBC_FS_LOCKSTEP && !live) return;
+  if (!live) idx = 0;
   const bool ok = flag[idx] != 0;
   uint32_t* g0 = mv + idx;                                     // f
   uint32_t* g1 = stash + idx;                                  // f^u
@@ -573,15 +587,15 @@ k_f_finalexp_s(uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag, uin
     f12_mul(&x, &x, &y);                 // f^(q^6 - 1)
     f12_frob(y, x, 2);
     f12_mul(&f, &y, &x);                 // ^(q^2 + 1)
-    f12_st_global(mv, n, idx, f);
+    if (live) f12_st_global(mv, n, idx, f);
 #pragma unroll 1
     for (int i = 0; i < 6; i++) { S::st(R1 + 2 * i, f.c[i].a); S::st(R1 + 2 * i + 1, f.c[i].b); }
   }
   S::f12powu(R0, R1, T, E);              // f^u
-  S::f12stg(g1, n, R0);
+  S::f12stg(g1, n, R0, live);
   S::f12copy(R1, R0);
   S::f12powu(R0, R1, T, E);              // f^(u^2)
-  S::f12stg(g2, n, R0);
+  S::f12stg(g2, n, R0, live);
   S::f12copy(R1, R0);
   S::f12powu(R0, R1, T, E);              // f^(u^3)
   // t0 = y6^2, y6 = 1 / (f^(u^3) f^(u^3 q))
@@ -590,7 +604,7 @@ k_f_finalexp_s(uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag, uin
   S::f12mul(R1, R0, T);
   S::f12conj(R1);
   S::f12cycsqr(R1, T, E);
-  S::f12stg(g3, n, R1);                  // park t0
+  S::f12stg(g3, n, R1, live);                  // park t0
   // y4 = 1 / (f^u f^(u^2 q))
   S::f12ldg(R0, g2, n);
   S::f12frob(R0, 1);
@@ -603,7 +617,7 @@ k_f_finalexp_s(uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag, uin
   S::f12ldg(R0, g2, n);
   S::f12conj(R0);
   S::f12mul(R1, R0, T);                  // t0 *= y5
-  S::f12stg(g3, n, R1);                  // park t0
+  S::f12stg(g3, n, R1, live);                  // park t0
   // t1 = y3 y5 t0, y3 = 1 / f^(u q)
   S::f12ldg(R1, g1, n);
   S::f12frob(R1, 1);
@@ -612,7 +626,7 @@ k_f_finalexp_s(uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag, uin
   S::f12ldg(R0, g3, n);
   S::f12mul(R1, R0, T);                  // R0 = t0, R1 = t1
   // t0 *= y2, y2 = f^(u^2 q^2)
-  S::f12stg(g4, n, R1);                  // park t1
+  S::f12stg(g4, n, R1, live);                  // park t1
   S::f12ldg(R1, g2, n);
   S::f12frob(R1, 2);
   S::f12mul(R0, R1, T);
@@ -624,8 +638,8 @@ k_f_finalexp_s(uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag, uin
   S::f12ldg(R0, g0, n);
   S::f12conj(R0);
   S::f12mul(R0, R1, T);
-  S::f12stg(g3, n, R0);                  // park t0
-  S::f12stg(g4, n, R1);                  // park t1
+  S::f12stg(g3, n, R0, live);                  // park t0
+  S::f12stg(g4, n, R1, live);                  // park t1
   // y0 = f^q f^(q^2) f^(q^3)
   S::f12ldg(R0, g0, n);
   S::f12frob(R0, 1);
@@ -640,6 +654,7 @@ k_f_finalexp_s(uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag, uin
   S::f12ldg(R0, g3, n);
   S::f12cycsqr(R0, T, E);
   S::f12mul(R0, R1, T);                  // result
+  if (!live) return;
   {
     F12 acc;
 #pragma unroll 1

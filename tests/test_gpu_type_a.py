@@ -176,6 +176,36 @@ def test_prod_any_infinite_input_gives_identity(dev, golden):
     assert got[128:256] == bytes.fromhex(g["prod"]["e"][1])
 
 
+@pytest.mark.parametrize("share", [2, 4, 3, 16])
+def test_prod_with_a_shared_miller_accumulator(golden, orc, share):
+    """a_pairings_affine shares one accumulator between the pairs of a product (ecc/a_param.c:1296-1306);
+    k_a_miller9_shared does so for `share` pairs per thread ("b200_prod_share" sets it; the largest divisor of
+    k not above it is used): the reference fixtures (k = 4), an O somewhere, and k = 12 / k = 16 products of the
+    fixture pairs against the oracle"""
+    from pbc_b200.pairing import Pairing
+    dev = Pairing(PARAMS["a"] + "\nb200_prod_share %d\n" % share)
+    g = golden["a"]
+    k, n_out = g["prod"]["k"], len(g["prod"]["e"])
+    assert dev.prod_apply(_cat(g["prod"]["P"]), _cat(g["prod"]["Q"]), k, n_out) == _cat(g["prod"]["e"])
+    P, Q = [bytes.fromhex(x) for x in g["prod"]["P"]], [bytes.fromhex(x) for x in g["prod"]["Q"]]
+    P[k + 2] = bytes.fromhex(g["offcurve"]["badP"])          # poisons output 1 only
+    got = dev.prod_apply(b"".join(P), b"".join(Q), k, n_out)
+    assert got[128:256] == bytes.fromhex(g["offcurve"]["identity"]) and got[:128] == bytes.fromhex(g["prod"]["e"][0])
+    pairs = g["pairing"]
+    for kk in (12, 16):
+        from pbc_b200 import _lib
+        n2 = 3 if _lib.IS_SIMULATOR else 130                 # on the GPU: more than one thread block at share = 1
+        idx = [(i * 7 + j * 5) % len(pairs["e"]) for i in range(n2) for j in range(kk)]
+        Pb = b"".join(bytes.fromhex(pairs["P"][t]) for t in idx)
+        Qb = b"".join(bytes.fromhex(pairs["Q"][t]) for t in idx)
+        got = dev.prod_apply(Pb, Qb, kk, n2)
+        for i in sorted({0, 1, min(64, n2 - 1), n2 - 1}):
+            acc = orc.GT.one
+            for t in idx[i * kk:(i + 1) * kk]:
+                acc = orc.GT.mul(acc, orc.GT.from_bytes(bytes.fromhex(pairs["e"][t])))
+            assert got[i * 128:(i + 1) * 128] == orc.GT.to_bytes(acc), (kk, i)
+
+
 def test_prod_k1_equals_single_and_empty(dev, golden):
     g = golden["a"]["pairing"]
     assert dev.prod_apply(_cat(g["P"]), _cat(g["Q"]), 1, len(g["e"])) == _cat(g["e"])

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2 measurement pass: tests, default bench, pp comparison, launch list + ncu captures of the two slot kernels
+# round 2 measurement pass: tests, default bench, pp comparison, launch lists (ncu --set full captures: tools/gpu_ncu.sh)
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2_pytest_gpu.log
 ( time timeout 900 python bench.py --steps ${STEPS:-8} --warmup 3 > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err ) 2>&1 | grep real
@@ -15,10 +15,10 @@ show('a', d)
 for k,v in d['configs'].items(): show(k, v)
 PY
 timeout 600 python tools/gpu_pp_compare.py a f d g 131072 > gpurun_out/r2_pp_compare.jsonl 2> gpurun_out/r2_pp_compare.err; cat gpurun_out/r2_pp_compare.jsonl; tail -2 gpurun_out/r2_pp_compare.err
+for w in pp g a1; do timeout 600 python bench.py --steps 5 --warmup 3 --workload $w --configs none > gpurun_out/r2_bench_$w.json 2> gpurun_out/r2_bench_$w.err; echo "bench $w rc=$?"; python -c "
+import json; d=json.loads([l for l in open('gpurun_out/r2_bench_$w.json') if l.startswith('{')][-1]); print('$w', round(d['value']), 'e2e', round(d['e2e']['value']), 'frac', round(d['roofline']['frac'],3), d['parity'] and (d['parity']['checked'], d['parity']['bit_exact']), {k: round(v,2) for k,v in d['stage_ms'].items()})"; done
 if [ -z "$SKIP_NCU" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_ncu_launches_a.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --configs none --n 262144 > gpurun_out/ncu_launches_a.out 2>&1; echo "ncu list a rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_ncu_launches_f.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --workload f --configs none --n 262144 > gpurun_out/ncu_launches_f.out 2>&1; echo "ncu list f rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_a_miller9 -s 1 -c 1 -o gpurun_out/r2_prof_a_miller9 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --configs none --n 227328 > gpurun_out/ncu_full_a.out 2>&1; echo "ncu full a rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_f_miller_s -s 1 -c 1 -o gpurun_out/r2_prof_f_miller_s python bench.py --steps 1 --warmup 3 --no-cpu-baseline --workload f --configs none --n 151552 > gpurun_out/ncu_full_f.out 2>&1; echo "ncu full f rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_f_finalexp_s -s 1 -c 1 -o gpurun_out/r2_prof_f_finalexp_s python bench.py --steps 1 --warmup 3 --no-cpu-baseline --workload f --configs none --n 151552 > gpurun_out/ncu_full_ff.out 2>&1; echo "ncu full ff rc=$?"
+KERNELS="k_a_miller9:a:227328 k_f_miller_s:f:151552 k_f_finalexp_s:f:151552" bash tools/gpu_ncu.sh
 fi
