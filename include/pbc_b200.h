@@ -104,7 +104,8 @@ int pbc_b200_pp_pairings_apply_device(pbc_b200_pairing_t *p, void *d_out, const 
  * kept in device memory by the handle, and reused by every apply until clear -- what pairing_pp_t
  * is for.  Types a and a1 keep the table of line coefficients (160 / about 1 500 rows; an apply then
  * costs 7 instead of 17-19 multiplications per step); types f, d and g keep the decoded point.
- * The handle lives on the device that was current at init; apply switches to it. */
+ * The handle lives on the device that was current at init; apply switches to it.  As in the reference
+ * (a pairing_pp_t points into its pairing_t), clear the pp handle before the pairing it belongs to. */
 typedef struct pbc_b200_pp_s pbc_b200_pp_t;
 int pbc_b200_pp_init(pbc_b200_pairing_t *p, pbc_b200_pp_t **pp, const unsigned char *in1);
 int pbc_b200_pp_apply(pbc_b200_pp_t *pp, unsigned char *out, const unsigned char *in2, size_t n);

@@ -133,6 +133,7 @@ struct pbc_b200_pairing_s {
   A1Naf a1naf;
 #endif
   size_t a1_rows = 0;          // rows of the fixed-argument line table (3 per tangent / chord)
+  size_t cc_rows = 0;          // types f, d, g: lines of the Miller walk (computed once at init)
   CCConsts cc;
 #if PBC_CC_NAF
   CCNaf ccnaf;
@@ -217,7 +218,7 @@ static size_t ws_bytes(const pbc_b200_pairing_s* p, const Job& job, size_t n_out
 }
 // lines of the Miller walk of types f, d, g: one tangent per loop position, one chord per non-zero digit
 // strictly between the top digit and digit 0 (miller_cc_walk)
-static size_t cc_table_rows(const pbc_b200_pairing_s* p) {
+static size_t cc_table_rows_compute(const pbc_b200_pairing_s* p) {
   BigUInt r;
   for (int i = kNS; i-- > 0;) r = r.shl(32) + BigUInt((uint64_t)p->cc.r[i]);
 #if PBC_CC_NAF
@@ -230,6 +231,7 @@ static size_t cc_table_rows(const pbc_b200_pairing_s* p) {
 #endif
   return rows;
 }
+static size_t cc_table_rows(const pbc_b200_pairing_s* p) { return p->cc_rows; }
 static size_t cc_table_bytes(const pbc_b200_pairing_s* p) { return (cc_table_rows(p) * 3 * kNS + 4) * 4; }
 
 static size_t in1_elems(const Job& job, size_t n_out) {
@@ -1228,6 +1230,7 @@ int pbc_b200_pairing_init_set_buf(pbc_b200_pairing_t** out, const char* param, s
   else if (it->second == "g") rc = init_type_g(p, tab);
   else rc = fail("pairing type `%s' is not on the B200 hot path (supported: a, a1, d with k = 6, f, g)", it->second.c_str());
   if (rc) { delete p; return 1; }
+  if (p->type == 'f' || p->type == 'd' || p->type == 'g') p->cc_rows = cc_table_rows_compute(p);
   *out = p;
   return 0;
 }

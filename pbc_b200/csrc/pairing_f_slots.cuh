@@ -138,6 +138,43 @@ struct FS {
     mont_sqr_ps<kNS, false>(x.v, x.v);
     st(d, x);
   }
+  // two / three independent products in ONE call, every operand read before any result is stored (so the
+  // results may overwrite operands of the other products).  A lone F_q product is one serial carry chain;
+  // the point arithmetic of a Miller step has them in independent pairs and triples, and two warps per
+  // scheduler do not hide a chain's latency (ncu: the F_q routines took 17 % of the samples for 11 % of
+  // the instructions).
+  static __device__ __noinline__ void qmul2(int d0, int a0, int b0, int d1, int a1, int b1) {
+    Fq x0, y0, x1, y1;
+    ld(x0, a0); ld(y0, b0); ld(x1, a1); ld(y1, b1);
+    mont_mul_ps<kNS, false>(x0.v, x0.v, y0.v);
+    mont_mul_ps<kNS, false>(x1.v, x1.v, y1.v);
+    st(d0, x0); st(d1, x1);
+  }
+  static __device__ __noinline__ void qmul3(int d0, int a0, int b0, int d1, int a1, int b1, int d2, int a2, int b2) {
+    Fq x0, y0, x1, y1, x2, y2;
+    ld(x0, a0); ld(y0, b0); ld(x1, a1); ld(y1, b1); ld(x2, a2); ld(y2, b2);
+    mont_mul_ps<kNS, false>(x0.v, x0.v, y0.v);
+    mont_mul_ps<kNS, false>(x1.v, x1.v, y1.v);
+    mont_mul_ps<kNS, false>(x2.v, x2.v, y2.v);
+    st(d0, x0); st(d1, x1); st(d2, x2);
+  }
+  static __device__ __noinline__ void qsqr3(int d0, int a0, int d1, int a1, int d2, int a2) {
+    Fq x0, x1, x2;
+    ld(x0, a0); ld(x1, a1); ld(x2, a2);
+    mont_sqr_ps<kNS, false>(x0.v, x0.v);
+    mont_sqr_ps<kNS, false>(x1.v, x1.v);
+    mont_sqr_ps<kNS, false>(x2.v, x2.v);
+    st(d0, x0); st(d1, x1); st(d2, x2);
+  }
+  // d0 = a0 b0, d1 = a1^2, d2 = a2^2
+  static __device__ __noinline__ void qmul1sqr2(int d0, int a0, int b0, int d1, int a1, int d2, int a2) {
+    Fq x0, y0, x1, x2;
+    ld(x0, a0); ld(y0, b0); ld(x1, a1); ld(x2, a2);
+    mont_mul_ps<kNS, false>(x0.v, x0.v, y0.v);
+    mont_sqr_ps<kNS, false>(x1.v, x1.v);
+    mont_sqr_ps<kNS, false>(x2.v, x2.v);
+    st(d0, x0); st(d1, x1); st(d2, x2);
+  }
   static __device__ __noinline__ void qadd(int d, int a, int b) { Fq x, y; ld(x, a); ld(y, b); fq_add(x, x, y); st(d, x); }
   static __device__ __noinline__ void qsub(int d, int a, int b) { Fq x, y; ld(x, a); ld(y, b); fq_sub(x, x, y); st(d, x); }
   static __device__ __noinline__ void qdbl(int d, int a, int k = 1) {
@@ -470,22 +507,23 @@ k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint3
       row++;
     } else {
     // ---- tangent at V (a = -M Z^2, b = 2 Y Z^3, c = M X - 2 Y^2; the curve has A = 0), V <- 2V ----
-    S::qsqr(T, fsZ);                                   // Z^2
-    S::qsqr(T + 5, fsX);
-    S::qdbl(T + 1, T + 5); S::qadd(T + 1, T + 1, T + 5);   // M = 3 X^2
-    S::qsqr(T + 2, fsY);                               // Y^2
-    S::qmul(T + 4, T + 1, T); S::qneg(T + 4, T + 4);   // a
-    S::f2scale_g(fsL4, g, 0, n, T + 4);                // L4 = Qx a
-    S::qmul(T + 3, fsY, fsZ); S::qdbl(T + 3, T + 3);   // Z' = 2 Y Z
-    S::qmul(T + 4, T + 3, T);                          // b = Z' Z^2
-    S::f2scale_g(fsL3, g, 2, n, T + 4);                // L3 = Qy b
-    S::qmul(fsC, T + 1, fsX); S::qsub(fsC, fsC, T + 2); S::qsub(fsC, fsC, T + 2);   // c
+    // (independent products grouped: 13 of them in five calls)
+    S::qsqr3(T, fsZ, T + 5, fsX, T + 2, fsY);                            // Z^2, X^2, Y^2
+    S::qdbl(T + 1, T + 5); S::qadd(T + 1, T + 1, T + 5);                // M = 3 X^2
+    S::qmul2(T + 4, T + 1, T, T + 3, fsY, fsZ);                          // M Z^2, Y Z
+    S::qneg(T + 4, T + 4);                                              // a
+    S::f2scale_g(fsL4, g, 0, n, T + 4);                                 // L4 = Qx a
+    S::qdbl(T + 3, T + 3);                                              // Z' = 2 Y Z
+    S::qmul2(T + 4, T + 3, T, fsC, T + 1, fsX);                         // b = Z' Z^2, M X
+    S::f2scale_g(fsL3, g, 2, n, T + 4);                                 // L3 = Qy b
+    S::qsub(fsC, fsC, T + 2); S::qsub(fsC, fsC, T + 2);                 // c = M X - 2 Y^2
     S::f2mulxi(fsXL3, fsL3); S::f2mulxi(fsXL4, fsL4);
     if (m != 0) {
-      S::qmul(T + 5, fsX, T + 2); S::qdbl(T + 5, T + 5, 2);   // S = 4 X Y^2
       S::qcopy(fsZ, T + 3);
-      S::qsqr(fsX, T + 1); S::qsub(fsX, fsX, T + 5); S::qsub(fsX, fsX, T + 5);   // X' = M^2 - 2 S
-      S::qsqr(T + 2, T + 2); S::qdbl(T + 2, T + 2, 3);   // 8 Y^4
+      S::qmul1sqr2(T + 5, fsX, T + 2, fsX, T + 1, T + 2, T + 2);         // X Y^2, M^2, Y^4
+      S::qdbl(T + 5, T + 5, 2);                                         // S = 4 X Y^2
+      S::qsub(fsX, fsX, T + 5); S::qsub(fsX, fsX, T + 5);               // X' = M^2 - 2 S
+      S::qdbl(T + 2, T + 2, 3);                                         // 8 Y^4
       S::qsub(T + 5, T + 5, fsX); S::qmul(fsY, T + 1, T + 5); S::qsub(fsY, fsY, T + 2);   // Y'
     }
     }
@@ -508,29 +546,26 @@ k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint3
       } else {
       (void)minus;
       // ---- chord through V and +-P (a = Y - yS Z^3, b = (xP Z^2 - X) Z, c = yS Z X - xP Y), V <- V +- P ----
+      // (14 products in six calls of independent pairs / triples)
       S::qldg(T + 6, g, 4, n, false);                    // xP
       S::qldg(T + 7, g, 5, n, minus);                    // yS
-      S::qsqr(T, fsZ);                                   // Z^2
-      S::qmul(T + 1, T, fsZ);                            // Z^3
-      S::qmul(T + 2, T + 6, T); S::qsub(T + 2, T + 2, fsX);   // H
-      S::qmul(T + 3, T + 7, T + 1);                      // yS Z^3
-      S::qsub(T + 4, fsY, T + 3);                        // a
-      S::f2scale_g(fsL4, g, 0, n, T + 4);
-      S::qsub(T + 3, T + 3, fsY);                        // R
-      S::qmul(T + 4, T + 2, fsZ);                        // b = H Z
+      S::qmul3(T, fsZ, fsZ, T + 8, T + 7, fsZ, T + 9, T + 6, fsY);       // Z^2, yS Z, xP Y
+      S::qmul2(T + 1, T, fsZ, T + 2, T + 6, T);                          // Z^3, xP Z^2
+      S::qsub(T + 2, T + 2, fsX);                                        // H = xP Z^2 - X
+      S::qmul3(T + 3, T + 7, T + 1, T + 4, T + 2, fsZ, T + 8, T + 8, fsX);   // yS Z^3, b = H Z, yS Z X
+      S::qsub(T + 5, fsY, T + 3);                                        // a = Y - yS Z^3
+      S::f2scale_g(fsL4, g, 0, n, T + 5);
+      S::qsub(T + 3, T + 3, fsY);                                        // R = yS Z^3 - Y
       S::f2scale_g(fsL3, g, 2, n, T + 4);
-      S::qmul(T + 1, T + 7, fsZ); S::qmul(T + 1, T + 1, fsX);   // yS Z X
-      S::qmul(T, T + 6, fsY);                            // xP Y
-      S::qsub(fsC, T + 1, T);                            // c
+      S::qsub(fsC, T + 8, T + 9);                                        // c
       S::f2mulxi(fsXL3, fsL3); S::f2mulxi(fsXL4, fsL4);
-      S::qcopy(fsZ, T + 4);                              // Z of the sum
-      S::qsqr(T, T + 2);                                 // H^2
-      S::qmul(T + 1, T, T + 2);                          // H^3
-      S::qmul(T, T, fsX);                                // X H^2
-      S::qsqr(fsX, T + 3); S::qsub(fsX, fsX, T + 1); S::qsub(fsX, fsX, T); S::qsub(fsX, fsX, T);   // X3
-      S::qsub(T, T, fsX); S::qmul(T, T, T + 3);
-      S::qmul(T + 1, T + 1, fsY);
-      S::qsub(fsY, T, T + 1);                            // Y3
+      S::qcopy(fsZ, T + 4);                                              // Z of the sum
+      S::qmul2(T, T + 2, T + 2, T + 10, T + 3, T + 3);                   // H^2, R^2
+      S::qmul2(T + 1, T, T + 2, T, T, fsX);                              // H^3, X H^2
+      S::qsub(fsX, T + 10, T + 1); S::qsub(fsX, fsX, T); S::qsub(fsX, fsX, T);   // X3 = R^2 - H^3 - 2 X H^2
+      S::qsub(T, T, fsX);
+      S::qmul2(T, T, T + 3, T + 1, T + 1, fsY);                          // R (X H^2 - X3), H^3 Y
+      S::qsub(fsY, T, T + 1);                                            // Y3
       }
       S::line_mul(T, V);
       { int s = V; V = T; T = s; }

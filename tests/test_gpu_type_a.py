@@ -141,6 +141,40 @@ def test_device_pointer_entry(dev, golden):
     assert bytes(out.cpu().numpy().tobytes()) == _cat(g["e"])
 
 
+def test_device_pointer_calls_on_two_streams_share_the_workspace_in_order(dev, golden):
+    """the _device entry points of one handle use one workspace per device; the library orders its users
+    with an event, so back-to-back calls on DIFFERENT streams (pairings, then a product, then a G1 power
+    and a pp handle) must each give the reference bytes -- unordered they would overwrite each other's
+    Miller values"""
+    import torch
+    g = golden["a"]
+    reps = 600                                              # long enough for the calls to overlap if they could
+    n = len(g["pairing"]["e"])
+    P = torch.frombuffer(bytearray(_cat(g["pairing"]["P"]) * reps), dtype=torch.uint8).cuda()
+    Q = torch.frombuffer(bytearray(_cat(g["pairing"]["Q"]) * reps), dtype=torch.uint8).cuda()
+    k, n_out = g["prod"]["k"], len(g["prod"]["e"])
+    PP = torch.frombuffer(bytearray(_cat(g["prod"]["P"]) * reps), dtype=torch.uint8).cuda()
+    QQ = torch.frombuffer(bytearray(_cat(g["prod"]["Q"]) * reps), dtype=torch.uint8).cuda()
+    o1 = torch.empty(n * reps * 128, dtype=torch.uint8, device="cuda")
+    o2 = torch.empty(n_out * reps * 128, dtype=torch.uint8, device="cuda")
+    o3 = torch.empty(n * reps * 128, dtype=torch.uint8, device="cuda")
+    o4 = torch.empty(n * reps * 128, dtype=torch.uint8, device="cuda")
+    s1, s2, s3 = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    h = dev.pp_init(bytes.fromhex(g["pairing"]["P"][0]))
+    dev.apply_device(o1.data_ptr(), P.data_ptr(), Q.data_ptr(), n * reps, s1.cuda_stream)
+    dev.prod_apply_device(o2.data_ptr(), PP.data_ptr(), QQ.data_ptr(), k, n_out * reps, s2.cuda_stream)
+    dev.apply_device(o3.data_ptr(), P.data_ptr(), Q.data_ptr(), n * reps, s3.cuda_stream)
+    h.apply_device(o4.data_ptr(), Q.data_ptr(), n * reps, s1.cuda_stream)
+    torch.cuda.synchronize()
+    assert bytes(o1.cpu().numpy().tobytes()) == _cat(g["pairing"]["e"]) * reps
+    assert bytes(o2.cpu().numpy().tobytes()) == _cat(g["prod"]["e"]) * reps
+    assert bytes(o3.cpu().numpy().tobytes()) == _cat(g["pairing"]["e"]) * reps
+    want = dev.apply(bytes.fromhex(g["pairing"]["P"][0]) * n, _cat(g["pairing"]["Q"]), n)
+    assert bytes(o4.cpu().numpy().tobytes()) == want * reps
+    h.clear()
+
+
 # ---- element_prod_pairing (ecc/a_param.c:1283-1383) ----
 def test_prod_reference_fixtures(dev, golden):
     g = golden["a"]["prod"]
