@@ -253,6 +253,16 @@ static void fill_fp_consts(FpConsts* c, const BigUInt& q, int nlimbs) {
   (q - BigUInt(2)).to_words(c->pm2, nlimbs);
   c->np0 = neg_inv32(q.word(0));
   c->nlimbs = (uint32_t)nlimbs;
+  if (nlimbs == kNS) {
+    // -q^-1 mod 2^160 by Newton iteration x <- x (2 - q x): each step doubles the number of correct low bits
+    BigUInt R5 = BigUInt(1).shl(160), x(1), two(2);
+    for (int it = 0; it < 9; it++) {
+      BigUInt qx = (q * x) % R5;
+      BigUInt f = (two + R5 - qx) % R5;                 // 2 - q x mod 2^160
+      x = (x * f) % R5;
+    }
+    ((R5 - x) % R5).to_words(c->ninv, 5);
+  }
 }
 
 static bool get_big(const std::map<std::string, std::string>& tab, const char* key, BigUInt* out) {

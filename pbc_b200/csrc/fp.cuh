@@ -30,6 +30,7 @@ struct FpConsts {
   uint32_t np0;              // -p^-1 mod 2^32
   uint32_t nlimbs;
   uint32_t pad[2];
+  uint32_t ninv[8];          // -p^-1 mod 2^160 (five-limb fields: the two-product Montgomery reduction fqw_redc_split)
 };
 
 __constant__ FpConsts c_fp;   // single translation unit (engine.cu)

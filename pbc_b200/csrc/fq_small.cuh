@@ -287,6 +287,82 @@ __device__ __forceinline__ void fqw_redc2(Fq& r, const FqW& t) {
 #pragma unroll
   for (int k = 0; k < kNS; k++) r.v[k] = borrow == 0 ? d[k] : o[k];
 }
+// ---------------------------------------------------------------------------------------------
+// Montgomery reduction as two products (PBC_FQW_REDC_SPLIT): m = (t mod R) (-q^-1) mod R -- the low half of
+// a 5 x 5 product, 10 full and 5 low-word products on the even / odd accumulators -- then u = m q (fqw_mul)
+// and r = (t + u) / R = t_hi + u_hi + (t_lo != 0).  40 products instead of 30, but no serial chain through
+// the five quotient digits: the column-wise fqw_redc2 computes each digit from the column sum the
+// previous digits feed, which is what a warp waits for when only two warps share a scheduler.
+// t < 2 q R as for fqw_redc2.
+// ---------------------------------------------------------------------------------------------
+#ifndef PBC_FQW_REDC_SPLIT
+#define PBC_FQW_REDC_SPLIT 0
+#endif
+__device__ __forceinline__ void fq_mullo(uint32_t* m, const uint32_t* x, const uint32_t* y) {
+  uint32_t E[5], O[5];
+  // row 0
+  PBC_MULW_PAIR(E[0], E[1], x[0], y[0]);
+  PBC_MULW_PAIR(E[2], E[3], x[2], y[0]);
+  E[4] = x[4] * y[0];
+  PBC_MULW_PAIR(O[1], O[2], x[1], y[0]);
+  PBC_MULW_PAIR(O[3], O[4], x[3], y[0]);
+  // row 1: even columns 2, 4 (low word only); odd columns 1, 3
+  PBC_MADW_FIRST(E[2], E[3], x[1], y[1]);
+  PBC_ASM("madc.lo.u32 %0, %1, %2, %0;" : "+r"(E[4]) : "r"(x[3]), "r"(y[1]));
+  PBC_MADW_FIRST(O[1], O[2], x[0], y[1]);
+  PBC_ASM("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(O[3]), "+r"(O[4]) : "r"(x[2]), "r"(y[1]));
+  // row 2: even columns 2, 4; odd column 3
+  PBC_MADW_FIRST(E[2], E[3], x[0], y[2]);
+  PBC_ASM("madc.lo.u32 %0, %1, %2, %0;" : "+r"(E[4]) : "r"(x[2]), "r"(y[2]));
+  PBC_ASM("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(O[3]), "+r"(O[4]) : "r"(x[1]), "r"(y[2]));
+  // row 3: even column 4; odd column 3
+  E[4] += x[1] * y[3];
+  PBC_ASM("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(O[3]), "+r"(O[4]) : "r"(x[0]), "r"(y[3]));
+  // row 4: even column 4
+  E[4] += x[0] * y[4];
+  m[0] = E[0];
+  PBC_ASM("add.cc.u32 %0, %1, %2;" : "=r"(m[1]) : "r"(E[1]), "r"(O[1]));
+  PBC_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(m[2]) : "r"(E[2]), "r"(O[2]));
+  PBC_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(m[3]) : "r"(E[3]), "r"(O[3]));
+  PBC_ASM("addc.u32 %0, %1, %2;" : "=r"(m[4]) : "r"(E[4]), "r"(O[4]));
+}
+__device__ __forceinline__ void fqw_redc_split(Fq& r, const FqW& t) {
+  Fq m, q;
+  FqW u;
+  fq_mullo(m.v, t.v, c_fp.ninv);
+  fq_set(q, c_fp.p);
+  fqw_mul(u, m, q);
+  // t_lo + u_lo is 0 or R: the carry into the high halves is (t_lo != 0)
+  uint32_t nz = t.v[0] | t.v[1] | t.v[2] | t.v[3] | t.v[4];
+  uint32_t o[kNS], top;
+  PBC_ASM("add.cc.u32 %0, %1, 0xffffffff;" : "=r"(top) : "r"(nz));          // carry flag = (nz != 0)
+  PBC_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(o[0]) : "r"(t.v[5]), "r"(u.v[5]));
+  PBC_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(o[1]) : "r"(t.v[6]), "r"(u.v[6]));
+  PBC_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(o[2]) : "r"(t.v[7]), "r"(u.v[7]));
+  PBC_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(o[3]) : "r"(t.v[8]), "r"(u.v[8]));
+  PBC_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(o[4]) : "r"(t.v[9]), "r"(u.v[9]));
+  PBC_ASM("addc.u32 %0, 0, 0;" : "=r"(top));
+  // value = o + top 2^160 < 3 q: subtract q while it is >= q
+  uint32_t d[kNS], borrow;
+  PBC_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(d[0]) : "r"(o[0]), "r"(c_fp.p[0]));
+#pragma unroll
+  for (int k = 1; k < kNS; k++) PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(d[k]) : "r"(o[k]), "r"(c_fp.p[k]));
+  PBC_ASM("subc.u32 %0, 0, 0;" : "=r"(borrow));
+  bool use_d = top != 0 || borrow == 0;
+#pragma unroll
+  for (int k = 0; k < kNS; k++) o[k] = use_d ? d[k] : o[k];
+  PBC_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(d[0]) : "r"(o[0]), "r"(c_fp.p[0]));
+#pragma unroll
+  for (int k = 1; k < kNS; k++) PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(d[k]) : "r"(o[k]), "r"(c_fp.p[k]));
+  PBC_ASM("subc.u32 %0, 0, 0;" : "=r"(borrow));
+#pragma unroll
+  for (int k = 0; k < kNS; k++) r.v[k] = borrow == 0 ? d[k] : o[k];
+}
+// the reduction the slot-machine routines call
+__device__ __forceinline__ void fqw_reduce(Fq& r, const FqW& t) {
+  if (PBC_FQW_REDC_SPLIT) fqw_redc_split(r, t); else fqw_redc2(r, t);
+}
+
 // a + b without reduction (the caller knows the sum fits the limbs)
 __device__ __forceinline__ void fq_add_nr(Fq& r, const Fq& a, const Fq& b) {
   PBC_ASM("add.cc.u32 %0, %1, %2;" : "=r"(r.v[0]) : "r"(a.v[0]), "r"(b.v[0]));

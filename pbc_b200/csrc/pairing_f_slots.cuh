@@ -48,6 +48,12 @@ enum FGlobalMap { fgQx = 0, fgQy = 2, fgPx = 4, fgPy = 5 };
 constexpr int kFGWords = 6 * kNS;
 
 // ---- register-level pieces (fqw_mul, fqw_redc2: fq_small.cuh) ----
+// r = a b (Montgomery): interleaved column-wise product, or wide product + two-product reduction
+__device__ __forceinline__ void fq_mul_sel(Fq& r, const Fq& a, const Fq& b) {
+  if (PBC_FQW_REDC_SPLIT) { FqW t; fqw_mul(t, a, b); fqw_redc_split(r, t); }
+  else mont_mul_ps<kNS, false>(r.v, a.v, b.v);
+}
+
 // (re, im) += x y for F_q^2 operands in the internal basis (i^2 = -1), double width, unreduced:
 //   re += x0 y0 - x1 y1,  im += (x0 + x1)(y0 + y1) - x0 y0 - x1 y1.
 // The caller starts re at (number of terms) * q^2 so that it never goes negative.
@@ -84,8 +90,8 @@ __device__ __forceinline__ void f2r_sqr(Fq& o0, Fq& o1, const Fq& x0, const Fq& 
   Fq s, t;
   fq_add_nr(s, x0, x1);                    // below 2q < 2^160: fine as a multiplier operand
   fq_sub(t, x0, x1);
-  mont_mul_ps<kNS, false>(s.v, s.v, t.v);
-  mont_mul_ps<kNS, false>(t.v, x0.v, x1.v);
+  fq_mul_sel(s, s, t);
+  fq_mul_sel(t, x0, x1);
   fq_dbl(o1, t);
   o0 = s;
 }
@@ -129,7 +135,7 @@ struct FS {
   static __device__ __noinline__ void qmul(int d, int a, int b) {
     Fq x, y;
     ld(x, a); ld(y, b);
-    mont_mul_ps<kNS, false>(x.v, x.v, y.v);
+    fq_mul_sel(x, x, y);
     st(d, x);
   }
   static __device__ __noinline__ void qsqr(int d, int a) {
@@ -146,16 +152,16 @@ struct FS {
   static __device__ __noinline__ void qmul2(int d0, int a0, int b0, int d1, int a1, int b1) {
     Fq x0, y0, x1, y1;
     ld(x0, a0); ld(y0, b0); ld(x1, a1); ld(y1, b1);
-    mont_mul_ps<kNS, false>(x0.v, x0.v, y0.v);
-    mont_mul_ps<kNS, false>(x1.v, x1.v, y1.v);
+    fq_mul_sel(x0, x0, y0);
+    fq_mul_sel(x1, x1, y1);
     st(d0, x0); st(d1, x1);
   }
   static __device__ __noinline__ void qmul3(int d0, int a0, int b0, int d1, int a1, int b1, int d2, int a2, int b2) {
     Fq x0, y0, x1, y1, x2, y2;
     ld(x0, a0); ld(y0, b0); ld(x1, a1); ld(y1, b1); ld(x2, a2); ld(y2, b2);
-    mont_mul_ps<kNS, false>(x0.v, x0.v, y0.v);
-    mont_mul_ps<kNS, false>(x1.v, x1.v, y1.v);
-    mont_mul_ps<kNS, false>(x2.v, x2.v, y2.v);
+    fq_mul_sel(x0, x0, y0);
+    fq_mul_sel(x1, x1, y1);
+    fq_mul_sel(x2, x2, y2);
     st(d0, x0); st(d1, x1); st(d2, x2);
   }
   static __device__ __noinline__ void qsqr3(int d0, int a0, int d1, int a1, int d2, int a2) {
@@ -170,7 +176,7 @@ struct FS {
   static __device__ __noinline__ void qmul1sqr2(int d0, int a0, int b0, int d1, int a1, int d2, int a2) {
     Fq x0, y0, x1, x2;
     ld(x0, a0); ld(y0, b0); ld(x1, a1); ld(x2, a2);
-    mont_mul_ps<kNS, false>(x0.v, x0.v, y0.v);
+    fq_mul_sel(x0, x0, y0);
     mont_sqr_ps<kNS, false>(x1.v, x1.v);
     mont_sqr_ps<kNS, false>(x2.v, x2.v);
     st(d0, x0); st(d1, x1); st(d2, x2);
@@ -206,8 +212,8 @@ struct FS {
 #pragma unroll
     for (int k = 0; k < kNS; k++) { y0.v[k] = g[((size_t)e * kNS + k) * n]; y1.v[k] = g[((size_t)(e + 1) * kNS + k) * n]; }
     ld(x, a);
-    mont_mul_ps<kNS, false>(y0.v, y0.v, x.v);
-    mont_mul_ps<kNS, false>(y1.v, y1.v, x.v);
+    fq_mul_sel(y0, y0, x);
+    fq_mul_sel(y1, y1, x);
     st(d, y0); st(d + 1, y1);
   }
   // ---- F_q^2 (two consecutive slots) ----
@@ -239,8 +245,8 @@ struct FS {
     ld(x0, a); ld(x1, a + 1);
     fq_add_nr(s, x0, x1);                  // below 2q < 2^160: fine as a multiplier operand
     fq_sub(t, x0, x1);
-    mont_mul_ps<kNS, false>(s.v, s.v, t.v);
-    mont_mul_ps<kNS, false>(t.v, x0.v, x1.v);
+    fq_mul_sel(s, s, t);
+    fq_mul_sel(t, x0, x1);
     fq_dbl(t, t);
     st(d, s); st(d + 1, t);
   }
@@ -267,8 +273,8 @@ struct FS {
 #pragma unroll
     for (int w = 0; w < 2 * kNS; w++) { re.v[w] = c_f.qsqm[0][w]; im.v[w] = 0; }
     f2w_mac(re, im, x0, x1, y0, y1);
-    fqw_redc2(x0, re);
-    fqw_redc2(x1, im);
+    fqw_reduce(x0, re);
+    fqw_reduce(x1, im);
     st(d, x0); st(d + 1, x1);
   }
 
@@ -294,8 +300,8 @@ struct FS {
         f2w_mac(re, im, x0, x1, y0, y1);
       }
       Fq r0, r1;
-      fqw_redc2(r0, re);
-      fqw_redc2(r1, im);
+      fqw_reduce(r0, re);
+      fqw_reduce(r1, im);
       st(d + 2 * k, r0); st(d + 2 * k + 1, r1);
     }
   }
@@ -322,8 +328,8 @@ struct FS {
       fqw_add(re, re, t);
       fqw_mul(t, x0, y1);
       fqw_add(im, im, t);
-      fqw_redc2(x0, re);
-      fqw_redc2(x1, im);
+      fqw_reduce(x0, re);
+      fqw_reduce(x1, im);
       st(o + 2 * f12_pos(k), x0); st(o + 2 * f12_pos(k) + 1, x1);
     }
   }

@@ -135,3 +135,22 @@ def test_operand_scanning_wide_product_is_exact(harness):
     got = _run(harness, [(5, 0, "fq_wmul", p, a, b, 0, 0) for a, b in pairs])
     bad = [(hex(a), hex(b)) for (a, b), g in zip(pairs, got) if g != a * b]
     assert not bad, bad[:5]
+
+
+def test_two_product_montgomery_reduction(harness):
+    """fqw_redc_split (fq_small.cuh): m = t_lo (-q^-1) mod 2^160 on the truncated even / odd accumulators, u = m q,
+    r = t_hi + u_hi + (t_lo != 0): against Python integers, including products of unreduced operands (t up to 2 q R)
+    and t_lo = 0"""
+    rnd = random.Random(31)
+    N, R = 5, 1 << 160
+    reqs, want = [], []
+    for p in _moduli(5, 0, rnd):
+        Rinv, ninv = pow(R, -1, p), (-pow(p, -1, R)) % R
+        pairs = _operands(p, 5, rnd, 60) + [(2 * p - 1, p - 1), (R - 1, 1), (1 << 159, 2), (0, 5), (R >> 1, 2)]
+        for a, b in pairs:
+            if a * b < 2 * p * R:
+                reqs.append((N, 0, "fq_mul_split", p, a, b, 0, ninv))
+                want.append(a * b * Rinv % p)
+    got = _run(harness, reqs)
+    bad = [(hex(r[3]), hex(r[4]), hex(r[5])) for r, g, w in zip(reqs, got, want) if g != w]
+    assert len(got) == len(want) and not bad, bad[:5]
