@@ -60,7 +60,7 @@ WORKLOADS = {
               name="type F (param/f.param, BN k=12) element_pairing, batch 2^20 pairs per GPU, 158-bit F_q",
               dtype="u32 limbs (5 x 32-bit = 160-bit F_q, exact integer)", kernels=("k_f_miller_s", "-", "k_f_finalexp_s")),
     "d": dict(param="d159", mode="single", k=1, n=1 << 18, unit=78, ref_mulmods=23039, ref_main=None,
-              exec_unit_ops_main=None, exec_unit_ops_all=812590, cpu_rate=350.0, port_rate=10.0,
+              exec_unit_ops_main=None, exec_unit_ops_all=720295, cpu_rate=350.0, port_rate=10.0,
               name="type D (param/d159.param, MNT k=6) element_pairing, batch 2^18 pairs per GPU, 159-bit F_q",
               dtype="u32 limbs (5 x 32-bit = 160-bit F_q, exact integer)", kernels=("k_d_miller", "-", "k_d_finalexp")),
     "g": dict(param="g149", mode="single", k=1, n=1 << 18, unit=78, ref_mulmods=None, ref_main=None,
@@ -578,11 +578,20 @@ def run_config(G, wname, args, Ph, Qh, n, idx, cpu_out, cpu, steps, warmup, per_
         ach_ref = None
         if w.get("exec_unit_ops_main"):
             kern, kms = w["kernels"][0], stage[0]
-            ach_exec = n * w["exec_unit_ops_main"] / (kms * 1e-3)
+            exec_main = w["exec_unit_ops_main"]
+            if w["mode"] == "prod" and w["param"] == "a":
+                # the engine shares one Miller accumulator between M = 2 pairs of a product while four waves
+                # of threads remain (engine.cu, PBC_A_PROD_SHARE): per pair 159 x (10 M + 6 S) + 23.5 M + 7 S
+                # instead of 159 x (11 M + 6 S) + 26 M + 8 S
+                sms = torch.cuda.get_device_properties(G.local).multi_processor_count
+                if n * k // 2 >= 4 * sms * 384 and k % 2 == 0 and "b200_prod_share" not in os.environ.get("PBC_B200_PARAM_EXTRA", ""):
+                    exec_main = int(k * ((159 * 10 + 23.5) * 528 + (159 * 6 + 7) * 408))
+                    kern = "k_a_miller9_shared+k_a_prod"
+            ach_exec = n * exec_main / (kms * 1e-3)
             if w["ref_main"] is not None:
                 ach_ref = n * w["ref_main"] * unit / (kms * 1e-3)
             work = ("%d IMAD.WIDE.U32 executed per output in this kernel (counted from the slot programs; "
-                    "tests/test_kernels_on_cpu_sim.py ties it to the code)" % w["exec_unit_ops_main"])
+                    "tests/test_kernels_on_cpu_sim.py ties it to the code)" % exec_main)
         else:
             # types f, d, g: the 32x32 products of the whole kernel sequence, counted by the CPU simulator
             # of the library while it runs these kernels (tests/test_kernels_on_cpu_sim.py)

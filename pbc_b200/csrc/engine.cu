@@ -632,6 +632,8 @@ static int init_type_d(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   to_mont(c.twist_a, BigUInt::mulmod(a % q, v2, q), q, kNS);
   to_mont(c.twist_b, BigUInt::mulmod(b % q, BigUInt::mulmod(v2, v, q), q), q, kNS);
   to_mont(c.two, BigUInt(2), q, kNS);
+  (q * q).to_words(c.qsqm[0], 2 * kNS);
+  (q * q * BigUInt(2)).to_words(c.qsqm[1], 2 * kNS);
   HostF3Field Kref{q, {c0 % q, c1 % q, c2 % q}};
   HostF3 x;
   x.c[1] = one;

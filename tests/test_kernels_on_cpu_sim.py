@@ -109,6 +109,14 @@ for wl in ("a", "a1", "f", "d", "g"):
     c0 = lib.pbc_b200_sim_products()
     pr.apply(P, Q, 1)
     out[wl] = [lib.pbc_b200_sim_products() - c0, w["exec_unit_ops_main"] or w["exec_unit_ops_all"], bool(w["exec_unit_ops_main"])]
+# products of 4 pairings with two pairs per thread sharing one Miller accumulator (bench.py's prod16 figure)
+g = json.load(open("tests/golden/a.json"))["prod"]
+pr = Pairing(PARAMS["a"] + chr(10) + "b200_prod_share 2" + chr(10))
+P, Q = b"".join(bytes.fromhex(x) for x in g["P"][:4]), b"".join(bytes.fromhex(x) for x in g["Q"][:4])
+pr.prod_apply(P, Q, 4, 1)
+c0 = lib.pbc_b200_sim_products()
+pr.prod_apply(P, Q, 4, 1)
+out["prod_share2"] = [lib.pbc_b200_sim_products() - c0, int(4 * ((159 * 10 + 23.5) * 528 + (159 * 6 + 7) * 408)), True]
 print(json.dumps(out))
 """
     out = subprocess.run([sys.executable, "-c", code], env=_env(sim), capture_output=True, text=True, timeout=900, cwd=ROOT)
