@@ -56,7 +56,7 @@ WORKLOADS = {
               name="type A (param/a.param) element_pairing, batch 2^20 (P,Q) pairs per GPU, 512-bit F_q",
               dtype="u32 limbs (16 x 32-bit = 512-bit F_q, exact integer)", kernels=("k_a_miller9", "k_batch_invert", "k_a_finalexp")),
     "f": dict(param="f", mode="single", k=1, n=1 << 20, unit=78, ref_mulmods=98183, ref_main=None,
-              exec_unit_ops_main=None, exec_unit_ops_all=853625, cpu_rate=70.0, port_rate=3.0,
+              exec_unit_ops_main=None, exec_unit_ops_all=861455, cpu_rate=70.0, port_rate=3.0,
               name="type F (param/f.param, BN k=12) element_pairing, batch 2^20 pairs per GPU, 158-bit F_q",
               dtype="u32 limbs (5 x 32-bit = 160-bit F_q, exact integer)", kernels=("k_f_miller_s", "-", "k_f_finalexp_s")),
     "d": dict(param="d159", mode="single", k=1, n=1 << 18, unit=78, ref_mulmods=23039, ref_main=None,

@@ -542,7 +542,8 @@ static int init_type_f(pbc_b200_pairing_s* p, const std::map<std::string, std::s
   for (int k = 0; k < 3; k++) (q * q * BigUInt((uint64_t)(k + 1))).to_words(c.qsqm[k], 2 * kNS);
   // the slot-machine kernels accumulate up to three F_q^2 products (each below 2 q^2) before one
   // reduction of a value below 2 q R: needs 6 q^2 < 2 q 2^160
-  c.slots_ok = (c.nice && (q * BigUInt(3)).bits() <= 160) ? 1u : 0u;
+  // and keep three Karatsuba cross sums (each below 4 q^2) on ten words: 12 q^2 < 2^320
+  c.slots_ok = (c.nice && (q * BigUInt(3)).bits() <= 160 && (q * q * BigUInt(12)).bits() <= 320) ? 1u : 0u;
   to_mont(c.sigma, sigma, q, kNS);
   to_mont(c.sigma_inv, sigma_inv, q, kNS);
   for (int j = 1; j < 6; j++) { put2(c.tau[j - 1], taup[j]); put2(c.tau_inv[j - 1], tauinv[j]); }

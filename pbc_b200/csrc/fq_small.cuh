@@ -370,6 +370,186 @@ __device__ __forceinline__ void fq_add_nr(Fq& r, const Fq& a, const Fq& b) {
   for (int k = 1; k < kNS; k++) PBC_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(r.v[k]) : "r"(a.v[k]), "r"(b.v[k]));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Accumulating products (PBC_FQ_ACC): sums of several 5 x 5 products kept UNMERGED on the even / odd
+// accumulators and merged once.  ncu on the first slot kernels: IMAD.WIDE was 22 % of the instruction
+// stream and IADD3 31 % -- every product paid a ten-word merge of its two accumulators plus one or two
+// ten-word additions into the running sums of an F_q^2 product, and the warps (two per scheduler) spent
+// 1.7 cycles per issue waiting on those serial carry chains.  Here each of the three sums of an F_q^2
+// Karatsuba product (a0 b0, a1 b1, (a0 + a1)(b0 + b1)) lives on one FqAcc across all the terms of a
+// coefficient: a product adds 25 IMAD.WIDE and nine carry captures, the merge is paid once per sum.
+//   value = E + O + sum_p K[p] 2^(32 (5 + p));  O[0] stays zero.
+// Row i of a product (all a_j b_i) puts a_0, a_2, a_4 on the accumulator of i's parity (words i .. i+5) and
+// a_1, a_3 on the other (words i+1 .. i+4); the carry out of either run is counted in K at the word
+// above the run.  The total stays below 2^320 (callers' bounds), so nothing is carried out of word 9.
+// ---------------------------------------------------------------------------------------------
+#ifndef PBC_FQ_ACC
+#define PBC_FQ_ACC 1
+#endif
+struct FqAcc { uint32_t E[10], O[10], K[5]; };
+
+#define PBC_CARRY_ADD(w) PBC_ASM("addc.u32 %0, %0, 0;" : "+r"(w))
+
+// c = a b (the schedule of fqw_mul: every word of E and O is written, fresh words take the carries); K is
+// NOT written: the first fqa_mac after it sets K (SETK), a lone product is merged with fqa_merge<false>.
+__device__ __forceinline__ void fqa_mul(FqAcc& c, const Fq& a, const Fq& b) {
+  static_assert(kNS == 5, "the row schedule below is written out for five limbs");
+  uint32_t* E = c.E;
+  uint32_t* O = c.O;
+  const uint32_t* x = a.v;
+  const uint32_t* y = b.v;
+  PBC_MULW_PAIR(E[0], E[1], x[0], y[0]);
+  PBC_MULW_PAIR(E[2], E[3], x[2], y[0]);
+  PBC_MULW_PAIR(E[4], E[5], x[4], y[0]);
+  PBC_MULW_PAIR(O[1], O[2], x[1], y[0]);
+  PBC_MULW_PAIR(O[3], O[4], x[3], y[0]);
+  O[0] = 0; O[5] = 0; O[6] = 0;
+  PBC_MADW_FIRST(E[2], E[3], x[1], y[1]);
+  PBC_MADW_NEXT(E[4], E[5], x[3], y[1]);
+  PBC_CARRY_TO(E[6]);
+  PBC_MADW_FIRST(O[1], O[2], x[0], y[1]);
+  PBC_MADW_NEXT(O[3], O[4], x[2], y[1]);
+  PBC_MADW_NEXT(O[5], O[6], x[4], y[1]);
+  E[7] = 0;
+  PBC_MADW_FIRST(E[2], E[3], x[0], y[2]);
+  PBC_MADW_NEXT(E[4], E[5], x[2], y[2]);
+  PBC_MADW_NEXT(E[6], E[7], x[4], y[2]);
+  PBC_MADW_FIRST(O[3], O[4], x[1], y[2]);
+  PBC_MADW_NEXT(O[5], O[6], x[3], y[2]);
+  PBC_CARRY_TO(O[7]);
+  O[8] = 0;
+  PBC_MADW_FIRST(E[4], E[5], x[1], y[3]);
+  PBC_MADW_NEXT(E[6], E[7], x[3], y[3]);
+  PBC_CARRY_TO(E[8]);
+  PBC_MADW_FIRST(O[3], O[4], x[0], y[3]);
+  PBC_MADW_NEXT(O[5], O[6], x[2], y[3]);
+  PBC_MADW_NEXT(O[7], O[8], x[4], y[3]);
+  E[9] = 0;
+  PBC_MADW_FIRST(E[4], E[5], x[0], y[4]);
+  PBC_MADW_NEXT(E[6], E[7], x[2], y[4]);
+  PBC_MADW_NEXT(E[8], E[9], x[4], y[4]);
+  PBC_MADW_FIRST(O[5], O[6], x[1], y[4]);
+  PBC_MADW_NEXT(O[7], O[8], x[3], y[4]);
+  PBC_CARRY_TO(O[9]);
+}
+// c += a b.  SETK: the first accumulation after fqa_mul -- the first capture at each word writes K.
+// (K[i+1] is first touched by row i's long run, K[0] by row 0's short run.)
+template <bool SETK>
+__device__ __forceinline__ void fqa_mac(FqAcc& c, const Fq& a, const Fq& b) {
+  const uint32_t* x = a.v;
+  const uint32_t* y = b.v;
+#pragma unroll
+  for (int i = 0; i < kNS; i++) {
+    uint32_t* S = (i & 1) ? c.O : c.E;
+    uint32_t* T = (i & 1) ? c.E : c.O;
+    PBC_MADW_FIRST(S[i], S[i + 1], x[0], y[i]);
+    PBC_MADW_NEXT(S[i + 2], S[i + 3], x[2], y[i]);
+    PBC_MADW_NEXT(S[i + 4], S[i + 5], x[4], y[i]);
+    if (i < 4) {                                            // carry into word i + 6
+      if (SETK) PBC_CARRY_TO(c.K[i + 1]); else PBC_CARRY_ADD(c.K[i + 1]);
+    }
+    PBC_MADW_FIRST(T[i + 1], T[i + 2], x[1], y[i]);
+    PBC_MADW_NEXT(T[i + 3], T[i + 4], x[3], y[i]);
+    if (SETK && i == 0) PBC_CARRY_TO(c.K[0]); else PBC_CARRY_ADD(c.K[i]);   // carry into word i + 5
+  }
+}
+// t = the value of c.  HASK = false: straight after fqa_mul (K not written).
+template <bool HASK>
+__device__ __forceinline__ void fqa_merge(FqW& t, const FqAcc& c) {
+  t.v[0] = c.E[0];
+  PBC_ASM("add.cc.u32 %0, %1, %2;" : "=r"(t.v[1]) : "r"(c.E[1]), "r"(c.O[1]));
+#pragma unroll
+  for (int k = 2; k < 9; k++) PBC_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(t.v[k]) : "r"(c.E[k]), "r"(c.O[k]));
+  PBC_ASM("addc.u32 %0, %1, %2;" : "=r"(t.v[9]) : "r"(c.E[9]), "r"(c.O[9]));
+  if (HASK) {
+    PBC_ASM("add.cc.u32 %0, %0, %1;" : "+r"(t.v[5]) : "r"(c.K[0]));
+#pragma unroll
+    for (int k = 1; k < 4; k++) PBC_ASM("addc.cc.u32 %0, %0, %1;" : "+r"(t.v[5 + k]) : "r"(c.K[k]));
+    PBC_ASM("addc.u32 %0, %0, %1;" : "+r"(t.v[9]) : "r"(c.K[4]));
+  }
+}
+
+// Montgomery reduction by rows (operand scanning): r = t / R mod q, canonical.  TWO = false: t < q R (one
+// conditional subtraction); TWO = true: t < 2 q R.
+// The quotient digits depend on the LOW half of t only: X = (t_lo + M q) / R with M = sum m_i 2^(32 i) is
+// computed on a sliding pair of even / odd accumulators -- row i adds m_i (q_0, q_2, q_4) to the
+// accumulator whose low word is column i (that word becomes zero and drops out) and m_i (q_1, q_3) to the
+// other one -- and X <= q, so no run ever carries out of its fresh top pair except the short run into
+// the word above it, which the next row's top pair takes as its addend.  r = X + t_hi - {0, q, 2q}.
+// 25 IMAD.WIDE + 5 IMAD and about 30 additions; the column-wise fqw_redc2 needs about 60 and a serial
+// chain of three-word column sums.
+template <bool TWO>
+__device__ __forceinline__ void fqw_redc_os(Fq& r, const FqW& t) {
+  static_assert(kNS == 5, "written out for five limbs");
+  const uint32_t* q = c_fp.p;
+  // a: the accumulator with its low word at the current column (six words), b: the other (four words above
+  // that column), top: the carry out of b's run, one word above it.  Words are named by absolute column.
+  uint32_t E[10], O[10], top, m;
+  // row 0: E = t_lo + m (q0, q2, q4) on words 0..5, O = m (q1, q3) on words 1..4
+  m = t.v[0] * c_fp.np0;
+  PBC_ASM("mad.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;" : "=r"(E[0]), "=r"(E[1]) : "r"(m), "r"(q[0]), "r"(t.v[0]), "r"(t.v[1]));
+  PBC_ASM("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;" : "=r"(E[2]), "=r"(E[3]) : "r"(m), "r"(q[2]), "r"(t.v[2]), "r"(t.v[3]));
+  PBC_ASM("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.u32 %1, %2, %3, 0;" : "=r"(E[4]), "=r"(E[5]) : "r"(m), "r"(q[4]), "r"(t.v[4]));
+  PBC_MULW_PAIR(O[1], O[2], m, q[1]);
+  PBC_MULW_PAIR(O[3], O[4], m, q[3]);
+  top = 0;
+#pragma unroll
+  for (int i = 1; i < kNS; i++) {
+    uint32_t* S = (i & 1) ? O : E;
+    uint32_t* T = (i & 1) ? E : O;
+    // the lone word of T at column i joins S; the carry enters T's run at column i + 1
+    PBC_ASM("add.cc.u32 %0, %0, %1;" : "+r"(S[i]) : "r"(T[i]));
+    m = S[i] * c_fp.np0;
+    PBC_ASM("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(T[i + 1]), "+r"(T[i + 2]) : "r"(m), "r"(q[1]));
+    PBC_ASM("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(T[i + 3]), "+r"(T[i + 4]) : "r"(m), "r"(q[3]));
+    uint32_t ntop;
+    PBC_CARRY_TO(ntop);                                     // into word i + 5 of T: the next row's fresh low word
+    PBC_MADW_FIRST(S[i], S[i + 1], m, q[0]);                // S[i] becomes zero
+    PBC_MADW_NEXT(S[i + 2], S[i + 3], m, q[2]);
+    PBC_ASM("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.u32 %1, %2, %3, 0;" : "=r"(S[i + 4]), "=r"(S[i + 5]) : "r"(m), "r"(q[4]), "r"(top));
+    top = ntop;
+  }
+  // after row 4 (S = E): E holds words 5..9, O words 5..8, top is word 9 of O.  X = E + O + top 2^(32 * 9)
+  uint32_t o[kNS], v0;
+  PBC_ASM("add.cc.u32 %0, %1, %2;" : "=r"(o[0]) : "r"(E[5]), "r"(O[5]));
+  PBC_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(o[1]) : "r"(E[6]), "r"(O[6]));
+  PBC_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(o[2]) : "r"(E[7]), "r"(O[7]));
+  PBC_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(o[3]) : "r"(E[8]), "r"(O[8]));
+  PBC_ASM("addc.u32 %0, %1, %2;" : "=r"(o[4]) : "r"(E[9]), "r"(top));
+  // + t_hi: below (1 or 2) q + q + 1 <= 3 q < 2^161
+  PBC_ASM("add.cc.u32 %0, %0, %1;" : "+r"(o[0]) : "r"(t.v[5]));
+#pragma unroll
+  for (int k = 1; k < kNS; k++) PBC_ASM("addc.cc.u32 %0, %0, %1;" : "+r"(o[k]) : "r"(t.v[5 + k]));
+  PBC_CARRY_TO(v0);
+  uint32_t d[kNS], borrow;
+  PBC_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(d[0]) : "r"(o[0]), "r"(q[0]));
+#pragma unroll
+  for (int k = 1; k < kNS; k++) PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(d[k]) : "r"(o[k]), "r"(q[k]));
+  PBC_ASM("subc.u32 %0, 0, 0;" : "=r"(borrow));
+  bool use_d = v0 != 0 || borrow == 0;
+  if (!TWO) {
+#pragma unroll
+    for (int k = 0; k < kNS; k++) r.v[k] = use_d ? d[k] : o[k];
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < kNS; k++) o[k] = use_d ? d[k] : o[k];
+  PBC_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(d[0]) : "r"(o[0]), "r"(q[0]));
+#pragma unroll
+  for (int k = 1; k < kNS; k++) PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(d[k]) : "r"(o[k]), "r"(q[k]));
+  PBC_ASM("subc.u32 %0, 0, 0;" : "=r"(borrow));
+#pragma unroll
+  for (int k = 0; k < kNS; k++) r.v[k] = borrow == 0 ? d[k] : o[k];
+}
+// r = a b, one product with the row-wise reduction
+__device__ __forceinline__ void fq_mul_os(Fq& r, const Fq& a, const Fq& b) {
+  FqAcc c;
+  FqW t;
+  fqa_mul(c, a, b);
+  fqa_merge<false>(t, c);
+  fqw_redc_os<false>(r, t);
+}
+
 // wire bytes (big-endian, 20 per coordinate) -> Montgomery form (arith/montfp.c:498-517 reduces mod q)
 __device__ __forceinline__ void fq_from_wire(Fq& r, const uint8_t* p) {
   limbs_from_be<kNS, kWS>(r.v, p);

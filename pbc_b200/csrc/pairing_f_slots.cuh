@@ -50,8 +50,59 @@ constexpr int kFGWords = 6 * kNS;
 // ---- register-level pieces (fqw_mul, fqw_redc2: fq_small.cuh) ----
 // r = a b (Montgomery): interleaved column-wise product, or wide product + two-product reduction
 __device__ __forceinline__ void fq_mul_sel(Fq& r, const Fq& a, const Fq& b) {
-  if (PBC_FQW_REDC_SPLIT) { FqW t; fqw_mul(t, a, b); fqw_redc_split(r, t); }
+  if (PBC_FQ_ACC) fq_mul_os(r, a, b);
+  else if (PBC_FQW_REDC_SPLIT) { FqW t; fqw_mul(t, a, b); fqw_redc_split(r, t); }
   else mont_mul_ps<kNS, false>(r.v, a.v, b.v);
+}
+// r = a^2.  PBC_FS_SQR_OS: the full 25-product row schedule (fewer instructions); else the 15 + 25 product
+// column-wise squarer.
+#ifndef PBC_FS_SQR_OS
+#define PBC_FS_SQR_OS PBC_FQ_ACC
+#endif
+__device__ __forceinline__ void fq_sqr_sel(Fq& r, const Fq& a) {
+  if (PBC_FS_SQR_OS) fq_mul_os(r, a, a); else mont_sqr_ps<kNS, false>(r.v, a.v);
+}
+
+// ---- F_q^2 products on three unmerged sums (fq_small.cuh, PBC_FQ_ACC) ----
+//   A = sum x0 y0,  B = sum x1 y1,  C = sum (x0 + x1)(y0 + y1);   re = A - B,  im = C - A - B.
+// Bounds: operands canonical, so a term adds less than q^2 to A and B and less than 4 q^2 to C; three terms
+// keep C below 12 q^2 < 2^320 (c_f.slots_ok).
+struct F2Acc { FqAcc A, B, C; };
+// PBC_F2A_FENCE = 1: a warp-level barrier between the products of a term.  It computes nothing; it keeps ptxas from
+// interleaving the carry runs of more products than there are carry predicates (seven): in f12's line product it
+// had a dozen runs in flight and spent 12 % of the routine saving and restoring predicates (LOP3 / P2R).
+#ifndef PBC_F2A_FENCE
+#define PBC_F2A_FENCE 0
+#endif
+__device__ __forceinline__ void f2a_fence() {
+#if PBC_F2A_FENCE
+  __syncwarp();
+#endif
+}
+// TERM 0: the first term (starts the sums), 1: the second (first carry counts), 2: any later one
+template <int TERM>
+__device__ __forceinline__ void f2a_term(F2Acc& g, const Fq& x0, const Fq& x1, const Fq& y0, const Fq& y1) {
+  Fq sx, sy;
+  fq_add_nr(sx, x0, x1);
+  fq_add_nr(sy, y0, y1);
+  if (TERM == 0) { fqa_mul(g.A, x0, y0); f2a_fence(); fqa_mul(g.B, x1, y1); f2a_fence(); fqa_mul(g.C, sx, sy); f2a_fence(); }
+  else { fqa_mac<TERM == 1>(g.A, x0, y0); f2a_fence(); fqa_mac<TERM == 1>(g.B, x1, y1); f2a_fence(); fqa_mac<TERM == 1>(g.C, sx, sy); f2a_fence(); }
+}
+// (r0, r1) = (re, im) reduced.  offs: a multiple of q^2 (double width) not below B, HASK: more than one term.
+template <bool HASK>
+__device__ __forceinline__ void f2a_finish(Fq& r0, Fq& r1, const F2Acc& g, const uint32_t* offs) {
+  FqW a, b, c;
+  fqa_merge<HASK>(a, g.A);
+  fqa_merge<HASK>(b, g.B);
+  fqa_merge<HASK>(c, g.C);
+  fqw_sub(c, c, a);
+  fqw_sub(c, c, b);                        // im = C - A - B >= 0
+  PBC_ASM("add.cc.u32 %0, %0, %1;" : "+r"(a.v[0]) : "r"(offs[0]));
+#pragma unroll
+  for (int k = 1; k < 2 * kNS; k++) PBC_ASM("addc.cc.u32 %0, %0, %1;" : "+r"(a.v[k]) : "r"(offs[k]));
+  fqw_sub(a, a, b);                        // re = A + offs - B
+  fqw_redc_os<true>(r0, a);
+  fqw_redc_os<true>(r1, c);
 }
 
 // (re, im) += x y for F_q^2 operands in the internal basis (i^2 = -1), double width, unreduced:
@@ -141,7 +192,7 @@ struct FS {
   static __device__ __noinline__ void qsqr(int d, int a) {
     Fq x;
     ld(x, a);
-    mont_sqr_ps<kNS, false>(x.v, x.v);
+    fq_sqr_sel(x, x);
     st(d, x);
   }
   // two / three independent products in ONE call, every operand read before any result is stored (so the
@@ -167,9 +218,9 @@ struct FS {
   static __device__ __noinline__ void qsqr3(int d0, int a0, int d1, int a1, int d2, int a2) {
     Fq x0, x1, x2;
     ld(x0, a0); ld(x1, a1); ld(x2, a2);
-    mont_sqr_ps<kNS, false>(x0.v, x0.v);
-    mont_sqr_ps<kNS, false>(x1.v, x1.v);
-    mont_sqr_ps<kNS, false>(x2.v, x2.v);
+    fq_sqr_sel(x0, x0);
+    fq_sqr_sel(x1, x1);
+    fq_sqr_sel(x2, x2);
     st(d0, x0); st(d1, x1); st(d2, x2);
   }
   // d0 = a0 b0, d1 = a1^2, d2 = a2^2
@@ -177,8 +228,8 @@ struct FS {
     Fq x0, y0, x1, x2;
     ld(x0, a0); ld(y0, b0); ld(x1, a1); ld(x2, a2);
     fq_mul_sel(x0, x0, y0);
-    mont_sqr_ps<kNS, false>(x1.v, x1.v);
-    mont_sqr_ps<kNS, false>(x2.v, x2.v);
+    fq_sqr_sel(x1, x1);
+    fq_sqr_sel(x2, x2);
     st(d0, x0); st(d1, x1); st(d2, x2);
   }
   static __device__ __noinline__ void qadd(int d, int a, int b) { Fq x, y; ld(x, a); ld(y, b); fq_add(x, x, y); st(d, x); }
@@ -269,12 +320,18 @@ struct FS {
     ld(x0, a); ld(x1, a + 1);
     if (conj) fq_neg(x1, x1);
     fq_set(y0, c[0]); fq_set(y1, c[1]);
+#if PBC_FQ_ACC
+    F2Acc g;
+    f2a_term<0>(g, x0, x1, y0, y1);
+    f2a_finish<false>(x0, x1, g, c_f.qsqm[0]);
+#else
     FqW re, im;
 #pragma unroll
     for (int w = 0; w < 2 * kNS; w++) { re.v[w] = c_f.qsqm[0][w]; im.v[w] = 0; }
     f2w_mac(re, im, x0, x1, y0, y1);
     fqw_reduce(x0, re);
     fqw_reduce(x1, im);
+#endif
     st(d, x0); st(d + 1, x1);
   }
 
@@ -282,7 +339,31 @@ struct FS {
   // overlap a or b.  c_k = sum_i a_i b'_(k-i), b' = xi b where the index wrapped: three products per
   // coefficient accumulated double width (each term below 2 q^2, the sum below 6 q^2 < 2 q R), one
   // reduction per F_q.
-  static __device__ __noinline__ void f6mul(int d, int a, int b) {
+  // xs: four scratch slots (they receive xi b_1 and xi b_2), apart from d, a, b.
+  static __device__ __noinline__ void f6mul(int d, int a, int b, int xs) {
+#if PBC_FQ_ACC
+    // The three terms of a coefficient are written out: sums carried around a loop cost a register move per
+    // accumulator pair and iteration (ncu: IMAD.MOV was 21 % of this routine with the terms in a loop).  The
+    // wrapped operands xi b_1, xi b_2 are made once, so a term only selects its slot.
+    f2mulxi(xs, b + 2);
+    f2mulxi(xs + 2, b + 4);
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {
+      F2Acc g;
+      Fq x0, x1, y0, y1;
+      ld(x0, a); ld(x1, a + 1); ld(y0, b + 2 * k); ld(y1, b + 2 * k + 1);      // a_0 b_k
+      f2a_term<0>(g, x0, x1, y0, y1);
+      const int s1 = k >= 1 ? b + 2 * (k - 1) : xs + 2;                        // a_1 b_(k-1)  or  a_1 (xi b_2)
+      ld(x0, a + 2); ld(x1, a + 3); ld(y0, s1); ld(y1, s1 + 1);
+      f2a_term<1>(g, x0, x1, y0, y1);
+      const int s2 = k == 2 ? b : (k == 1 ? xs + 2 : xs);                      // a_2 b_0,  a_2 (xi b_2),  a_2 (xi b_1)
+      ld(x0, a + 4); ld(x1, a + 5); ld(y0, s2); ld(y1, s2 + 1);
+      f2a_term<2>(g, x0, x1, y0, y1);
+      f2a_finish<true>(x0, x1, g, c_f.qsqm[2]);
+      st(d + 2 * k, x0); st(d + 2 * k + 1, x1);
+    }
+#else
+    (void)xs;
 #pragma unroll 1
     for (int k = 0; k < 3; k++) {
       FqW re, im;
@@ -304,6 +385,7 @@ struct FS {
       fqw_reduce(r1, im);
       st(d + 2 * k, r0); st(d + 2 * k + 1, r1);
     }
+#endif
   }
   // o = v * (c + L3 x^3 + L4 x^4)   (f12_mul_line): o and v are 12-slot F_q^12 areas, distinct.
   //   o_k = c v_k + m3 v_(k-3) + m4 v_(k-4), indices below zero wrap with xi (slots fsXL3 / fsXL4)
@@ -311,6 +393,27 @@ struct FS {
 #pragma unroll 1
     for (int k = 0; k < 6; k++) {
       const int i3 = k >= 3 ? k - 3 : k + 3, i4 = k >= 4 ? k - 4 : k + 2;
+#if PBC_FQ_ACC
+      // re = A - B + c y0,  im = C - A - B + c y1:  c y0 joins A and c (y0 + y1) joins C
+      F2Acc g;
+      Fq x0, x1, y0, y1;
+      const int m3 = k >= 3 ? fsL3 : fsXL3, m4 = k >= 4 ? fsL4 : fsXL4;
+      ld(x0, m3); ld(x1, m3 + 1);
+      ld(y0, v + 2 * f12_pos(i3)); ld(y1, v + 2 * f12_pos(i3) + 1);
+      f2a_term<0>(g, x0, x1, y0, y1);
+      ld(x0, m4); ld(x1, m4 + 1);
+      ld(y0, v + 2 * f12_pos(i4)); ld(y1, v + 2 * f12_pos(i4) + 1);
+      f2a_term<1>(g, x0, x1, y0, y1);
+      ld(x0, fsC);
+      ld(y0, v + 2 * f12_pos(k)); ld(y1, v + 2 * f12_pos(k) + 1);
+      fq_add_nr(x1, y0, y1);
+      fqa_mac<false>(g.A, x0, y0);
+      f2a_fence();
+      fqa_mac<false>(g.C, x0, x1);
+      f2a_fence();
+      f2a_finish<true>(x0, x1, g, c_f.qsqm[1]);
+      st(o + 2 * f12_pos(k), x0); st(o + 2 * f12_pos(k) + 1, x1);
+#else
       FqW re, im, t;
 #pragma unroll
       for (int w = 0; w < 2 * kNS; w++) { re.v[w] = c_f.qsqm[1][w]; im.v[w] = 0; }
@@ -331,15 +434,16 @@ struct FS {
       fqw_reduce(x0, re);
       fqw_reduce(x1, im);
       st(o + 2 * f12_pos(k), x0); st(o + 2 * f12_pos(k) + 1, x1);
+#endif
     }
   }
   // v <- v^2 in place with the 12-slot scratch t (f12_sqr: complex squaring over F_q^6).
   //   A = v[0..5], B = v[6..11];  t0 = A B;  t1 = (A + B)(A + y B);  A' = t1 - t0 - y t0,  B' = 2 t0
-  static __device__ __forceinline__ void f12sqr(int v, int t) {
-    f6mul(t, v, v + 6);                                        // t0
+  static __device__ __forceinline__ void f12sqr(int v, int t, int xs) {
+    f6mul(t, v, v + 6, xs);                                    // t0
     f2add(t + 6, v, v + 6); f2add(t + 8, v + 2, v + 8); f2add(t + 10, v + 4, v + 10);        // A + B
     f2addxi(v, v, v + 10); f2add(v + 2, v + 2, v + 6); f2add(v + 4, v + 4, v + 8);           // A + y B, in place
-    f6mul(v + 6, t + 6, v);                                    // t1 over B (B is dead)
+    f6mul(v + 6, t + 6, v, xs);                                // t1 over B (B is dead)
     f2sub(v, v + 6, t); f2subxi(v, v, t + 4);                  // A'0 = t1_0 - t0_0 - xi t0_2
     f2sub(v + 2, v + 8, t + 2); f2sub(v + 2, v + 2, t);        // A'1 = t1_1 - t0_1 - t0_0
     f2sub(v + 4, v + 10, t + 4); f2sub(v + 4, v + 4, t + 2);   // A'2 = t1_2 - t0_2 - t0_1
@@ -347,12 +451,12 @@ struct FS {
   }
   // p <- p q with the 12-slot scratch t (f12_mul: Karatsuba over F_q^6); q is left as it was.
   //   p = A + B x, q = C + D x:  t0 = A C, t1 = B D, t2 = (A + B)(C + D);  lo = t0 + y t1, hi = t2 - t0 - t1
-  static __device__ __forceinline__ void f12mul(int p, int q, int t) {
-    f6mul(t, p, q);                                            // t0
-    f6mul(t + 6, p + 6, q + 6);                                // t1
+  static __device__ __forceinline__ void f12mul(int p, int q, int t, int xs) {
+    f6mul(t, p, q, xs);                                        // t0
+    f6mul(t + 6, p + 6, q + 6, xs);                            // t1
     f2add(p, p, p + 6); f2add(p + 2, p + 2, p + 8); f2add(p + 4, p + 4, p + 10);     // A + B over A
     f2add(q, q, q + 6); f2add(q + 2, q + 2, q + 8); f2add(q + 4, q + 4, q + 10);     // C + D over C
-    f6mul(p + 6, p, q);                                        // t2 over B
+    f6mul(p + 6, p, q, xs);                                    // t2 over B
     f2sub(q, q, q + 6); f2sub(q + 2, q + 2, q + 8); f2sub(q + 4, q + 4, q + 10);     // C back
     f2sub(p + 6, p + 6, t); f2sub(p + 6, p + 6, t + 6);
     f2sub(p + 8, p + 8, t + 2); f2sub(p + 8, p + 8, t + 8);
@@ -437,7 +541,7 @@ struct FS {
     for (int j = (int)c_f.u_bits - 2; j >= 0; j--) {
       if (PBC_FS_LOCKSTEP) __syncthreads();
       f12cycsqr(r0, t, e);
-      if ((c_f.u_abs[j >> 5] >> (j & 31)) & 1u) f12mul(r0, r1, t);
+      if ((c_f.u_abs[j >> 5] >> (j & 31)) & 1u) f12mul(r0, r1, t, e);
     }
     if (c_f.u_neg) f12conj(r0);
   }
@@ -445,8 +549,15 @@ struct FS {
 
 // Same interface as k_f_miller plus gq: [6 * kNS][n] words of scratch (Qx, Qy untwisted and scaled, P;
 // Montgomery form, internal basis).
+// PBC_FS_MILLER_MAXREG: register cap of the Miller kernel (for block sizes where the default would cost a
+// resident block); not defined = no cap
+#ifdef PBC_FS_MILLER_MAXREG
+#define PBC_FS_MILLER_BOUNDS __maxnreg__(PBC_FS_MILLER_MAXREG)
+#else
+#define PBC_FS_MILLER_BOUNDS __launch_bounds__(BLOCK)
+#endif
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void PBC_FS_MILLER_BOUNDS
 k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_t* __restrict__ mv,
              uint32_t* __restrict__ flag, uint32_t* __restrict__ gq, size_t n, size_t stride1,
              const uint32_t* __restrict__ tab, size_t rows) {
@@ -577,7 +688,7 @@ k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint3
       { int s = V; V = T; T = s; }
     }
     m--;
-    S::f12sqr(V, T);
+    S::f12sqr(V, T, fsL3);                   // the line's slots are dead here: scratch
   }
   if (!live) return;
   // publish (flagged-off inputs: the identity)
@@ -596,11 +707,11 @@ k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint3
 // f12_final_exp of pairing_f.cuh).  The easy part (one F_q^12 inversion, a tenth of the work) and the
 // change of basis on the way out run on the structs of pairing_f.cuh; the hard part -- three powers
 // by the BN parameter and the multiplication chain -- runs on slots: two resident F_q^12 values, the
-// 12-slot scratch and one spare F_q^2 (38 slots = 760 B per thread), everything else parked in a
+// 12-slot scratch and two spare F_q^2 (40 slots = 800 B per thread; the spares hold xi b_1, xi b_2 inside f6mul), everything else parked in a
 // limb-major global stash of four F_q^12 per pairing (about a dozen 240-byte moves each way).
 // mv is overwritten (it holds f after the easy part).  Needs c_f.bn and c_f.slots_ok.
 // ---------------------------------------------------------------------------------------------
-constexpr int kFFinalSlots = 38;
+constexpr int kFFinalSlots = 40;
 constexpr int kFStashWords = 4 * kF12Words;
 
 template <int BLOCK>
@@ -642,7 +753,7 @@ k_f_finalexp_s(uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag, uin
   // t0 = y6^2, y6 = 1 / (f^(u^3) f^(u^3 q))
   S::f12copy(R1, R0);
   S::f12frob(R1, 1);
-  S::f12mul(R1, R0, T);
+  S::f12mul(R1, R0, T, E);
   S::f12conj(R1);
   S::f12cycsqr(R1, T, E);
   S::f12stg(g3, n, R1, live);                  // park t0
@@ -650,35 +761,35 @@ k_f_finalexp_s(uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag, uin
   S::f12ldg(R0, g2, n);
   S::f12frob(R0, 1);
   S::f12ldg(R1, g1, n);
-  S::f12mul(R0, R1, T);
+  S::f12mul(R0, R1, T, E);
   S::f12conj(R0);
   S::f12ldg(R1, g3, n);
-  S::f12mul(R1, R0, T);                  // t0 *= y4
+  S::f12mul(R1, R0, T, E);                  // t0 *= y4
   // y5 = 1 / f^(u^2)
   S::f12ldg(R0, g2, n);
   S::f12conj(R0);
-  S::f12mul(R1, R0, T);                  // t0 *= y5
+  S::f12mul(R1, R0, T, E);                  // t0 *= y5
   S::f12stg(g3, n, R1, live);                  // park t0
   // t1 = y3 y5 t0, y3 = 1 / f^(u q)
   S::f12ldg(R1, g1, n);
   S::f12frob(R1, 1);
   S::f12conj(R1);
-  S::f12mul(R1, R0, T);
+  S::f12mul(R1, R0, T, E);
   S::f12ldg(R0, g3, n);
-  S::f12mul(R1, R0, T);                  // R0 = t0, R1 = t1
+  S::f12mul(R1, R0, T, E);                  // R0 = t0, R1 = t1
   // t0 *= y2, y2 = f^(u^2 q^2)
   S::f12stg(g4, n, R1, live);                  // park t1
   S::f12ldg(R1, g2, n);
   S::f12frob(R1, 2);
-  S::f12mul(R0, R1, T);
+  S::f12mul(R0, R1, T, E);
   S::f12ldg(R1, g4, n);
   S::f12cycsqr(R1, T, E);
-  S::f12mul(R1, R0, T);
+  S::f12mul(R1, R0, T, E);
   S::f12cycsqr(R1, T, E);                // t1 = (t1^2 t0)^2
   // t0 = t1 y1, y1 = 1 / f
   S::f12ldg(R0, g0, n);
   S::f12conj(R0);
-  S::f12mul(R0, R1, T);
+  S::f12mul(R0, R1, T, E);
   S::f12stg(g3, n, R0, live);                  // park t0
   S::f12stg(g4, n, R1, live);                  // park t1
   // y0 = f^q f^(q^2) f^(q^3)
@@ -686,15 +797,15 @@ k_f_finalexp_s(uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag, uin
   S::f12frob(R0, 1);
   S::f12ldg(R1, g0, n);
   S::f12frob(R1, 2);
-  S::f12mul(R0, R1, T);
+  S::f12mul(R0, R1, T, E);
   S::f12ldg(R1, g0, n);
   S::f12frob(R1, 3);
-  S::f12mul(R0, R1, T);
+  S::f12mul(R0, R1, T, E);
   S::f12ldg(R1, g4, n);
-  S::f12mul(R1, R0, T);                  // t1 *= y0
+  S::f12mul(R1, R0, T, E);                  // t1 *= y0
   S::f12ldg(R0, g3, n);
   S::f12cycsqr(R0, T, E);
-  S::f12mul(R0, R1, T);                  // result
+  S::f12mul(R0, R1, T, E);                  // result
   if (!live) return;
   {
     F12 acc;

@@ -56,6 +56,7 @@ inline void launch(dim3 grid, dim3 block, F&& body) {
 #define gridDim (::cusim::gdim())
 
 static inline void __syncthreads() {}
+static inline void __syncwarp() {}
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) {
   return (uint32_t)((((uint64_t)hi << 32) | lo) >> (s & 31));
 }

@@ -8,6 +8,7 @@
 //   add sub neg halve                      fp_add / fp_sub / fp_neg / fp_halve
 //   fq_mul  fq_redc_call(fq_mulw_call(a, b))                       (N = kNS only)
 //   fq_mul_os / fq_mac_os  the same through the inline operand-scanning product fqw_mul and fqw_redc2
+//   fq_mul_rows / fq_mul_rows2 / fq_acc3 / fq_acc4  the accumulating products (FqAcc) and the row-wise reduction fqw_redc_os
 //   fq_mac  fq_redc2_call(a b + c d)  fq_msb  fq_redc2_call(a b + (q R - c d))... see the test
 #include HOST_FP_HEADER
 
@@ -78,6 +79,16 @@ int main() {
         else if (op == "fq_mul_os") { FqW t; fqw_mul(t, A, B); fqw_redc2(R, t); }
         else if (op == "fq_mac_os") { FqW s, t, u; fqw_mul(t, A, B); fqw_mul(u, C, D); fqw_add(s, t, u); fqw_redc2(R, s); }
         else if (op == "fq_mul_split") { FqW t; fqw_mul(t, A, B); fqw_redc_split(R, t); }
+        else if (op == "fq_mul_rows") { fq_mul_os(R, A, B); }                                   // fqa_mul + fqa_merge + fqw_redc_os<false>
+        else if (op == "fq_mul_rows2") { FqAcc g; FqW t; fqa_mul(g, A, B); fqa_merge<false>(t, g); fqw_redc_os<true>(R, t); }
+        else if (op == "fq_acc3" || op == "fq_acc4") {
+          // a b + c d + a d (+ c b), unmerged; printed as the 320-bit value
+          FqAcc g; FqW t;
+          fqa_mul(g, A, B); fqa_mac<true>(g, C, D); fqa_mac<false>(g, A, D);
+          if (op == "fq_acc4") fqa_mac<false>(g, C, B);
+          fqa_merge<true>(t, g);
+          std::cout << to_hex(t.v, 2 * kNS) << "\n"; continue;
+        }
         else if (op == "fq_mulcall") R = fq_mul_call(A, B);
         else if (op == "fq_sqrcall") R = fq_sqr_call(A);
         else { std::cout << "?" << "\n"; continue; }

@@ -154,3 +154,36 @@ def test_two_product_montgomery_reduction(harness):
     got = _run(harness, reqs)
     bad = [(hex(r[3]), hex(r[4]), hex(r[5])) for r, g, w in zip(reqs, got, want) if g != w]
     assert len(got) == len(want) and not bad, bad[:5]
+
+
+def test_accumulating_products_and_row_wise_reduction(harness):
+    """FqAcc / fqw_redc_os (fq_small.cuh, PBC_FQ_ACC): sums of up to four 5 x 5 products kept unmerged on the even / odd
+    accumulators with carry counts, against Python integers on the operands that drive every carry path; the row-wise
+    Montgomery reduction for t < q R (one conditional subtraction) and t < 2 q R (two), including t_lo = 0, t = 0 and the
+    largest inputs"""
+    rnd = random.Random(47)
+    N, R = 5, 1 << 160
+    ones = R - 1
+    edge = [0, 1, ones, ones - 1, 1 << 159, (1 << 159) - 1, int("ffffffff00000000" * 3, 16) & ones,
+            int("00000000ffffffff" * 3, 16) & ones, 0xffffffff, 0xffffffff << 128, (1 << 64) - 1]
+    p0 = (1 << 158) | 0x1234567 | 1
+    reqs, want = [], []
+    quads = [(a, b, c, d) for a in edge for b in edge[:6] for c in edge[2:5] for d in edge[1:4]]
+    quads += [tuple(rnd.getrandbits(160) for _ in range(4)) for _ in range(200)]
+    for a, b, c, d in quads:
+        if a * b + c * d + a * d < 1 << 320:
+            reqs.append((N, 0, "fq_acc3", p0, a, b, c, d)); want.append(a * b + c * d + a * d)
+        if a * b + c * d + a * d + c * b < 1 << 320:
+            reqs.append((N, 0, "fq_acc4", p0, a, b, c, d)); want.append(a * b + c * d + a * d + c * b)
+    for p in _moduli(5, 0, rnd):
+        Rinv = pow(R, -1, p)
+        pairs = _operands(p, 5, rnd, 60) + [(2 * p - 1, p - 1), (R - 1, 1), (1 << 159, 2), (0, 5), (R >> 1, 2), (p - 1, p - 1),
+                                            (ones, ones), (ones, p), (2 * p - 2, 2 * p - 1), (R >> 32, 1 << 32)]
+        for a, b in pairs:
+            if a * b < p * R:
+                reqs.append((N, 0, "fq_mul_rows", p, a, b, 0, 0)); want.append(a * b * Rinv % p)
+            if a * b < 2 * p * R and 3 * p <= R:
+                reqs.append((N, 0, "fq_mul_rows2", p, a, b, 0, 0)); want.append(a * b * Rinv % p)
+    got = _run(harness, reqs)
+    bad = [(r[2], hex(r[3]), hex(r[4]), hex(r[5])) for r, g, w in zip(reqs, got, want) if g != w]
+    assert len(got) == len(want) and len(want) > 800 and not bad, bad[:5]
