@@ -163,27 +163,31 @@ __device__ __noinline__ void f3_to_reference(F3& v) {
 #ifndef PBC_D_LAZY
 #define PBC_D_LAZY 1
 #endif
+// the reduction of the lazy product: row-wise (fq_small.cuh, PBC_FQ_ACC) or column-wise
+__device__ __forceinline__ void fqw_reduce2(Fq& r, const FqW& t) {
+  if (PBC_FQ_ACC) fqw_redc_os<true>(r, t); else fqw_redc2(r, t);
+}
 __device__ __forceinline__ void f3_fold_lazy(F3* r, const FqW& d0, const FqW& d1, const FqW& d2, const FqW& d3,
                                              const FqW& d4) {
   Fq d3r, d4r, p;
   FqW w, t, q1, q2;
-  fqw_redc2(d3r, d3);
-  fqw_redc2(d4r, d4);
+  fqw_reduce2(d3r, d3);
+  fqw_reduce2(d4r, d4);
   fq_set(p, c_d.pcoef);
 #pragma unroll
   for (int k = 0; k < 2 * kNS; k++) { q1.v[k] = c_d.qsqm[0][k]; q2.v[k] = c_d.qsqm[1][k]; }
   fqw_add(w, d0, q2);
   fqw_sub(w, w, d3);
-  fqw_redc2(r->c[0], w);
+  fqw_reduce2(r->c[0], w);
   fqw_mul(t, p, d3r);
   fqw_add(w, d1, q2);
   fqw_sub(w, w, t);
   fqw_sub(w, w, d4);
-  fqw_redc2(r->c[1], w);
+  fqw_reduce2(r->c[1], w);
   fqw_mul(t, p, d4r);
   fqw_add(w, d2, q1);
   fqw_sub(w, w, t);
-  fqw_redc2(r->c[2], w);
+  fqw_reduce2(r->c[2], w);
 }
 __device__ __noinline__ void f3_mul(F3* r, const F3* x, const F3* y) {
   if (PBC_D_LAZY && c_d.nice) {

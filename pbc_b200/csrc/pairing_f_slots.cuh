@@ -475,11 +475,35 @@ struct FS {
     f2sub(r1, r1, e);
     f2addxi(r0, r0, e);
   }
-  // v <- v^2 for v in the cyclotomic subgroup (Granger-Scott, see f12_cyc_sqr), in place, two fused
-  // routines working in registers (the first version made 28 calls of F_q^2 routines per squaring and
-  // ran at 0.3 of the multiplier peak: 5.5 instructions per product).  Coefficient j lives at
+  // v <- v^2 for v in the cyclotomic subgroup (Granger-Scott, see f12_cyc_sqr), in place.  Coefficient j lives at
   // v + 2 f12_pos(j): c0 -> 0, c1 -> 6, c2 -> 2, c3 -> 8, c4 -> 4, c5 -> 10.
   //   A = (c0 + c3 s)^2:  c0' = 3 A0 - 2 c0,  c3' = 3 A1 + 2 c3
+  //   B = (c1 + c4 s)^2:  c2' = 3 B0 - 2 c2,  c5' = 3 B1 + 2 c5
+  //   C = (c2 + c5 s)^2:  c4' = 3 C0 - 2 c4,  c1' = 3 xi C1 + 2 c1
+  // History: 28 calls of F_q^2 routines per squaring ran at 0.3 of the multiplier peak (5.5 instructions per
+  // product); two fused routines working in registers (cyc_pair_a, cyc_pair_bc: the three F_q^4 squarings written out,
+  // 2 200 instructions executed once per squaring) left the warps waiting for instructions a sixth of the time
+  // (ncu: stall_no_instruction 0.67 per issue in k_f_finalexp_s).  PBC_FS_CYC_ONE = 1: ONE out-of-line F_q^4 squaring
+  // with the recombination, called three times (B's square waits in the four scratch slots e while C -- which reads
+  // what B's results overwrite -- is done).
+#ifndef PBC_FS_CYC_ONE
+#define PBC_FS_CYC_ONE 1
+#endif
+  // (r0, r1) = (a + b s)^2 for the F_q^2 at slots a, b.  raw: tm <- r0, tp <- r1;  else tm <- 3 r0 - 2 tm and
+  // tp <- 3 r1' + 2 tp with r1' = xi r1 when xi is set.
+  static __device__ __noinline__ void f4sqr_gs(int a, int b, int tm, int tp, bool raw, bool xi) {
+    Fq a0, a1, b0, b1, r00, r01, r10, r11;
+    ld(a0, a); ld(a1, a + 1); ld(b0, b); ld(b1, b + 1);
+    f4r_sqr(r00, r01, r10, r11, a0, a1, b0, b1);
+    if (!raw) {
+      if (xi) f2r_mul_xi(r10, r11);
+      ld(a0, tm); ld(a1, tm + 1); ld(b0, tp); ld(b1, tp + 1);
+      gs_combine<false>(a0, r00); gs_combine<false>(a1, r01);
+      gs_combine<true>(b0, r10); gs_combine<true>(b1, r11);
+      r00 = a0; r01 = a1; r10 = b0; r11 = b1;
+    }
+    st(tm, r00); st(tm + 1, r01); st(tp, r10); st(tp + 1, r11);
+  }
   static __device__ __noinline__ void cyc_pair_a(int v) {
     Fq a0, a1, b0, b1, r00, r01, r10, r11;
     ld(a0, v); ld(a1, v + 1); ld(b0, v + 8); ld(b1, v + 9);
@@ -488,7 +512,6 @@ struct FS {
     gs_combine<true>(b0, r10); gs_combine<true>(b1, r11);
     st(v, a0); st(v + 1, a1); st(v + 8, b0); st(v + 9, b1);
   }
-  //   B = (c1 + c4 s)^2, C = (c2 + c5 s)^2:  c2' = 3 B0 - 2 c2, c5' = 3 B1 + 2 c5, c1' = 3 xi C1 + 2 c1, c4' = 3 C0 - 2 c4
   static __device__ __noinline__ void cyc_pair_bc(int v) {
     Fq c10, c11, c40, c41, c20, c21, c50, c51;
     Fq B00, B01, B10, B11, C00, C01, C10, C11;
@@ -504,9 +527,18 @@ struct FS {
     st(v + 2, c20); st(v + 3, c21); st(v + 10, c50); st(v + 11, c51);
     st(v + 6, c10); st(v + 7, c11); st(v + 4, c40); st(v + 5, c41);
   }
-  static __device__ __forceinline__ void f12cycsqr(int v, int, int) {
-    cyc_pair_a(v);
-    cyc_pair_bc(v);
+  // e: four scratch slots
+  static __device__ __forceinline__ void f12cycsqr(int v, int, int e) {
+    if (PBC_FS_CYC_ONE) {
+      f4sqr_gs(v + 6, v + 4, e, e + 2, true, false);            // B -> scratch
+      f4sqr_gs(v, v + 8, v, v + 8, false, false);               // A
+      f4sqr_gs(v + 2, v + 10, v + 4, v + 6, false, true);       // C (reads c2, c5; writes c4, c1)
+      f2gs<false>(v + 2, e, v + 2);                             // c2' = 3 B0 - 2 c2
+      f2gs<true>(v + 10, e + 2, v + 10);                        // c5' = 3 B1 + 2 c5
+    } else {
+      cyc_pair_a(v);
+      cyc_pair_bc(v);
+    }
   }
   // v <- v^(q^k), k = 1, 2, 3 (f12_frob)
   static __device__ __noinline__ void f12frob(int v, int k) {
