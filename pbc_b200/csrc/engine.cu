@@ -27,6 +27,7 @@
 #include "pairing_d.cuh"
 #include "pairing_f.cuh"
 #include "pairing_f_slots.cuh"
+#include "pairing_f_pair.cuh"
 #include "pairing_g.cuh"
 #include "group_a.cuh"
 #include "group_a1.cuh"
@@ -785,6 +786,23 @@ static constexpr size_t kSmemAMiller9 = (size_t)kA9Slots * 64 * kBlockMiller;
 #define PBC_F_SLOTS 1
 #endif
 static constexpr int kBlockFS = 128;
+// PBC_F_PAIR = 1: the type F Miller loop with two lanes per pairing (pairing_f_pair.cuh): k_f_prep + k_f_miller_p.
+// Bit-exact (simulator test + GPU fixtures) and measured: 55.9 ms against 55.3 ms for k_f_miller_s on 378 880 pairings
+// (profiles/r2_variants_pair.jsonl).  Sixteen resident warps instead of eight change nothing: ncu shows the same
+// 62.7 % multiplier-pipe activity with math_pipe_throttle 1.14 and dispatch_stall 0.80 per issue
+// (profiles/r2_ncu_k_f_miller_p_v1.json) -- the five-limb instruction mix saturates the pipe's issue path, not the
+// warps' latency.  Kept off; the path to more speed is fewer multiplier-pipe instructions per pairing.
+#ifndef PBC_F_PAIR
+#define PBC_F_PAIR 0
+#endif
+static constexpr int kPairsFP = 128;             // pairings per block (256 threads)
+static constexpr size_t kSmemFMillerP = (size_t)kFPSlots * kNS * 4 * kPairsFP;
+// the CPU simulator (tests/host) runs the two lanes of a pair on two host threads when told to
+#ifdef PBC_HOST_SIM
+#define PBC_PAIR_LAUNCH(on) (::cusim::pair_mode() = (on))
+#else
+#define PBC_PAIR_LAUNCH(on) ((void)0)
+#endif
 // threads per block of the slot-machine Miller kernel: 128 -> two blocks (8 warps) per SM, 96 -> three blocks (9 warps)
 #ifndef PBC_FS_MILLER_BLOCK
 #define PBC_FS_MILLER_BLOCK 128
@@ -840,6 +858,7 @@ static int ctx_prepare(pbc_b200_pairing_s* p, int dev) {
       CUDA_OK(allow_smem(k_a_g1_decompress<kBlockMiller>, (size_t)5 * 64 * kBlockMiller));
     }
     if (p->type == 'f') CUDA_OK(allow_smem(k_f_miller_s<kBlockFSM>, kSmemFMillerS));
+    if (p->type == 'f') CUDA_OK(allow_smem(k_f_miller_p<kPairsFP>, kSmemFMillerP));
     if (p->type == 'f') CUDA_OK(allow_smem(k_f_finalexp_s<kBlockFS>, kSmemFFinalS));
     if (p->type == '1') {
       CUDA_OK(allow_smem(k_a1_miller<kBlockA1>, kSmemA1Miller));
@@ -1081,6 +1100,13 @@ static int enqueue_pairings(pbc_b200_pairing_s* p, const Job& job, uint8_t* d_ou
     }
     if (isf && PBC_F_SLOTS && p->f.slots_ok) {
       uint32_t* gq = mv + (W + 1) * m + (job.mode == kProd ? (W + 1) * n : 0);   // after the Miller values and flags
+      if (PBC_F_PAIR) {
+        k_f_prep<kBlockCC><<<(unsigned)((m + kBlockCC - 1) / kBlockCC), kBlockCC, 0, st>>>(d_in1, d_in2, flag, gq, m, stride1, tab, rows);
+        LAUNCHED();
+        PBC_PAIR_LAUNCH(true);
+        k_f_miller_p<kPairsFP><<<(unsigned)((m + kPairsFP - 1) / kPairsFP), 2 * kPairsFP, kSmemFMillerP, st>>>(mv, flag, gq, m, tab, rows);
+        PBC_PAIR_LAUNCH(false);
+      } else
       k_f_miller_s<kBlockFSM><<<(unsigned)((m + kBlockFSM - 1) / kBlockFSM), kBlockFSM, kSmemFMillerS, st>>>(d_in1, d_in2, mv, flag, gq, m, stride1, tab, rows);
     } else if (isf) k_f_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1, tab, rows);
     else if (isg) k_g_miller<kBlockCCMiller><<<gm, kBlockCCMiller, 0, st>>>(d_in1, d_in2, mv, flag, m, stride1, tab, rows);

@@ -117,12 +117,12 @@ inline void run(const std::vector<Insn>& prog, std::initializer_list<uint32_t*> 
     switch (in.op) {
       case ADD: r = (uint64_t)rd(in.src[0]) + rd(in.src[1]) + cin; if (in.cc) cf = (uint32_t)(r >> 32); break;
       case SUB: r = (uint64_t)rd(in.src[0]) - rd(in.src[1]) - cin; if (in.cc) cf = (uint32_t)((r >> 32) & 1); break;
-      case MUL: { uint64_t m = (uint64_t)rd(in.src[0]) * rd(in.src[1]); r = in.hi ? m >> 32 : (uint32_t)m; if (!in.hi) products()++; break; }
+      case MUL: { uint64_t m = (uint64_t)rd(in.src[0]) * rd(in.src[1]); r = in.hi ? m >> 32 : (uint32_t)m; if (!in.hi) __atomic_fetch_add(&products(), 1, __ATOMIC_RELAXED); break; }
       default: {
         uint64_t m = (uint64_t)rd(in.src[0]) * rd(in.src[1]);
         r = (uint64_t)(in.hi ? (uint32_t)(m >> 32) : (uint32_t)m) + rd(in.src[2]) + cin;
         if (in.cc) cf = (uint32_t)(r >> 32);
-        if (!in.hi) products()++;
+        if (!in.hi) __atomic_fetch_add(&products(), 1, __ATOMIC_RELAXED);
       }
     }
     if (in.dst.idx >= no) { fprintf(stderr, "ptx_emul: write to an input operand\n"); abort(); }

@@ -86,6 +86,27 @@ def test_kernel_variants_give_the_same_bytes(tmp_path):
     assert len(res) >= 38 and all(res.values()), {k: v for k, v in res.items() if not v}
 
 
+def test_type_f_lane_pair_kernels_give_the_same_bytes(tmp_path):
+    """PBC_F_PAIR = 1 (pairing_f_pair.cuh: k_f_prep + k_f_miller_p, two lanes per pairing meeting at __syncwarp; measured on
+    the B200 and kept off, engine.cu says why): the type F / D fixtures and the edge cases through that build.  The simulator
+    runs the two lanes of a pair on two host threads (tests/host/cuda_sim.hpp), so a missing barrier shows up here."""
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    so = _build(tmp_path, "-DPBC_F_PAIR=1")
+    files = [os.path.join(ROOT, "tests", f) for f in ("test_gpu_type_fd.py", "test_gpu_edge_cases.py")]
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider",
+           "-k", "not large_batch and not device_pointer and not tiles and not across_blocks"] + files
+    try:
+        import xdist  # noqa: F401
+        cmd += ["-n", str(max(1, min(8, len(os.sched_getaffinity(0)))))]
+    except Exception:
+        pass
+    out = subprocess.run(cmd, env=_env(so), capture_output=True, text=True, timeout=1500, cwd=ROOT)
+    tail = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-500:]
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert int(tail.split(" passed")[0].split()[-1]) >= 150, tail
+
+
 def test_multiplier_work_counted_by_the_simulator_matches_bench(sim):
     """bench.py's roofline numerator (32x32 products the Miller kernel executes per pairing) against
     the count the PTX interpreter takes while running that kernel"""
