@@ -197,7 +197,19 @@ __device__ __forceinline__ void fqw_sub(FqW& r, const FqW& a, const FqW& b) {
 #endif
 #define PBC_MADW_FIRST(lo, hi, x, y) PBC_ASM("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(x), "r"(y))
 #define PBC_MADW_NEXT(lo, hi, x, y) PBC_ASM("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(x), "r"(y))
+// (lo, hi) = x y.  Written as a multiply-add of zero: ptxas turns mad.lo.cc + madc.hi into ONE IMAD.WIDE.U32, while
+// mul.lo + mul.hi stayed an IMAD + IMAD.HI pair in places.  Clobbers the carry flag (no run is in flight where a
+// row starts).  Worth 0.3 % (profiles/r2_variants_tile.jsonl); the same file has the experiment that tiled the
+// accumulators with nine plain products first to avoid the "(carry word, 0)" top pairs and their zeroing moves:
+// ptxas moved other additions onto the multiplier pipe instead (IMAD.X / IMAD), no gain for F, -3 % for D.
+#ifndef PBC_MULW_MAD
+#define PBC_MULW_MAD 1
+#endif
+#if PBC_MULW_MAD
+#define PBC_MULW_PAIR(lo, hi, x, y) PBC_ASM("mad.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;" : "=r"(lo), "=r"(hi) : "r"(x), "r"(y))
+#else
 #define PBC_MULW_PAIR(lo, hi, x, y) PBC_ASM("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(x), "r"(y))
+#endif
 #define PBC_CARRY_TO(w) PBC_ASM("addc.u32 %0, 0, 0;" : "=r"(w))
 __device__ __forceinline__ void fqw_mul(FqW& t, const Fq& a, const Fq& b) {
   static_assert(kNS == 5, "the row schedule below is written out for five limbs");
