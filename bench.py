@@ -633,7 +633,10 @@ def run_config(G, wname, args, Ph, Qh, n, idx, cpu_out, cpu, steps, warmup, per_
             roof["frac_reference_equivalent"] = ach_ref / peak
             roof["reference_equivalent_is"] = ("the reference algorithm's mulmod count x %d unit ops per mulmod over the same "
                                                "time: above frac because these kernels execute fewer multiplications" % unit)
-        assert frac <= 1.05, "roofline.frac %.3f > 1: the executed-work count or the peak is wrong" % frac
+        # (a run under a profiler times the peak microkernel with the profiler's per-launch overhead in it: the launch-list
+        # recipes set PBC_B200_UNDER_PROFILER=1, and no number printed by such a run is a bench value)
+        assert frac <= 1.05 or os.environ.get("PBC_B200_UNDER_PROFILER"), \
+            "roofline.frac %.3f > 1: the executed-work count or the peak is wrong" % frac
         ws_per = 704 * k if w["param"] == "a" else {"f": (61 + 30 + 240) * 4, "d159": 31 * 4, "g149": 51 * 4, "a1": 6 * 136}[w["param"]]
         rec = {
             "value": value, "unit": unit_name, "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,

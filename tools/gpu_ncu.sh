@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 for spec in $KERNELS; do
   k=${spec%%:*}; rest=${spec#*:}; w=${rest%%:*}; n=${rest#*:}
   rep=/tmp/prof_$k
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -o $rep \
+  PBC_B200_UNDER_PROFILER=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -o $rep \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --workload $w --configs none --n $n > gpurun_out/ncu_$k.out 2>&1; echo "ncu $k rc=$?"
   ncu -i $rep.ncu-rep --page raw --csv > gpurun_out/r2_ncu_${k}_raw.csv 2>/dev/null
   ncu -i $rep.ncu-rep --page details > gpurun_out/r2_ncu_${k}_details.txt 2>/dev/null

@@ -21,6 +21,6 @@ tail -2 gpurun_out/r2_bench_fullparity.err; show gpurun_out/r2_bench_fullparity.
 timeout 300 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/r2_bench_reference.json 2>/dev/null; cut -c1-300 gpurun_out/r2_bench_reference.json
 for w in pp g a1; do timeout 600 python bench.py --steps 5 --warmup 3 --workload $w --configs none > gpurun_out/r2_bench_$w.json 2> gpurun_out/r2_bench_$w.err; echo "bench $w rc=$?"; show gpurun_out/r2_bench_$w.json; done
 timeout 600 python tools/gpu_pp_compare.py a f d g 131072 > gpurun_out/r2_pp_compare.jsonl 2> gpurun_out/r2_pp_compare.err; cut -c1-200 gpurun_out/r2_pp_compare.jsonl
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_ncu_launches_a.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --configs none --n 262144 > gpurun_out/ncu_launches_a.out 2>&1; echo "ncu list a rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_ncu_launches_f.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --workload f --configs none --n 262144 > gpurun_out/ncu_launches_f.out 2>&1; echo "ncu list f rc=$?"
-KERNELS="k_a_miller9:a:227328 k_f_miller_s:f:151552 k_f_finalexp_s:f:151552 k_a_finalexp:a:227328" bash tools/gpu_ncu.sh
+PBC_B200_UNDER_PROFILER=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_ncu_launches_a.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --configs none --n 262144 > gpurun_out/ncu_launches_a.out 2>&1; echo "ncu list a rc=$?"
+PBC_B200_UNDER_PROFILER=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_ncu_launches_f.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --workload f --configs none --n 262144 > gpurun_out/ncu_launches_f.out 2>&1; echo "ncu list f rc=$?"
+KERNELS="${KERNELS:-k_a_miller9:a:227328 k_f_miller_s:f:151552 k_f_finalexp_s:f:151552 k_a_finalexp:a:227328}" bash tools/gpu_ncu.sh

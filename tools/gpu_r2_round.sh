@@ -18,7 +18,7 @@ timeout 600 python tools/gpu_pp_compare.py a f d g 131072 > gpurun_out/r2_pp_com
 for w in pp g a1; do timeout 600 python bench.py --steps 5 --warmup 3 --workload $w --configs none > gpurun_out/r2_bench_$w.json 2> gpurun_out/r2_bench_$w.err; echo "bench $w rc=$?"; python -c "
 import json; d=json.loads([l for l in open('gpurun_out/r2_bench_$w.json') if l.startswith('{')][-1]); print('$w', round(d['value']), 'e2e', round(d['e2e']['value']), 'frac', round(d['roofline']['frac'],3), d['parity'] and (d['parity']['checked'], d['parity']['bit_exact']), {k: round(v,2) for k,v in d['stage_ms'].items()})"; done
 if [ -z "$SKIP_NCU" ]; then
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_ncu_launches_a.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --configs none --n 262144 > gpurun_out/ncu_launches_a.out 2>&1; echo "ncu list a rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_ncu_launches_f.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --workload f --configs none --n 262144 > gpurun_out/ncu_launches_f.out 2>&1; echo "ncu list f rc=$?"
+PBC_B200_UNDER_PROFILER=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_ncu_launches_a.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --configs none --n 262144 > gpurun_out/ncu_launches_a.out 2>&1; echo "ncu list a rc=$?"
+PBC_B200_UNDER_PROFILER=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_ncu_launches_f.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --workload f --configs none --n 262144 > gpurun_out/ncu_launches_f.out 2>&1; echo "ncu list f rc=$?"
 KERNELS="k_a_miller9:a:227328 k_f_miller_s:f:151552 k_f_finalexp_s:f:151552" bash tools/gpu_ncu.sh
 fi
