@@ -795,7 +795,10 @@ static constexpr int kBlockFS = 128;
 #ifndef PBC_F_PAIR
 #define PBC_F_PAIR 0
 #endif
-static constexpr int kPairsFP = 128;             // pairings per block (256 threads)
+#ifndef PBC_FP_PAIRS
+#define PBC_FP_PAIRS 128
+#endif
+static constexpr int kPairsFP = PBC_FP_PAIRS;    // pairings per block (twice as many threads)
 static constexpr size_t kSmemFMillerP = (size_t)kFPSlots * kNS * 4 * kPairsFP;
 // the CPU simulator (tests/host) runs the two lanes of a pair on two host threads when told to
 #ifdef PBC_HOST_SIM

@@ -252,7 +252,7 @@ k_f_prep(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint32_t*
 
 // The Miller loop proper: block = 2 BP threads, lanes (2j, 2j+1) share pairing blockIdx.x * BP + j.
 template <int BP>
-__global__ void __launch_bounds__(2 * BP, 2)
+__global__ void __launch_bounds__(2 * BP, 256 / BP)
 k_f_miller_p(uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ gq, size_t n,
              const uint32_t* __restrict__ tab, size_t rows) {
   using S = FP<BP>;
