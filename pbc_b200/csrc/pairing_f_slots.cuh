@@ -200,6 +200,29 @@ struct FS {
   // the point arithmetic of a Miller step has them in independent pairs and triples, and two warps per
   // scheduler do not hide a chain's latency (ncu: the F_q routines took 17 % of the samples for 11 % of
   // the instructions).
+  // PBC_FS_ONE_QMUL = 1: the grouped calls below run their products one after the other through qmul / qsqr (one copy
+  // of the multiplier in the loop body instead of nine: 25 KB less code to fetch per iteration; an A/B experiment)
+#ifndef PBC_FS_ONE_QMUL
+#define PBC_FS_ONE_QMUL 0
+#endif
+#if PBC_FS_ONE_QMUL
+  static __device__ __forceinline__ void qmul2(int d0, int a0, int b0, int d1, int a1, int b1) {
+    Fq x0, x1;                                    // every operand is read before any result is stored
+    ld(x0, a1); ld(x1, b1);
+    qmul(d0, a0, b0);
+    qmul_r(d1, x0, x1);
+  }
+  static __device__ __noinline__ void qmul_r(int d, Fq x, Fq y) { fq_mul_sel(x, x, y); st(d, x); }
+  static __device__ __forceinline__ void qmul3(int d0, int a0, int b0, int d1, int a1, int b1, int d2, int a2, int b2) {
+    Fq x1, y1, x2, y2;
+    ld(x1, a1); ld(y1, b1); ld(x2, a2); ld(y2, b2);
+    qmul(d0, a0, b0);
+    qmul_r(d1, x1, y1);
+    qmul_r(d2, x2, y2);
+  }
+  static __device__ __forceinline__ void qsqr3(int d0, int a0, int d1, int a1, int d2, int a2) { qmul3(d0, a0, a0, d1, a1, a1, d2, a2, a2); }
+  static __device__ __forceinline__ void qmul1sqr2(int d0, int a0, int b0, int d1, int a1, int d2, int a2) { qmul3(d0, a0, b0, d1, a1, a1, d2, a2, a2); }
+#else
   static __device__ __noinline__ void qmul2(int d0, int a0, int b0, int d1, int a1, int b1) {
     Fq x0, y0, x1, y1;
     ld(x0, a0); ld(y0, b0); ld(x1, a1); ld(y1, b1);
@@ -232,6 +255,7 @@ struct FS {
     fq_sqr_sel(x2, x2);
     st(d0, x0); st(d1, x1); st(d2, x2);
   }
+#endif
   static __device__ __noinline__ void qadd(int d, int a, int b) { Fq x, y; ld(x, a); ld(y, b); fq_add(x, x, y); st(d, x); }
   static __device__ __noinline__ void qsub(int d, int a, int b) { Fq x, y; ld(x, a); ld(y, b); fq_sub(x, x, y); st(d, x); }
   static __device__ __noinline__ void qdbl(int d, int a, int k = 1) {
