@@ -550,19 +550,19 @@ __device__ __forceinline__ void fqw_redc_os(Fq& r, const FqW& t) {
   for (int k = 1; k < kNS; k++) PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(d[k]) : "r"(o[k]), "r"(q[k]));
   PBC_ASM("subc.u32 %0, 0, 0;" : "=r"(borrow));
   bool use_d = v0 != 0 || borrow == 0;
-  if (!TWO) {
+  if constexpr (!TWO) {
 #pragma unroll
     for (int k = 0; k < kNS; k++) r.v[k] = use_d ? d[k] : o[k];
-    return;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kNS; k++) o[k] = use_d ? d[k] : o[k];
+    PBC_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(d[0]) : "r"(o[0]), "r"(q[0]));
+#pragma unroll
+    for (int k = 1; k < kNS; k++) PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(d[k]) : "r"(o[k]), "r"(q[k]));
+    PBC_ASM("subc.u32 %0, 0, 0;" : "=r"(borrow));
+#pragma unroll
+    for (int k = 0; k < kNS; k++) r.v[k] = borrow == 0 ? d[k] : o[k];
   }
-#pragma unroll
-  for (int k = 0; k < kNS; k++) o[k] = use_d ? d[k] : o[k];
-  PBC_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(d[0]) : "r"(o[0]), "r"(q[0]));
-#pragma unroll
-  for (int k = 1; k < kNS; k++) PBC_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(d[k]) : "r"(o[k]), "r"(q[k]));
-  PBC_ASM("subc.u32 %0, 0, 0;" : "=r"(borrow));
-#pragma unroll
-  for (int k = 0; k < kNS; k++) r.v[k] = borrow == 0 ? d[k] : o[k];
 }
 // r = a b, one product with the row-wise reduction
 __device__ __forceinline__ void fq_mul_os(Fq& r, const Fq& a, const Fq& b) {
