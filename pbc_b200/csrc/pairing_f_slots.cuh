@@ -171,6 +171,9 @@ __device__ __forceinline__ void gs_combine(Fq& c, const Fq& r) {
 // ---- the slot machine ----
 template <int BLOCK>
 struct FS {
+  // PBC_FS_LOCKSTEP >= 2: a block-wide barrier before every big routine as well (F_q^6 products, line product), not only
+  // at the top of an iteration
+  static __device__ __forceinline__ void step_barrier() { if (PBC_FS_LOCKSTEP >= 2) __syncthreads(); }
   static __device__ __forceinline__ uint32_t* base() { return reinterpret_cast<uint32_t*>(pbc_smem) + threadIdx.x; }
   static __device__ __forceinline__ void ld(Fq& r, int s) {
     const uint32_t* b = base() + s * (kNS * BLOCK);
@@ -373,6 +376,7 @@ struct FS {
     f2mulxi(xs + 2, b + 4);
 #pragma unroll 1
     for (int k = 0; k < 3; k++) {
+      if (PBC_FS_LOCKSTEP >= 3) __syncthreads();
       F2Acc g;
       Fq x0, x1, y0, y1;
       ld(x0, a); ld(x1, a + 1); ld(y0, b + 2 * k); ld(y1, b + 2 * k + 1);      // a_0 b_k
@@ -417,6 +421,7 @@ struct FS {
 #pragma unroll 1
     for (int k = 0; k < 6; k++) {
       const int i3 = k >= 3 ? k - 3 : k + 3, i4 = k >= 4 ? k - 4 : k + 2;
+      if (PBC_FS_LOCKSTEP >= 3) __syncthreads();
 #if PBC_FQ_ACC
       // re = A - B + c y0,  im = C - A - B + c y1:  c y0 joins A and c (y0 + y1) joins C
       F2Acc g;
@@ -464,9 +469,11 @@ struct FS {
   // v <- v^2 in place with the 12-slot scratch t (f12_sqr: complex squaring over F_q^6).
   //   A = v[0..5], B = v[6..11];  t0 = A B;  t1 = (A + B)(A + y B);  A' = t1 - t0 - y t0,  B' = 2 t0
   static __device__ __forceinline__ void f12sqr(int v, int t, int xs) {
+    step_barrier();
     f6mul(t, v, v + 6, xs);                                    // t0
     f2add(t + 6, v, v + 6); f2add(t + 8, v + 2, v + 8); f2add(t + 10, v + 4, v + 10);        // A + B
     f2addxi(v, v, v + 10); f2add(v + 2, v + 2, v + 6); f2add(v + 4, v + 4, v + 8);           // A + y B, in place
+    step_barrier();
     f6mul(v + 6, t + 6, v, xs);                                // t1 over B (B is dead)
     f2sub(v, v + 6, t); f2subxi(v, v, t + 4);                  // A'0 = t1_0 - t0_0 - xi t0_2
     f2sub(v + 2, v + 8, t + 2); f2sub(v + 2, v + 2, t);        // A'1 = t1_1 - t0_1 - t0_0
@@ -476,10 +483,13 @@ struct FS {
   // p <- p q with the 12-slot scratch t (f12_mul: Karatsuba over F_q^6); q is left as it was.
   //   p = A + B x, q = C + D x:  t0 = A C, t1 = B D, t2 = (A + B)(C + D);  lo = t0 + y t1, hi = t2 - t0 - t1
   static __device__ __forceinline__ void f12mul(int p, int q, int t, int xs) {
+    step_barrier();
     f6mul(t, p, q, xs);                                        // t0
+    step_barrier();
     f6mul(t + 6, p + 6, q + 6, xs);                            // t1
     f2add(p, p, p + 6); f2add(p + 2, p + 2, p + 8); f2add(p + 4, p + 4, p + 10);     // A + B over A
     f2add(q, q, q + 6); f2add(q + 2, q + 2, q + 8); f2add(q + 4, q + 4, q + 10);     // C + D over C
+    step_barrier();
     f6mul(p + 6, p, q, xs);                                    // t2 over B
     f2sub(q, q, q + 6); f2sub(q + 2, q + 2, q + 8); f2sub(q + 4, q + 4, q + 10);     // C back
     f2sub(p + 6, p + 6, t); f2sub(p + 6, p + 6, t + 6);
@@ -700,6 +710,7 @@ k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint3
       S::qsub(T + 5, T + 5, fsX); S::qmul(fsY, T + 1, T + 5); S::qsub(fsY, fsY, T + 2);   // Y'
     }
     }
+    S::step_barrier();
     S::line_mul(T, V);
     { int s = V; V = T; T = s; }
     if (m == 0) break;
@@ -740,6 +751,7 @@ k_f_miller_s(const uint8_t* __restrict__ P, const uint8_t* __restrict__ Q, uint3
       S::qmul2(T, T, T + 3, T + 1, T + 1, fsY);                          // R (X H^2 - X3), H^3 Y
       S::qsub(fsY, T, T + 1);                                            // Y3
       }
+      S::step_barrier();
       S::line_mul(T, V);
       { int s = V; V = T; T = s; }
     }
