@@ -790,8 +790,9 @@ static constexpr int kBlockFS = 128;
 // Bit-exact (simulator test + GPU fixtures) and measured: 55.9 ms against 55.3 ms for k_f_miller_s on 378 880 pairings
 // (profiles/r2_variants_pair.jsonl).  Sixteen resident warps instead of eight change nothing: ncu shows the same
 // 62.7 % multiplier-pipe activity with math_pipe_throttle 1.14 and dispatch_stall 0.80 per issue
-// (profiles/r2_ncu_k_f_miller_p_v1.json) -- the five-limb instruction mix saturates the pipe's issue path, not the
-// warps' latency.  Kept off; the path to more speed is fewer multiplier-pipe instructions per pairing.
+// (profiles/r2_ncu_k_f_miller_p_v1.json): latency is not what holds the slot kernel back.  What holds the pair kernel
+// at 0.184 multiplier-pipe instructions per cycle per scheduler (k_d_miller reaches 0.227) was not isolated -- DESIGN.md 3.3
+// lists the candidates.  Kept off.
 #ifndef PBC_F_PAIR
 #define PBC_F_PAIR 0
 #endif
