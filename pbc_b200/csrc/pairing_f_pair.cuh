@@ -25,22 +25,54 @@
 namespace pbcb200 {
 
 // 44 slots = 880 B per pairing (two 128-pairing blocks per SM): the 36 of k_f_miller_s + 8 of scratch.  During
-// the F_q^12 squaring the line's nine slots are dead, so slots 27..42 are its scratch: A + yB (6), the second
+// the F_q^12 squaring the line's slots are dead, so slots 28..43 are its scratch: A + yB (6), the second
 // product (6), xi B_2 and xi (A + yB)_2 (2 + 2).
 constexpr int kFPSlots = 44;
-constexpr int fpScratch = fsC;        // 27
+// Slot map of the pair kernel (0..26 as k_f_miller_s: value, scratch area, X, Y, Z).  The line's slots are laid
+// out so that the 16 scratch slots of the squaring are 28..43 and so that the bank rule below works out:
+//   27 c | 28..33: L3, L4, (2 spare) | 34..39: xi L3, xi L4, (2 spare) | 40, 41 | 42, 43
+//   squaring scratch:  28..33 = A + yB,  34..39 = the second product,  40, 41 = xi B_2,  42, 43 = xi (A + yB)_2
+enum FPSlotMap { fpC = 27, fpL3 = 28, fpL4 = 30, fpXL3 = 34, fpXL4 = 36, fpScratch = 28 };
+// PBC_FP_SWIZZLE = 1: word w of slot s of pairing p lives at row (s * 5 + w), column p ^ (16 sigma(s)).  Two lanes of
+// a pair that read different slots in the same instruction would otherwise hit the same 16 banks with two addresses each
+// (rows are 128 words apart; ncu: 1.2 G two-way conflicts per launch).  sigma(s) = (s & 1) ^ alpha(s), alpha = 0 on the
+// low halves of the two 12-slot areas and on 28..33, 40, 41; 1 on the high halves and on 34..39, 42, 43: every pair of
+// slots the big routines touch together (real / imaginary coordinate; A and the second area's high half; B and A + yB;
+// L and xi L; coefficient k and k + 3 of the line product; the two products' outputs) then differs in sigma.
+// Measured (profiles/r2_variants_pairsw.jsonl): 57.5 ms with the swizzle against 55.8 ms without -- the conflicts are
+// not what holds this kernel back and the extra address arithmetic costs more than they do.  Off; the simulator test
+// builds it on.
+#ifndef PBC_FP_SWIZZLE
+#define PBC_FP_SWIZZLE 0
+#endif
+constexpr uint64_t fp_sigma_mask() {
+  uint64_t m = 0;
+  for (int s = 0; s < kFPSlots; s++) {
+    int alpha = 0;
+    if (s < 24) alpha = (s % 12) >= 6;
+    else if (s >= 34 && s <= 39) alpha = 1;
+    else if (s >= 42) alpha = 1;
+    if (((s & 1) ^ alpha) != 0) m |= (uint64_t)1 << s;
+  }
+  return m;
+}
+constexpr uint64_t kFPSigma = fp_sigma_mask();
 
 template <int BP>                     // pairings per block; the block has 2 BP threads
 struct FP {
   static __device__ __forceinline__ int half() { return (int)(threadIdx.x & 1u); }
-  static __device__ __forceinline__ uint32_t* base() { return reinterpret_cast<uint32_t*>(pbc_smem) + (threadIdx.x >> 1); }
+  static __device__ __forceinline__ uint32_t* base(int s) {
+    uint32_t col = threadIdx.x >> 1;
+    if (PBC_FP_SWIZZLE) col ^= (uint32_t)((kFPSigma >> s) & 1u) << 4;
+    return reinterpret_cast<uint32_t*>(pbc_smem) + col;
+  }
   static __device__ __forceinline__ void ld(Fq& r, int s) {
-    const uint32_t* b = base() + s * (kNS * BP);
+    const uint32_t* b = base(s) + s * (kNS * BP);
 #pragma unroll
     for (int k = 0; k < kNS; k++) r.v[k] = b[k * BP];
   }
   static __device__ __forceinline__ void st(int s, const Fq& r) {
-    uint32_t* b = base() + s * (kNS * BP);
+    uint32_t* b = base(s) + s * (kNS * BP);
 #pragma unroll
     for (int k = 0; k < kNS; k++) b[k * BP] = r.v[k];
   }
@@ -175,14 +207,14 @@ struct FP {
       const int i3 = k >= 3 ? k - 3 : k + 3, i4 = k >= 4 ? k - 4 : k + 2;
       F2Acc g;
       Fq x0, x1, y0, y1;
-      const int m3 = k >= 3 ? fsL3 : fsXL3, m4 = k >= 4 ? fsL4 : fsXL4;
+      const int m3 = k >= 3 ? fpL3 : fpXL3, m4 = k >= 4 ? fpL4 : fpXL4;
       ld(x0, m3); ld(x1, m3 + 1);
       ld(y0, v + 2 * f12_pos(i3)); ld(y1, v + 2 * f12_pos(i3) + 1);
       f2a_term<0>(g, x0, x1, y0, y1);
       ld(x0, m4); ld(x1, m4 + 1);
       ld(y0, v + 2 * f12_pos(i4)); ld(y1, v + 2 * f12_pos(i4) + 1);
       f2a_term<1>(g, x0, x1, y0, y1);
-      ld(x0, fsC);
+      ld(x0, fpC);
       ld(y0, v + 2 * f12_pos(k)); ld(y1, v + 2 * f12_pos(k) + 1);
       fq_add_nr(x1, y0, y1);
       fqa_mac<false>(g.A, x0, y0);
@@ -278,10 +310,10 @@ k_f_miller_p(uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag, const
     if (PBC_FS_LOCKSTEP) __syncthreads();
     if (tab) {
       // ---- fixed first argument: (a, b, c) of the next line from the table ----
-      S::qldc(T + 4, tab + (3 * row + 0) * kNS); S::f2scale_g(fsL4, g, 0, n, T + 4);
-      S::qldc(T + 4, tab + (3 * row + 1) * kNS); S::f2scale_g(fsL3, g, 2, n, T + 4);
-      S::qldc(fsC, tab + (3 * row + 2) * kNS);
-      S::f2mulxi(fsXL3, fsL3); S::f2mulxi(fsXL4, fsL4);
+      S::qldc(T + 4, tab + (3 * row + 0) * kNS); S::f2scale_g(fpL4, g, 0, n, T + 4);
+      S::qldc(T + 4, tab + (3 * row + 1) * kNS); S::f2scale_g(fpL3, g, 2, n, T + 4);
+      S::qldc(fpC, tab + (3 * row + 2) * kNS);
+      S::f2mulxi(fpXL3, fpL3); S::f2mulxi(fpXL4, fpL4);
       row++;
     } else {
       // ---- tangent at V (a = -M Z^2, b = 2 Y Z^3, c = M X - 2 Y^2; the curve has A = 0), V <- 2V ----
@@ -290,14 +322,14 @@ k_f_miller_p(uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag, const
       S::qmulh(T, fsZ, fsZ, T + 5, fsX, fsX);                             // Z^2, X^2
       S::qmulh(T + 2, fsY, fsY, T + 3, fsY, fsZ);                         // Y^2, Y Z
       S::qdbl(T + 1, T + 5); S::qadd(T + 1, T + 1, T + 5);                // M = 3 X^2
-      S::qmulh(T + 4, T + 1, T, fsC, T + 1, fsX);                         // M Z^2, M X
+      S::qmulh(T + 4, T + 1, T, fpC, T + 1, fsX);                         // M Z^2, M X
       S::qneg(T + 4, T + 4);                                              // a
-      S::f2scale_g(fsL4, g, 0, n, T + 4);                                 // L4 = Qx a
+      S::f2scale_g(fpL4, g, 0, n, T + 4);                                 // L4 = Qx a
       S::qdbl(T + 3, T + 3);                                              // Z' = 2 Y Z
       S::qmulh(T + 4, T + 3, T, T + 5, fsX, T + 2);                       // b = Z' Z^2, X Y^2
-      S::f2scale_g(fsL3, g, 2, n, T + 4);                                 // L3 = Qy b
-      S::qsub(fsC, fsC, T + 2); S::qsub(fsC, fsC, T + 2);                 // c = M X - 2 Y^2
-      S::f2mulxi(fsXL3, fsL3); S::f2mulxi(fsXL4, fsL4);
+      S::f2scale_g(fpL3, g, 2, n, T + 4);                                 // L3 = Qy b
+      S::qsub(fpC, fpC, T + 2); S::qsub(fpC, fpC, T + 2);                 // c = M X - 2 Y^2
+      S::f2mulxi(fpXL3, fpL3); S::f2mulxi(fpXL4, fpL4);
       S::qcopy(fsZ, T + 3);
       S::qmulh(fsX, T + 1, T + 1, T + 2, T + 2, T + 2);                   // M^2, Y^4
       S::qdbl(T + 5, T + 5, 2);                                           // S = 4 X Y^2
@@ -318,10 +350,10 @@ k_f_miller_p(uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag, const
       const bool minus = false;
 #endif
       if (tab) {
-        S::qldc(T + 4, tab + (3 * row + 0) * kNS); S::f2scale_g(fsL4, g, 0, n, T + 4);
-        S::qldc(T + 4, tab + (3 * row + 1) * kNS); S::f2scale_g(fsL3, g, 2, n, T + 4);
-        S::qldc(fsC, tab + (3 * row + 2) * kNS);
-        S::f2mulxi(fsXL3, fsL3); S::f2mulxi(fsXL4, fsL4);
+        S::qldc(T + 4, tab + (3 * row + 0) * kNS); S::f2scale_g(fpL4, g, 0, n, T + 4);
+        S::qldc(T + 4, tab + (3 * row + 1) * kNS); S::f2scale_g(fpL3, g, 2, n, T + 4);
+        S::qldc(fpC, tab + (3 * row + 2) * kNS);
+        S::f2mulxi(fpXL3, fpL3); S::f2mulxi(fpXL4, fpL4);
         row++;
       } else {
         // ---- chord through V and +-P (a = Y - yS Z^3, b = (xP Z^2 - X) Z, c = yS Z X - xP Y), V <- V +- P ----
@@ -333,11 +365,11 @@ k_f_miller_p(uint32_t* __restrict__ mv, const uint32_t* __restrict__ flag, const
         S::qsub(T + 2, T + 2, fsX);                                        // H = xP Z^2 - X
         S::qmulh(T + 3, T + 7, T + 1, T + 4, T + 2, fsZ);                  // yS Z^3, b = H Z
         S::qsub(T + 5, fsY, T + 3);                                        // a = Y - yS Z^3
-        S::f2scale_g(fsL4, g, 0, n, T + 5);
+        S::f2scale_g(fpL4, g, 0, n, T + 5);
         S::qsub(T + 3, T + 3, fsY);                                        // R = yS Z^3 - Y
-        S::f2scale_g(fsL3, g, 2, n, T + 4);
-        S::qsub(fsC, T + 8, T + 9);                                        // c
-        S::f2mulxi(fsXL3, fsL3); S::f2mulxi(fsXL4, fsL4);
+        S::f2scale_g(fpL3, g, 2, n, T + 4);
+        S::qsub(fpC, T + 8, T + 9);                                        // c
+        S::f2mulxi(fpXL3, fpL3); S::f2mulxi(fpXL4, fpL4);
         S::qcopy(fsZ, T + 4);                                              // Z of the sum
         S::qmulh(T, T + 2, T + 2, T + 10, T + 3, T + 3);                   // H^2, R^2
         S::qmulh(T + 1, T, T + 2, T, T, fsX);                              // H^3, X H^2

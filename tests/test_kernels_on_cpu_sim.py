@@ -95,7 +95,7 @@ def test_type_f_lane_pair_kernels_give_the_same_bytes(tmp_path):
     runs the two lanes of a pair on two host threads (tests/host/cuda_sim.hpp), so a missing barrier shows up here."""
     if not shutil.which("g++"):
         pytest.skip("no g++")
-    so = _build(tmp_path, "-DPBC_F_PAIR=1")
+    so = _build(tmp_path, "-DPBC_F_PAIR=1", "-DPBC_FP_SWIZZLE=1")     # with the bank swizzle of the slots (measured, off by default)
     files = [os.path.join(ROOT, "tests", f) for f in ("test_gpu_type_fd.py", "test_gpu_edge_cases.py")]
     cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider",
            "-k", "not large_batch and not device_pointer and not tiles and not across_blocks"] + files
